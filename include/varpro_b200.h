@@ -1,0 +1,217 @@
+/*
+ * varpro_b200.h -- C ABI of the B200-native variable-projection engine.
+ *
+ * This is the drop-in boundary for the hot path of geo-ant/varpro v0.13.3
+ * (file:line below are relative to the reference repository):
+ *
+ *   per LM iteration:  Phi(alpha) / dPhi evaluation  ->  inner linear LSQ for
+ *   many right-hand sides  ->  Kaufman Jacobian  ->  Levenberg-Marquardt step
+ *
+ * i.e. `impl LeastSquaresProblem for SeparableProblem`
+ * (src/solvers/levmar/mod.rs:22-202), the state in `SeparableProblem` /
+ * `CachedCalculations` (src/problem.rs:57-107), basis-function evaluation
+ * (src/model/mod.rs:441-512) and the external `levenberg-marquardt` loop
+ * called at src/solvers/levmar/mod.rs:247.
+ *
+ * The reference has no FFI; INTEGRATION.md shows the Rust `extern "C"` block a
+ * maintainer adds to bind these symbols behind the unchanged trait surface.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a
+ * vp_status (0 = ok); no exceptions cross the ABI; the library owns all device
+ * memory and streams; one handle is used by one host thread at a time (mirrors
+ * `&mut self`). All matrices are COLUMN-MAJOR like nalgebra's. Host pointers
+ * unless the name says `_device`.
+ *
+ * There is NO CPU fallback: every entry point that computes needs a CUDA
+ * device and fails with VP_ERR_CUDA otherwise.
+ */
+#ifndef VARPRO_B200_H
+#define VARPRO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_ABI_VERSION 1
+#define VP_MAX_BASIS_PARAMS 4 /* parameters one basis function may depend on */
+#define VP_MAX_N 8            /* basis functions (linear coefficients) */
+#define VP_MAX_Q 8            /* nonlinear parameters */
+#define VP_MAX_P 12           /* non-zero columns over all dPhi/dalpha_k */
+
+typedef enum {
+    VP_OK = 0,
+    /* SeparableProblemBuilderError (src/problem/builder.rs:15-46) */
+    VP_ERR_Y_DATA_MISSING = 1,
+    VP_ERR_INVALID_LENGTH_OF_DATA = 2,
+    VP_ERR_ZERO_LENGTH_VECTOR = 3,
+    VP_ERR_INVALID_PARAMETER_COUNT = 4,
+    VP_ERR_INVALID_LENGTH_OF_WEIGHTS = 5,
+    /* ModelError / ModelBuildError (src/model/errors.rs:5-42, src/model/builder/error.rs) */
+    VP_ERR_PARAMETER_NOT_IN_MODEL = 10,
+    VP_ERR_DERIVATIVE_INDEX_OUT_OF_BOUNDS = 11,
+    VP_ERR_INCORRECT_PARAMETER_COUNT = 12,
+    VP_ERR_EMPTY_MODEL = 13,          /* ModelBuildError::EmptyModel: no basis function */
+    VP_ERR_UNUSED_PARAMETER = 14,     /* ModelBuildError::UnusedParameter */
+    VP_ERR_UNSUPPORTED_BASIS = 15,
+    VP_ERR_MODEL_TOO_LARGE = 16,      /* exceeds VP_MAX_N / VP_MAX_Q / VP_MAX_P */
+    /* cache is None (src/solvers/levmar/mod.rs:43-45,70-72): evaluation failed */
+    VP_ERR_NO_CACHED_CALCULATION = 20,
+    /* FitStatistics errors (src/statistics/mod.rs) */
+    VP_ERR_UNDERDETERMINED = 30,
+    VP_ERR_MATRIX_INVERSION = 31,
+    /* library */
+    VP_ERR_INVALID_ARGUMENT = 40,
+    VP_ERR_CUDA = 41,
+    VP_ERR_OUT_OF_MEMORY = 42,
+    VP_ERR_COMM = 43
+} vp_status;
+
+typedef enum { VP_F64 = 0, VP_F32 = 1 } vp_dtype;
+
+/* Built-in basis-function kinds evaluated on the device.
+ * The reference's basis functions are boxed CPU closures
+ * (src/model/model_basis_function.rs:11-12) which a kernel cannot call; models
+ * are therefore described by a table of these kinds plus the parameter-index
+ * map the reference builds in create_index_mapping (src/model/detail.rs:60-78). */
+typedef enum {
+    VP_BASIS_EXP_DECAY = 0,    /* exp(-x/tau); d/dtau = exp(-x/tau)*x/tau^2
+                                  shared_test_code/src/lib.rs:101-114            */
+    VP_BASIS_CONSTANT = 1,     /* 1 (invariant)  shared_test_code/src/lib.rs:123 */
+    VP_BASIS_EXP_RATE_COS = 2, /* exp(-a x)cos(b x), params (a,b)
+                                  shared_test_code/src/models.rs:321-322,362-385 */
+    VP_BASIS_SIN_PHASE = 3,    /* sin(omega x + phi), params (omega,phi)
+                                  src/test_helpers/mod.rs:27-51                  */
+    VP_BASIS_LINEAR_X = 4      /* scale*x (invariant) src/model/builder/test.rs:97,101 */
+} vp_basis_kind;
+
+typedef struct {
+    int32_t kind;                           /* vp_basis_kind */
+    int32_t n_params;                       /* 0..VP_MAX_BASIS_PARAMS */
+    int32_t param_idx[VP_MAX_BASIS_PARAMS]; /* index of each function parameter in alpha */
+    double scale;                           /* VP_BASIS_LINEAR_X only */
+} vp_basis_desc;
+
+/* TerminationReason of levenberg-marquardt 0.14. */
+typedef enum {
+    VP_TERM_USER = 0,
+    VP_TERM_NUMERICAL = 1,
+    VP_TERM_RESIDUALS_ZERO = 2,
+    VP_TERM_ORTHOGONAL = 3,
+    VP_TERM_CONVERGED_FTOL = 4,
+    VP_TERM_CONVERGED_XTOL = 5,
+    VP_TERM_CONVERGED_FTOL_XTOL = 6,
+    VP_TERM_NO_IMPROVEMENT_POSSIBLE = 7,
+    VP_TERM_LOST_PATIENCE = 8,
+    VP_TERM_NO_PARAMETERS = 9,
+    VP_TERM_NO_RESIDUALS = 10,
+    VP_TERM_WRONG_DIMENSIONS = 11
+} vp_termination;
+
+/* LevenbergMarquardt::new().with_*() knobs (src/solvers/levmar/mod.rs:221).
+ * A value <= 0 (scale_diag < 0) selects the crate default: ftol = xtol = gtol =
+ * 30*eps(dtype), stepbound = 100, patience = 100 (maxfev = patience*(q+1)),
+ * scale_diag = true. */
+typedef struct {
+    double ftol, xtol, gtol;
+    double stepbound;
+    int32_t patience;
+    int32_t scale_diag;
+} vp_lm_options;
+
+/* MinimizationReport (src/fit.rs:28) */
+typedef struct {
+    int32_t termination;           /* vp_termination */
+    int32_t number_of_evaluations; /* residual evaluations, as MINPACK counts nfev */
+    double objective_function;     /* 0.5*||r_w||^2 */
+    int32_t successful;            /* ResidualsZero | Orthogonal | Converged* */
+    int32_t reserved;
+} vp_fit_report;
+
+/* Everything the LM step needs from one evaluation: these are
+ * functions of the reference's residuals() and jacobian() outputs:
+ * rnorm2 = ||vec(R)||^2, g = J^T r, H = J^T J (q x q, column-major). */
+typedef struct {
+    double rnorm2;
+    double g[VP_MAX_Q];
+    double H[VP_MAX_Q * VP_MAX_Q];
+    int32_t finite; /* 0 if Phi/dPhi or the sums were not finite */
+    int32_t q;
+} vp_reduced;
+
+typedef struct vp_ctx vp_ctx;
+typedef struct vp_model vp_model;
+typedef struct vp_problem vp_problem;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int vp_abi_version(void);
+const char *vp_status_string(int status);
+int vp_ctx_create(int device_ordinal, vp_ctx **out);
+int vp_ctx_destroy(vp_ctx *ctx);
+/* text of the last error raised through this context (never NULL) */
+const char *vp_last_error(const vp_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t vp_ctx_kernel_launches(const vp_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
+void *vp_ctx_stream(const vp_ctx *ctx);
+
+/* ---- model: replaces SeparableModel / SeparableNonlinearModel evaluation --
+ * (src/model/mod.rs:239-363 trait, :441-512 eval / eval_partial_deriv).
+ * x_host: m values of the independent variable in `dtype`. alpha has q entries;
+ * every parameter must be used by some basis function
+ * (src/model/builder/mod.rs:547-557) and n >= 1 (:538). */
+int vp_model_create(vp_ctx *ctx, int dtype, int64_t m, const void *x_host, int32_t q, int32_t n,
+                    const vp_basis_desc *basis, vp_model **out);
+int vp_model_destroy(vp_model *model);
+
+/* ---- problem: replaces SeparableProblemBuilder::build + SeparableProblem ---
+ * (src/problem/builder.rs:278-324, src/problem.rs:57-107).
+ * Y_host: m x S column-major with leading dimension ldY >= m, in the model's
+ * dtype. w_host: m weights or NULL for unit weights. svd_eps: |eps| is used;
+ * pass a negative value for the default (machine epsilon of dtype,
+ * builder.rs:282). alpha0: q initial parameters (f64). Copies Y to the device,
+ * forms Y_w = W*Y once (:307) and runs the first evaluation (:321). */
+int vp_problem_create(vp_ctx *ctx, vp_model *model, int64_t S, const void *Y_host, int64_t ldY,
+                      const void *w_host, double svd_eps, const double *alpha0, vp_problem **out);
+/* Same, but Y is already resident in HBM (device pointer, same layout). The
+ * data is copied into the library's own buffer (device-to-device). */
+int vp_problem_create_device(vp_ctx *ctx, vp_model *model, int64_t S, const void *Y_device,
+                             int64_t ldY, const void *w_host, double svd_eps, const double *alpha0,
+                             vp_problem **out);
+int vp_problem_destroy(vp_problem *problem);
+
+/* ---- trait-mirroring entry points (LeastSquaresProblem) ------------------- */
+/* set_params: src/solvers/levmar/mod.rs:42-73 */
+int vp_set_params(vp_problem *problem, const double *alpha);
+/* params: :80-82 */
+int vp_params(const vp_problem *problem, double *alpha_out);
+/* residuals: :91-95 -> vec(R_w), m*S values in dtype, RHS-major (row = s*m+i) */
+int vp_residuals(vp_problem *problem, void *out_host);
+/* jacobian: :101-201 -> (m*S) x q column-major in dtype (Kaufman approximation) */
+int vp_jacobian(vp_problem *problem, void *out_host);
+/* SeparableProblem::linear_coefficients (src/problem.rs:142-150): n x S in dtype */
+int vp_linear_coefficients(vp_problem *problem, void *out_host);
+/* FitResult::best_fit (src/fit.rs:55-59): Phi(alpha)*C with the unweighted Phi, m x S */
+int vp_best_fit(vp_problem *problem, void *out_host);
+/* ||r||^2, J^T r and J^T J of the current parameters without materialising r or J */
+int vp_reduce(vp_problem *problem, vp_reduced *out);
+
+/* ---- solve: replaces LevMarSolver::fit (src/solvers/levmar/mod.rs:238-254) */
+int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *report);
+
+/* ---- diagnostics ---------------------------------------------------------
+ * Device time (CUDA events on the context's stream, microseconds, averaged over
+ * `iters`) of the two kernels of one evaluation at the current parameters:
+ * the panel kernel (K1) and the Y-streaming reduce (K2). If flush_bytes > 0 a
+ * scratch buffer of that size is overwritten before every iteration so that
+ * the observations are read from HBM, not from L2. Also reports K2's grid size
+ * and dynamic shared memory. */
+int vp_profile_evaluation(vp_problem *problem, int iters, int64_t flush_bytes, double *panel_us,
+                          double *stream_us, int64_t *stream_grid, int64_t *stream_smem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VARPRO_B200_H */

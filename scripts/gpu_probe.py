@@ -1,0 +1,45 @@
+"""Quick GPU probe: C2 evaluation timings (host-driven), fit timing, per-kernel event times."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import workloads as W  # noqa: E402
+import varpro_b200 as vb  # noqa: E402
+from varpro_b200 import _lib  # noqa: E402
+
+
+def prof(gp, iters=20, flush=0):
+    p, s = C.c_double(), C.c_double()
+    g, sm = C.c_int64(), C.c_int64()
+    st = _lib.load().vp_profile_evaluation(gp._h, iters, flush, C.byref(p), C.byref(s), C.byref(g), C.byref(sm))
+    assert st == 0, st
+    return p.value, s.value, g.value, sm.value
+
+
+S = int(os.environ.get("S", 4096))
+wl = W.c2(S=S)
+t0 = time.time()
+gp = W.make_gpu_problem(wl)
+print("create: %.1f ms" % (1e3 * (time.time() - t0)))
+bytes_eval = 8 * 1024 * S
+for flush in (0, 256 << 20):
+    prof(gp, 3, flush)
+    p, s, g, sm = prof(gp, 20, flush)
+    print(f"flush={flush>>20}MB panel {p:.2f} us  stream {s:.2f} us  grid {g} smem {sm}  "
+          f"=> {bytes_eval / s / 1e3:.1f} GB/s ({bytes_eval / s / 1e3 / 6552.6:.3f} of measured HBM peak)")
+t0 = time.time()
+res = vb.LevMarSolver.default().fit(gp)
+dt = time.time() - t0
+rep = res.minimization_report
+print(f"fit: {1e3*dt:.2f} ms, nfev {rep.number_of_evaluations}, term {rep.termination}, alpha {res.nonlinear_parameters()}")
+for _ in range(3):
+    gp.set_params(wl["alpha0"])
+    t0 = time.time()
+    res = vb.LevMarSolver.default().fit(gp)
+    dt = time.time() - t0
+    print(f"fit again: {1e3*dt:.2f} ms nfev {res.minimization_report.number_of_evaluations} -> {1e6*dt/res.minimization_report.number_of_evaluations:.1f} us/eval")

@@ -1,0 +1,617 @@
+"""Host-side mirror of the reference's operator interface for the VarPro hot path.
+
+Names, argument meaning and error behaviour follow geo-ant/varpro v0.13.3 so that
+the parity tests read like the reference's own tests:
+
+  SeparableModelBuilder   src/model/builder/mod.rs:252-525
+  SeparableModel          src/model/mod.rs:367-517   (trait SeparableNonlinearModel :239-363)
+  SeparableProblemBuilder src/problem/builder.rs:116-324
+  SeparableProblem        src/problem.rs:57-213 + impl LeastSquaresProblem src/solvers/levmar/mod.rs:22-202
+  LevenbergMarquardt      levenberg-marquardt 0.14 knobs (call sites src/solvers/levmar/mod.rs:221,307-315)
+  LevMarSolver, FitResult src/solvers/levmar/mod.rs:208-315, src/fit.rs:15-123
+
+Everything numeric happens behind the C ABI (include/varpro_b200.h) in the CUDA
+library; this module only validates, marshals and owns handles. The one
+deliberate difference from the reference: basis functions are not closures but
+descriptors of built-in device functions (a kernel cannot call a host closure;
+see DESIGN.md), so `.function(params, ExpDecay())` replaces
+`.function(params, exp_decay).partial_deriv(p, exp_decay_dtau)`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import VP_F32, VP_F64
+
+# ---------------------------------------------------------------------------
+# errors (mirroring the reference's enums)
+# ---------------------------------------------------------------------------
+
+
+class VarproError(Exception):
+    """Base class. `.status` holds the vp_status code when it came through the ABI."""
+
+    def __init__(self, msg, status=None):
+        super().__init__(msg)
+        self.status = status
+
+
+class ModelBuildError(VarproError):  # src/model/builder/error.rs:5-129
+    pass
+
+
+class DuplicateParameterNames(ModelBuildError):
+    pass
+
+
+class EmptyParameters(ModelBuildError):
+    pass
+
+
+class FunctionParameterNotInModel(ModelBuildError):
+    pass
+
+
+class EmptyModel(ModelBuildError):
+    pass
+
+
+class UnusedParameter(ModelBuildError):
+    pass
+
+
+class IncorrectParameterCount(ModelBuildError):
+    pass
+
+
+class CommaInParameterNameNotAllowed(ModelBuildError):
+    pass
+
+
+class MissingX(ModelBuildError):
+    pass
+
+
+class MissingInitialParameters(ModelBuildError):
+    pass
+
+
+class SeparableProblemBuilderError(VarproError):  # src/problem/builder.rs:15-46
+    pass
+
+
+class YDataMissing(SeparableProblemBuilderError):
+    pass
+
+
+class InvalidLengthOfData(SeparableProblemBuilderError):
+    pass
+
+
+class ZeroLengthVector(SeparableProblemBuilderError):
+    pass
+
+
+class InvalidParameterCount(SeparableProblemBuilderError):
+    pass
+
+
+class InvalidLengthOfWeights(SeparableProblemBuilderError):
+    pass
+
+
+class ModelError(VarproError):  # src/model/errors.rs:5-42
+    pass
+
+
+_STATUS_TO_EXC = {
+    1: YDataMissing, 2: InvalidLengthOfData, 3: ZeroLengthVector, 4: InvalidParameterCount,
+    5: InvalidLengthOfWeights, 10: FunctionParameterNotInModel, 12: IncorrectParameterCount,
+    13: EmptyModel, 14: UnusedParameter,
+}
+
+
+def _check(status: int, ctx=None):
+    if status == 0:
+        return
+    lib = _lib.load()
+    msg = lib.vp_last_error(ctx).decode() if ctx is not None else ""
+    if not msg:
+        msg = lib.vp_status_string(status).decode()
+    raise _STATUS_TO_EXC.get(status, VarproError)(msg, status)
+
+
+# ---------------------------------------------------------------------------
+# basis-function descriptors
+# ---------------------------------------------------------------------------
+@dataclass(frozen=True)
+class BasisFunction:
+    kind: int
+    arity: int
+    scale: float = 1.0
+
+
+def ExpDecay():
+    """exp(-x/tau), d/dtau = exp(-x/tau) x/tau^2 (shared_test_code/src/lib.rs:101-114)."""
+    return BasisFunction(0, 1)
+
+
+def Constant():
+    """1 -- an invariant function (shared_test_code/src/lib.rs:123)."""
+    return BasisFunction(1, 0)
+
+
+def ExpRateCos():
+    """exp(-a x) cos(b x), parameters (a, b) (shared_test_code/src/models.rs:321-322)."""
+    return BasisFunction(2, 2)
+
+
+def SinPhase():
+    """sin(omega x + phi), parameters (omega, phi) (src/test_helpers/mod.rs:27-51)."""
+    return BasisFunction(3, 2)
+
+
+def LinearX(scale=1.0):
+    """scale * x -- invariant (src/model/builder/test.rs:97,101)."""
+    return BasisFunction(4, 0, float(scale))
+
+
+# ---------------------------------------------------------------------------
+# device context (one per device ordinal, created lazily)
+# ---------------------------------------------------------------------------
+class _Ctx:
+    _by_device = {}
+
+    def __init__(self, device: int):
+        lib = _lib.load()
+        h = C.c_void_p()
+        st = lib.vp_ctx_create(device, C.byref(h))
+        if st != 0:
+            raise VarproError(lib.vp_last_error(None).decode() or lib.vp_status_string(st).decode(), st)
+        self.h = h
+        self.device = device
+
+    @classmethod
+    def get(cls, device: int = 0) -> "_Ctx":
+        if device not in cls._by_device:
+            cls._by_device[device] = _Ctx(device)
+        return cls._by_device[device]
+
+    def kernel_launches(self) -> int:
+        return int(_lib.load().vp_ctx_kernel_launches(self.h))
+
+    def stream(self) -> int:
+        return int(_lib.load().vp_ctx_stream(self.h) or 0)
+
+
+def kernel_launches(device: int = 0) -> int:
+    """Kernels launched so far by the library on `device` (bench.py's gpu_launches)."""
+    return _Ctx.get(device).kernel_launches()
+
+
+# ---------------------------------------------------------------------------
+# model
+# ---------------------------------------------------------------------------
+class SeparableModel:
+    """Result of SeparableModelBuilder.build (src/model/mod.rs:367-517)."""
+
+    def __init__(self, parameter_names, functions, x, initial_parameters, dtype):
+        self._names = list(parameter_names)
+        self._functions = functions  # list of (BasisFunction, [param indices])
+        self.x = np.ascontiguousarray(x, dtype=dtype)
+        self._params = np.array(initial_parameters, dtype=np.float64)
+        self.dtype = np.dtype(dtype)
+
+    def parameters(self) -> List[str]:
+        return list(self._names)
+
+    def parameter_count(self) -> int:
+        return len(self._names)
+
+    def base_function_count(self) -> int:
+        return len(self._functions)
+
+    def output_len(self) -> int:
+        return int(self.x.shape[0])
+
+    def params(self) -> np.ndarray:
+        return self._params.copy()
+
+    def set_params(self, parameters):
+        p = np.asarray(parameters, dtype=np.float64).ravel()
+        if p.shape[0] != self.parameter_count():
+            raise ModelError(f"Model expects {self.parameter_count()} parameters, but got {p.shape[0]}")
+        self._params = p.copy()
+
+    def _descs(self):
+        arr = (_lib.BasisDesc * len(self._functions))()
+        for d, (f, idx) in zip(arr, self._functions):
+            d.kind, d.n_params, d.scale = f.kind, len(idx), f.scale
+            for i, v in enumerate(idx):
+                d.param_idx[i] = v
+        return arr
+
+
+class SeparableModelBuilder:
+    """State machine of src/model/builder/mod.rs:252-525. Errors are deferred to build()."""
+
+    def __init__(self, parameter_names: Sequence[str], dtype=np.float64):
+        self._names = list(parameter_names)
+        self._functions = []
+        self._x = None
+        self._p0 = None
+        self._dtype = np.dtype(dtype)
+        self._error: Optional[ModelBuildError] = None
+        self._check_names(self._names)
+
+    @classmethod
+    def new(cls, parameter_names, dtype=np.float64):
+        return cls(parameter_names, dtype)
+
+    def _fail(self, err):
+        if self._error is None:
+            self._error = err
+
+    def _check_names(self, names):
+        # check_parameter_names (src/model/detail.rs:14-46)
+        if len(names) == 0:
+            return self._fail(EmptyParameters(
+                "A function or model parameter list is empty! It must at least contain one parameter."))
+        for nm in names:
+            if "," in nm:
+                return self._fail(CommaInParameterNameNotAllowed(
+                    f"Parameter names may not contain comma separator: '{nm}'."))
+        if len(set(names)) != len(names):
+            return self._fail(DuplicateParameterNames(f"Parameter list {list(names)} contains duplicates!"))
+
+    def function(self, function_params: Sequence[str], function: BasisFunction):
+        fp = list(function_params)
+        self._check_names(fp)
+        if self._error:
+            return self
+        if len(fp) != function.arity:
+            self._fail(IncorrectParameterCount(
+                f"Incorrect number of parameters for function: expected {function.arity}, got {len(fp)}"))
+            return self
+        idx = []
+        for nm in fp:  # create_index_mapping (src/model/detail.rs:60-78)
+            if nm not in self._names:
+                self._fail(FunctionParameterNotInModel(
+                    f"Function parameter '{nm}' is not part of the model parameters."))
+                return self
+            idx.append(self._names.index(nm))
+        self._functions.append((function, idx))
+        return self
+
+    def invariant_function(self, function: BasisFunction):
+        if function.arity != 0:
+            self._fail(IncorrectParameterCount(
+                f"Incorrect number of parameters for function: expected {function.arity}, got 0"))
+            return self
+        self._functions.append((function, []))
+        return self
+
+    def partial_deriv(self, parameter: str, derivative=None):
+        """Accepted for source compatibility: derivatives of the built-in kinds are built in."""
+        return self
+
+    def independent_variable(self, x):
+        self._x = np.asarray(x)
+        return self
+
+    def initial_parameters(self, initial_parameters):
+        self._p0 = list(initial_parameters)
+        return self
+
+    def build(self) -> SeparableModel:
+        if self._error:
+            raise self._error
+        if not self._functions:
+            raise EmptyModel("Tried to construct model with no functions. A model must contain at least one function.")
+        used = {i for _, idx in self._functions for i in idx}
+        for k, nm in enumerate(self._names):  # src/model/builder/mod.rs:547-557
+            if k not in used:
+                raise UnusedParameter(f"Model depends on parameter '{nm}', but none of its functions use it.")
+        if self._x is None:
+            raise MissingX("Missing vector for independent variable x")
+        if self._p0 is None:
+            raise MissingInitialParameters("Missing initial guesses for model parameters")
+        if len(self._p0) != len(self._names):
+            raise IncorrectParameterCount(
+                f"Incorrect number of parameters for function: expected {len(self._names)}, got {len(self._p0)}")
+        return SeparableModel(self._names, self._functions, self._x, self._p0, self._dtype)
+
+
+# ---------------------------------------------------------------------------
+# problem
+# ---------------------------------------------------------------------------
+class SeparableProblem:
+    """Device-resident SeparableProblem (src/problem.rs:57-107). Created by the builder."""
+
+    def __init__(self, model: SeparableModel, Y: np.ndarray, weights, eps, single_rhs, device=0,
+                 y_device_ptr=None, S=None, ldY=None):
+        lib = _lib.load()
+        self._ctx = _Ctx.get(device)
+        self.model_host = model
+        self.single_rhs = single_rhs
+        self.dtype = model.dtype
+        self._m = model.output_len()
+        self._n = model.base_function_count()
+        self._q = model.parameter_count()
+        self._model_h = C.c_void_p()
+        self._h = C.c_void_p()
+        dt = VP_F32 if self.dtype == np.float32 else VP_F64
+        descs = model._descs()
+        _check(lib.vp_model_create(self._ctx.h, dt, self._m, model.x.ctypes.data_as(C.c_void_p), self._q,
+                                   self._n, descs, C.byref(self._model_h)), self._ctx.h)
+        a0 = np.ascontiguousarray(model.params(), dtype=np.float64)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=self.dtype)
+        wp = None if w is None else w.ctypes.data_as(C.c_void_p)
+        ap = a0.ctypes.data_as(C.POINTER(C.c_double))
+        try:
+            if y_device_ptr is not None:
+                self._S = int(S)
+                _check(lib.vp_problem_create_device(self._ctx.h, self._model_h, self._S, C.c_void_p(y_device_ptr),
+                                                    int(ldY), wp, float(eps), ap, C.byref(self._h)), self._ctx.h)
+            else:
+                self._S = int(Y.shape[1])
+                _check(lib.vp_problem_create(self._ctx.h, self._model_h, self._S, Y.ctypes.data_as(C.c_void_p),
+                                             int(Y.shape[0]), wp, float(eps), ap, C.byref(self._h)), self._ctx.h)
+        except Exception:
+            lib.vp_model_destroy(self._model_h)
+            self._model_h = C.c_void_p()
+            raise
+        self._weights = w
+
+    def close(self):
+        lib = _lib.load()
+        if getattr(self, "_h", None) and self._h.value:
+            lib.vp_problem_destroy(self._h)
+            self._h = C.c_void_p()
+        if getattr(self, "_model_h", None) and self._model_h.value:
+            lib.vp_model_destroy(self._model_h)
+            self._model_h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- impl LeastSquaresProblem (src/solvers/levmar/mod.rs:22-202) ---
+    def set_params(self, params):
+        a = np.ascontiguousarray(params, dtype=np.float64)
+        if a.shape[0] != self._q:
+            raise ModelError(f"Model expects {self._q} parameters, but got {a.shape[0]}")
+        _check(_lib.load().vp_set_params(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), self._ctx.h)
+        self.model_host._params = a.copy()
+
+    def params(self) -> np.ndarray:
+        out = np.empty(self._q, dtype=np.float64)
+        _check(_lib.load().vp_params(self._h, out.ctypes.data_as(C.POINTER(C.c_double))), self._ctx.h)
+        return out
+
+    def _fetch(self, fn, shape):
+        out = np.empty(shape, dtype=self.dtype, order="F")
+        st = fn(self._h, out.ctypes.data_as(C.c_void_p))
+        if st == 20:  # cache is None -> Option::None in the reference
+            return None
+        _check(st, self._ctx.h)
+        return out
+
+    def residuals(self) -> Optional[np.ndarray]:
+        return self._fetch(_lib.load().vp_residuals, (self._m * self._S,))
+
+    def jacobian(self) -> Optional[np.ndarray]:
+        return self._fetch(_lib.load().vp_jacobian, (self._m * self._S, self._q))
+
+    def linear_coefficients(self) -> Optional[np.ndarray]:
+        c = self._fetch(_lib.load().vp_linear_coefficients, (self._n, self._S))
+        if c is not None and self.single_rhs:
+            return c[:, 0]
+        return c
+
+    def best_fit(self) -> Optional[np.ndarray]:
+        b = self._fetch(_lib.load().vp_best_fit, (self._m, self._S))
+        if b is not None and self.single_rhs:
+            return b[:, 0]
+        return b
+
+    def reduce(self):
+        """(||r||^2, J^T r, J^T J) of the current parameters, or None if the cache is None."""
+        r = _lib.Reduced()
+        st = _lib.load().vp_reduce(self._h, C.byref(r))
+        if st == 20:
+            return None
+        _check(st, self._ctx.h)
+        q = self._q
+        return dict(rnorm2=r.rnorm2, g=np.array(r.g[:q]), H=np.array(r.H[:q * q]).reshape(q, q).T.copy(),
+                    finite=bool(r.finite))
+
+    def model(self) -> SeparableModel:
+        return self.model_host
+
+    def weights(self):
+        return self._weights
+
+
+class SeparableProblemBuilder:
+    """src/problem/builder.rs:116-324."""
+
+    def __init__(self, model: SeparableModel, single_rhs: bool):
+        self._model = model
+        self._single = single_rhs
+        self._Y = None
+        self._w = None
+        self._eps = None
+        self._device = 0
+
+    @classmethod
+    def new(cls, model):  # :116
+        return cls(model, True)
+
+    @classmethod
+    def mrhs(cls, model):  # :194
+        return cls(model, False)
+
+    def observations(self, observed):  # :142 / :220
+        y = np.asarray(observed)
+        if self._single:
+            y = y.reshape(-1, 1) if y.ndim == 1 else y
+        self._Y = y
+        return self
+
+    def weights(self, weights):  # :261-266
+        self._w = np.asarray(weights)
+        return self
+
+    def epsilon(self, eps):  # :246-251
+        self._eps = abs(float(eps))
+        return self
+
+    def device(self, ordinal: int):
+        self._device = int(ordinal)
+        return self
+
+    def build(self) -> SeparableProblem:  # :278-324
+        if self._Y is None:
+            raise YDataMissing("Right hand side(s) not provided", 1)
+        Y = self._Y
+        x_len = self._model.output_len()
+        if x_len == 0 or Y.size == 0:
+            raise ZeroLengthVector("x or y must have nonzero number of elements.", 3)
+        if Y.ndim != 2 or (self._single and Y.shape[1] != 1):
+            raise InvalidLengthOfData("observations have the wrong shape", 2)
+        if x_len != Y.shape[0]:
+            raise InvalidLengthOfData(
+                f"Vectors x and y must have same lengths. Given x length = {x_len} and y length = {Y.shape[0]}", 2)
+        if self._w is not None and self._w.shape != (Y.shape[0],):
+            raise InvalidLengthOfWeights("The weights must have the same length as the data y.", 5)
+        eps = -1.0 if self._eps is None else self._eps  # default: machine epsilon of the scalar (:282)
+        Yf = np.asfortranarray(Y, dtype=self._model.dtype)
+        return SeparableProblem(self._model, Yf, self._w, eps, self._single, self._device)
+
+
+# ---------------------------------------------------------------------------
+# solver
+# ---------------------------------------------------------------------------
+TERMINATION_NAMES = [
+    "User", "Numerical", "ResidualsZero", "Orthogonal", "Converged{ftol}", "Converged{xtol}",
+    "Converged{ftol,xtol}", "NoImprovementPossible", "LostPatience", "NoParameters", "NoResiduals",
+    "WrongDimensions",
+]
+
+
+class TerminationReason:
+    def __init__(self, code: int):
+        self.code = code
+
+    def was_successful(self) -> bool:
+        return self.code in (2, 3, 4, 5, 6)
+
+    def __repr__(self):
+        return TERMINATION_NAMES[self.code] if 0 <= self.code < len(TERMINATION_NAMES) else f"?({self.code})"
+
+
+@dataclass
+class MinimizationReport:
+    termination: TerminationReason
+    number_of_evaluations: int
+    objective_function: float
+
+
+class LevenbergMarquardt:
+    """Option holder with the levenberg-marquardt crate's builder knobs (0 => crate default)."""
+
+    def __init__(self):
+        self._o = _lib.LmOptions(0.0, 0.0, 0.0, 0.0, 0, -1)
+
+    @classmethod
+    def new(cls):
+        return cls()
+
+    def with_ftol(self, v):
+        self._o.ftol = float(v)
+        return self
+
+    def with_xtol(self, v):
+        self._o.xtol = float(v)
+        return self
+
+    def with_gtol(self, v):
+        self._o.gtol = float(v)
+        return self
+
+    def with_tol(self, v):
+        return self.with_ftol(v).with_xtol(v).with_gtol(v)
+
+    def with_stepbound(self, v):
+        self._o.stepbound = float(v)
+        return self
+
+    def with_patience(self, v):
+        self._o.patience = int(v)
+        return self
+
+    def with_scale_diag(self, v):
+        self._o.scale_diag = 1 if v else 0
+        return self
+
+
+class FitResult:
+    """src/fit.rs:15-123."""
+
+    def __init__(self, problem: SeparableProblem, report: MinimizationReport):
+        self.problem = problem
+        self.minimization_report = report
+
+    def nonlinear_parameters(self) -> np.ndarray:
+        return self.problem.params()
+
+    def linear_coefficients(self):
+        return self.problem.linear_coefficients()
+
+    def best_fit(self):
+        return self.problem.best_fit()
+
+    def was_successful(self) -> bool:
+        return self.minimization_report.termination.was_successful()
+
+
+class FitError(VarproError):
+    """Err(FitResult) of LevMarSolver::fit: carries the same FitResult in `.result`."""
+
+    def __init__(self, result: FitResult):
+        super().__init__(f"fit did not terminate successfully: {result.minimization_report.termination!r}")
+        self.result = result
+
+
+class LevMarSolver:
+    """src/solvers/levmar/mod.rs:208-315."""
+
+    def __init__(self, solver: Optional[LevenbergMarquardt] = None):
+        self._solver = solver or LevenbergMarquardt()
+
+    @classmethod
+    def default(cls):
+        return cls()
+
+    @classmethod
+    def with_solver(cls, solver: LevenbergMarquardt):
+        return cls(solver)
+
+    def fit(self, problem: SeparableProblem) -> FitResult:
+        """Ok(FitResult) is returned, Err(FitResult) is raised as FitError (same payload)."""
+        rep = _lib.FitReport()
+        _check(_lib.load().vp_fit(problem._h, C.byref(self._solver._o), C.byref(rep)), problem._ctx.h)
+        problem.model_host._params = problem.params()
+        result = FitResult(problem, MinimizationReport(TerminationReason(rep.termination),
+                                                       rep.number_of_evaluations, rep.objective_function))
+        if not result.was_successful():
+            raise FitError(result)
+        return result

@@ -1,0 +1,144 @@
+// device_common.cuh -- shared device-side definitions: model descriptor, basis
+// evaluation, mbarrier / bulk-copy (TMA) PTX wrappers, block reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/varpro_b200.h"
+
+namespace vp {
+
+// Device-side model description: the table of built-in basis kinds plus the
+// parameter-index map (reference: create_index_mapping, src/model/detail.rs:60-78)
+// and the list of non-zero derivative columns (the reference stores these as a
+// HashMap per basis function, src/model/mod.rs:497-510; MATLAB varpro calls it
+// `Ind`, matlab/varpro.m:147-189).
+struct ModelDesc {
+    int m, n, q, p;
+    int kind[VP_MAX_N];
+    int npar[VP_MAX_N];
+    int pidx[VP_MAX_N][VP_MAX_BASIS_PARAMS];
+    double scale[VP_MAX_N];
+    int e_basis[VP_MAX_P]; // basis function j(e) of derivative column e
+    int e_slot[VP_MAX_P];  // which of that function's parameters
+    int e_param[VP_MAX_P]; // model parameter index k(e)
+};
+
+// Layout of the per-evaluation reduction vector produced by the streaming pass:
+// [0]                 sum_s ||r_s||^2
+// [1 .. 1+n(n+1)/2)   G = sum_s c_s c_s^T, upper triangle packed row-wise (i<=j)
+// [.. +p)             V_e = sum_s c_{s,j(e)} * (E_e^T y_s)
+__host__ __device__ inline int red_count(int n, int p) { return 1 + n * (n + 1) / 2 + p; }
+__host__ __device__ inline int g_index(int n, int i, int j)
+{ // i <= j
+    return 1 + i * n - i * (i - 1) / 2 + (j - i);
+}
+
+// --- basis functions, formulas as the reference writes them ---
+__device__ __forceinline__ double basis_value(int kind, double x, const double *a, double scale)
+{
+    switch (kind) {
+    case VP_BASIS_EXP_DECAY: return exp(-x / a[0]);            // shared_test_code/src/lib.rs:101-106
+    case VP_BASIS_CONSTANT: return 1.0;                        // lib.rs:123
+    case VP_BASIS_EXP_RATE_COS: return exp(-a[0] * x) * cos(a[1] * x); // models.rs:321-322
+    case VP_BASIS_SIN_PHASE: return sin(a[0] * x + a[1]);      // src/test_helpers/mod.rs:27-33
+    case VP_BASIS_LINEAR_X: return scale * x;                  // src/model/builder/test.rs:97,101
+    default: return nan("");
+    }
+}
+
+__device__ __forceinline__ double basis_deriv(int kind, int slot, double x, const double *a)
+{
+    switch (kind) {
+    case VP_BASIS_EXP_DECAY: return exp(-x / a[0]) * x / (a[0] * a[0]); // lib.rs:108-114
+    case VP_BASIS_EXP_RATE_COS:                                          // models.rs:362-385
+        return slot == 0 ? -x * (exp(-a[0] * x) * cos(a[1] * x)) : -x * exp(-a[0] * x) * sin(a[1] * x);
+    case VP_BASIS_SIN_PHASE:                                             // src/test_helpers/mod.rs:36-51
+        return slot == 0 ? x * cos(a[0] * x + a[1]) : cos(a[0] * x + a[1]);
+    default: return 0.0;
+    }
+}
+
+// --- mbarrier + bulk async copy (TMA, SASS: UBLKCP / SYNCS) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// --- reductions ---------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum NV per-thread values over the whole CTA; every thread receives the totals.
+// scratch: at least (blockDim.x/32)*NV + NV doubles of shared memory.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = warp_sum(v[k]);
+        if (lane == 0) scratch[warp * NV + k] = t;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double t = 0.0;
+            for (int w = lane; w < nw; w += 32) t += scratch[w * NV + k];
+            t = warp_sum(t);
+            if (lane == 0) scratch[nw * NV + k] = t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = scratch[nw * NV + k];
+    __syncthreads();
+}
+
+} // namespace vp

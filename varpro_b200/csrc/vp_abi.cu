@@ -1,0 +1,761 @@
+// vp_abi.cu -- implementation of the C ABI declared in include/varpro_b200.h.
+// Host-side handle management, kernel dispatch and the LM driver. There is no
+// CPU compute path in this file: every evaluation launches the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/varpro_b200.h"
+#include "aux_kernels.cuh"
+#include "device_common.cuh"
+#include "lm_step.cuh"
+#include "panel_kernel.cuh"
+#include "stream_kernel.cuh"
+
+using namespace vp;
+
+// ----------------------------------------------------------------------------
+// handles
+// ----------------------------------------------------------------------------
+struct vp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int64_t launches = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+};
+
+struct vp_model {
+    vp_ctx *ctx = nullptr;
+    int dtype = VP_F64;
+    ModelDesc md{};
+    void *x_dev = nullptr;
+    int ld = 0; // padded row count (multiple of 16/sizeof(T))
+};
+
+struct vp_problem {
+    vp_ctx *ctx = nullptr;
+    vp_model *model = nullptr;
+    int64_t S = 0;
+    void *Yw = nullptr;    // ld x S
+    void *w_dev = nullptr; // m or null
+    double svd_eps = 0.0;
+    double alpha[VP_MAX_Q] = {0};
+    double *alpha_dev = nullptr;
+    void *Pq = nullptr, *Pe = nullptr;
+    PanelSmall *small = nullptr;
+    void *C[2] = {nullptr, nullptr}; // coefficient buffers (n x S); C[cur] belongs to `alpha`
+    int cur = 0;
+    double *partials = nullptr;
+    int red_stride = 0;
+    int max_grid = 0;
+    unsigned int *ticket = nullptr;
+    EvalOut *out_dev = nullptr;
+    EvalOut *out_host = nullptr; // pinned
+    double *alpha_stage = nullptr; // pinned
+    double *phi_scratch = nullptr; // m x n (best_fit)
+    LmEval eval{};                 // reduction at `alpha`
+    bool cached = false;
+    // streaming-kernel launch plan
+    int plan_kind = -1; // index into the dispatch table, -1 = generic
+    int plan_grid = 0, plan_nst = 0;
+    size_t plan_smem = 0;
+};
+
+static thread_local std::string g_last_error_noctx;
+
+static int fail(vp_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx)
+        ctx->last_error = msg;
+    else
+        g_last_error_noctx = msg;
+    return code;
+}
+
+#define VP_CUDA(ctx, expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail((ctx), (_e == cudaErrorMemoryAllocation) ? VP_ERR_OUT_OF_MEMORY : VP_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+    } while (0)
+
+static size_t esize(int dtype) { return dtype == VP_F32 ? 4 : 8; }
+static int vec_of(int dtype) { return dtype == VP_F32 ? 4 : 2; }
+
+extern "C" int vp_abi_version(void) { return VP_ABI_VERSION; }
+
+extern "C" const char *vp_status_string(int s)
+{
+    switch (s) {
+    case VP_OK: return "ok";
+    case VP_ERR_Y_DATA_MISSING: return "Right hand side(s) not provided";
+    case VP_ERR_INVALID_LENGTH_OF_DATA: return "Vectors x and y must have same lengths";
+    case VP_ERR_ZERO_LENGTH_VECTOR: return "x or y must have nonzero number of elements";
+    case VP_ERR_INVALID_PARAMETER_COUNT: return "Initial guess vector must have same length as parameters";
+    case VP_ERR_INVALID_LENGTH_OF_WEIGHTS: return "The weights must have the same length as the data y";
+    case VP_ERR_PARAMETER_NOT_IN_MODEL: return "Parameter is not in model";
+    case VP_ERR_DERIVATIVE_INDEX_OUT_OF_BOUNDS: return "Index for derivative is out of bounds";
+    case VP_ERR_INCORRECT_PARAMETER_COUNT: return "Model expects a different number of parameters";
+    case VP_ERR_EMPTY_MODEL: return "Model contains no basis functions";
+    case VP_ERR_UNUSED_PARAMETER: return "A model parameter is not used by any basis function";
+    case VP_ERR_UNSUPPORTED_BASIS: return "Unsupported basis-function kind";
+    case VP_ERR_MODEL_TOO_LARGE: return "Model exceeds the compiled-in size limits";
+    case VP_ERR_NO_CACHED_CALCULATION: return "No cached calculation (evaluation failed)";
+    case VP_ERR_UNDERDETERMINED: return "Problem is underdetermined";
+    case VP_ERR_MATRIX_INVERSION: return "Matrix inversion failed";
+    case VP_ERR_INVALID_ARGUMENT: return "Invalid argument";
+    case VP_ERR_CUDA: return "CUDA error";
+    case VP_ERR_OUT_OF_MEMORY: return "Out of device memory";
+    case VP_ERR_COMM: return "Communicator error";
+    default: return "unknown status";
+    }
+}
+
+extern "C" int vp_ctx_create(int device, vp_ctx **out)
+{
+    if (!out) return VP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VP_ERR_CUDA,
+                    std::string("no CUDA device available (this library has no CPU fallback): ") +
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, VP_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    vp_ctx *ctx = new (std::nothrow) vp_ctx();
+    if (!ctx) return VP_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    cudaDeviceProp prop{};
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, VP_ERR_CUDA, "cannot initialise device");
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return VP_OK;
+}
+
+extern "C" int vp_ctx_destroy(vp_ctx *ctx)
+{
+    if (!ctx) return VP_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return VP_OK;
+}
+
+extern "C" const char *vp_last_error(const vp_ctx *ctx)
+{
+    return ctx ? ctx->last_error.c_str() : g_last_error_noctx.c_str();
+}
+extern "C" int64_t vp_ctx_kernel_launches(const vp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void *vp_ctx_stream(const vp_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// ----------------------------------------------------------------------------
+// model
+// ----------------------------------------------------------------------------
+static int basis_arity(int kind)
+{
+    switch (kind) {
+    case VP_BASIS_EXP_DECAY: return 1;
+    case VP_BASIS_CONSTANT: return 0;
+    case VP_BASIS_EXP_RATE_COS: return 2;
+    case VP_BASIS_SIN_PHASE: return 2;
+    case VP_BASIS_LINEAR_X: return 0;
+    default: return -1;
+    }
+}
+
+extern "C" int vp_model_create(vp_ctx *ctx, int dtype, int64_t m, const void *x_host, int32_t q, int32_t n,
+                               const vp_basis_desc *basis, vp_model **out)
+{
+    if (!ctx || !out) return VP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (dtype != VP_F64 && dtype != VP_F32) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "dtype must be VP_F64 or VP_F32");
+    if (n <= 0 || !basis) return fail(ctx, VP_ERR_EMPTY_MODEL, vp_status_string(VP_ERR_EMPTY_MODEL));
+    if (m <= 0 || !x_host) return fail(ctx, VP_ERR_ZERO_LENGTH_VECTOR, vp_status_string(VP_ERR_ZERO_LENGTH_VECTOR));
+    if (n > VP_MAX_N || q > VP_MAX_Q || q < 0 || m > (1 << 24))
+        return fail(ctx, VP_ERR_MODEL_TOO_LARGE, vp_status_string(VP_ERR_MODEL_TOO_LARGE));
+    ModelDesc md{};
+    md.m = (int)m; md.n = n; md.q = q; md.p = 0;
+    std::vector<int> used(q > 0 ? q : 1, 0);
+    for (int j = 0; j < n; ++j) {
+        const vp_basis_desc &b = basis[j];
+        const int ar = basis_arity(b.kind);
+        if (ar < 0) return fail(ctx, VP_ERR_UNSUPPORTED_BASIS, vp_status_string(VP_ERR_UNSUPPORTED_BASIS));
+        if (b.n_params != ar)
+            return fail(ctx, VP_ERR_INCORRECT_PARAMETER_COUNT, "basis function " + std::to_string(j) + " expects " +
+                                                                   std::to_string(ar) + " parameters, but got " +
+                                                                   std::to_string(b.n_params));
+        md.kind[j] = b.kind;
+        md.npar[j] = ar;
+        md.scale[j] = b.scale;
+        for (int s = 0; s < ar; ++s) {
+            const int k = b.param_idx[s];
+            if (k < 0 || k >= q) return fail(ctx, VP_ERR_PARAMETER_NOT_IN_MODEL, vp_status_string(VP_ERR_PARAMETER_NOT_IN_MODEL));
+            md.pidx[j][s] = k;
+            used[k] = 1;
+            if (md.p >= VP_MAX_P) return fail(ctx, VP_ERR_MODEL_TOO_LARGE, vp_status_string(VP_ERR_MODEL_TOO_LARGE));
+            md.e_basis[md.p] = j;
+            md.e_slot[md.p] = s;
+            md.e_param[md.p] = k;
+            md.p++;
+        }
+    }
+    for (int k = 0; k < q; ++k)
+        if (!used[k]) return fail(ctx, VP_ERR_UNUSED_PARAMETER, vp_status_string(VP_ERR_UNUSED_PARAMETER));
+
+    vp_model *mo = new (std::nothrow) vp_model();
+    if (!mo) return VP_ERR_OUT_OF_MEMORY;
+    mo->ctx = ctx; mo->dtype = dtype; mo->md = md;
+    const int v = vec_of(dtype);
+    mo->ld = (int)((m + v - 1) / v * v);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(&mo->x_dev, esize(dtype) * (size_t)m);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mo->x_dev, x_host, esize(dtype) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (mo->x_dev) cudaFree(mo->x_dev);
+        delete mo;
+        return fail(ctx, VP_ERR_CUDA, std::string("vp_model_create: ") + cudaGetErrorString(e));
+    }
+    *out = mo;
+    return VP_OK;
+}
+
+extern "C" int vp_model_destroy(vp_model *model)
+{
+    if (!model) return VP_OK;
+    cudaSetDevice(model->ctx->device);
+    cudaFree(model->x_dev);
+    delete model;
+    return VP_OK;
+}
+
+// ----------------------------------------------------------------------------
+// streaming-kernel dispatch table
+// ----------------------------------------------------------------------------
+struct StreamKernelEntry {
+    int dtype, n, p, threads, chunks, ct;
+    const void *fn;
+};
+
+#define VP_SK(T, DT, N, P, THREADS, CHUNKS, CT) \
+    {DT, N, P, THREADS, CHUNKS, CT, (const void *)&stream_kernel<T, N, P, CHUNKS, CT, THREADS>}
+#define VP_SK_SHAPES(T, DT, N, P)                                                  \
+    VP_SK(T, DT, N, P, 128, 1, 4), VP_SK(T, DT, N, P, 128, 4, 4), VP_SK(T, DT, N, P, 128, 4, 8), \
+        VP_SK(T, DT, N, P, 256, 4, 4), VP_SK(T, DT, N, P, 256, 8, 4)
+
+static const StreamKernelEntry g_stream_kernels[] = {
+    VP_SK_SHAPES(double, VP_F64, 3, 2), // double exponential + offset (benches, C1/C2/C5)
+    VP_SK_SHAPES(float, VP_F32, 3, 2),  // the same in fp32 (C4)
+    VP_SK_SHAPES(double, VP_F64, 3, 3), // triple exponential
+    VP_SK_SHAPES(double, VP_F64, 2, 4), // O'Leary exp*cos example
+};
+static const int g_num_stream_kernels = (int)(sizeof(g_stream_kernels) / sizeof(g_stream_kernels[0]));
+
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// choose the kernel instantiation, stage count and grid for a problem
+static int plan_stream(vp_problem *pr)
+{
+    vp_ctx *ctx = pr->ctx;
+    const vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    const int want_ct = env_int("VP_STREAM_CT", 4);
+    const int want_occ = env_int("VP_STREAM_OCC", 2);
+    const int force_generic = env_int("VP_STREAM_GENERIC", 0);
+    const size_t es = esize(mo->dtype);
+    pr->plan_kind = -1;
+    int best = -1;
+    if (!force_generic) {
+        for (int i = 0; i < g_num_stream_kernels; ++i) {
+            const StreamKernelEntry &k = g_stream_kernels[i];
+            if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p) continue;
+            if ((long long)k.threads * k.chunks * vec_of(mo->dtype) < mo->ld) continue;
+            // smallest covering (threads*chunks) first, then the requested tile width
+            if (best < 0) { best = i; continue; }
+            const StreamKernelEntry &b = g_stream_kernels[best];
+            const long long ck = (long long)k.threads * k.chunks, cb = (long long)b.threads * b.chunks;
+            if (ck < cb || (ck == cb && k.threads < b.threads) ||
+                (ck == cb && k.threads == b.threads && std::abs(k.ct - want_ct) < std::abs(b.ct - want_ct)))
+                best = i;
+        }
+    }
+    if (best >= 0) {
+        const StreamKernelEntry &k = g_stream_kernels[best];
+        const size_t stage_bytes = (size_t)k.ct * mo->ld * es;
+        // static shared memory of the kernel + a safety margin
+        cudaFuncAttributes fa{};
+        VP_CUDA(ctx, cudaFuncGetAttributes(&fa, k.fn));
+        const size_t per_sm = 227 * 1024; // usable shared memory per SM
+        int occ = want_occ < 1 ? 1 : want_occ;
+        int nst = 0;
+        for (; occ >= 1; --occ) {
+            const size_t budget = per_sm / occ - fa.sharedSizeBytes - 1024;
+            nst = (int)(budget / stage_bytes);
+            if (nst >= 2) break;
+        }
+        if (nst >= 2) {
+            if (nst > STREAM_MAX_STAGES) nst = STREAM_MAX_STAGES;
+            const int max_st = env_int("VP_STREAM_STAGES", 0);
+            if (max_st >= 2 && nst > max_st) nst = max_st;
+            const size_t smem = (size_t)nst * stage_bytes;
+            if (smem + fa.sharedSizeBytes <= ctx->smem_optin) {
+                VP_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int occ_real = 0;
+                VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k.fn, k.threads, smem));
+                if (occ_real >= 1) {
+                    const long long ntiles = (pr->S + k.ct - 1) / k.ct;
+                    long long grid = (long long)ctx->sm_count * occ_real;
+                    if (grid > ntiles) grid = ntiles;
+                    if (grid > pr->max_grid) grid = pr->max_grid;
+                    pr->plan_kind = best;
+                    pr->plan_grid = (int)grid;
+                    pr->plan_nst = nst;
+                    pr->plan_smem = smem;
+                    return VP_OK;
+                }
+            }
+        }
+    }
+    // generic fallback: one warp per column
+    pr->plan_kind = -1;
+    long long grid = (pr->S + 7) / 8;
+    const long long cap = (long long)ctx->sm_count * 8;
+    pr->plan_grid = (int)(grid < cap ? grid : cap);
+    pr->plan_nst = 0;
+    pr->plan_smem = 0;
+    return VP_OK;
+}
+
+template <typename T>
+static int launch_panel_t(vp_problem *pr)
+{
+    vp_ctx *ctx = pr->ctx;
+    vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    int threads = PANEL_THREADS;
+    if (md.m < threads) threads = ((md.m + 31) / 32) * 32;
+    const size_t smem = sizeof(double) * ((size_t)(md.n + md.p) * md.m + (size_t)(threads / 32 + 1) * 8 + 64);
+    if (smem > ctx->smem_optin)
+        return fail(ctx, VP_ERR_MODEL_TOO_LARGE, "m*(n+p) panel does not fit in shared memory");
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        VP_CUDA(ctx, cudaFuncSetAttribute(panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    panel_kernel<T><<<1, threads, smem, ctx->stream>>>(md, (const T *)mo->x_dev, (const T *)pr->w_dev, pr->alpha_dev,
+                                                       pr->svd_eps, mo->ld, (T *)pr->Pq, (T *)pr->Pe, pr->small);
+    ctx->launches++;
+    VP_CUDA(ctx, cudaGetLastError());
+    return VP_OK;
+}
+
+template <typename T>
+static int launch_stream_t(vp_problem *pr, int cdst)
+{
+    vp_ctx *ctx = pr->ctx;
+    vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    StreamArgs<T> a{};
+    a.Y = (const T *)pr->Yw; a.ld = mo->ld; a.S = (int)pr->S;
+    a.Pq = (const T *)pr->Pq; a.Pe = (const T *)pr->Pe; a.small = pr->small;
+    a.Cout = (T *)pr->C[cdst];
+    a.partials = pr->partials; a.red_stride = pr->red_stride; a.ticket = pr->ticket; a.out = pr->out_dev;
+    a.nstages = pr->plan_nst; a.q = md.q;
+    for (int e = 0; e < VP_MAX_P; ++e) { a.e_basis[e] = md.e_basis[e]; a.e_param[e] = md.e_param[e]; }
+    if (pr->plan_kind >= 0) {
+        const StreamKernelEntry &k = g_stream_kernels[pr->plan_kind];
+        void *args[] = {(void *)&a};
+        VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(pr->plan_grid), dim3(k.threads), args, pr->plan_smem, ctx->stream));
+    } else {
+        stream_kernel_generic<T, 256><<<pr->plan_grid, 256, 0, ctx->stream>>>(a, md.n, md.p, md.m);
+    }
+    ctx->launches++;
+    VP_CUDA(ctx, cudaGetLastError());
+    return VP_OK;
+}
+
+static int launch_panel(vp_problem *pr)
+{
+    return pr->model->dtype == VP_F32 ? launch_panel_t<float>(pr) : launch_panel_t<double>(pr);
+}
+static int launch_stream(vp_problem *pr, int cdst)
+{
+    return pr->model->dtype == VP_F32 ? launch_stream_t<float>(pr, cdst) : launch_stream_t<double>(pr, cdst);
+}
+static int launch_eval(vp_problem *pr, int cdst)
+{
+    int rc = launch_panel(pr);
+    return rc != VP_OK ? rc : launch_stream(pr, cdst);
+}
+
+// Evaluate at `alpha` into coefficient buffer `cdst`; result in pr->out_host.
+static int evaluate_sync(vp_problem *pr, const double *alpha, int cdst)
+{
+    vp_ctx *ctx = pr->ctx;
+    const int q = pr->model->md.q;
+    cudaSetDevice(ctx->device);
+    for (int k = 0; k < q; ++k) pr->alpha_stage[k] = alpha[k];
+    if (q > 0)
+        VP_CUDA(ctx, cudaMemcpyAsync(pr->alpha_dev, pr->alpha_stage, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_eval(pr, cdst);
+    if (rc != VP_OK) return rc;
+    VP_CUDA(ctx, cudaMemcpyAsync(pr->out_host, pr->out_dev, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
+    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VP_OK;
+}
+
+static void evalout_to_lm(const EvalOut &o, int q, LmEval &ev)
+{
+    ev.rnorm2 = o.rnorm2;
+    ev.finite = o.finite;
+    for (int k = 0; k < q; ++k) ev.g[k] = o.g[k];
+    for (int i = 0; i < q * q; ++i) ev.H[i] = o.H[i];
+}
+
+// ----------------------------------------------------------------------------
+// problem
+// ----------------------------------------------------------------------------
+static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const void *Y, int64_t ldY, bool y_on_device,
+                                 const void *w_host, double svd_eps, const double *alpha0, vp_problem **out)
+{
+    if (!ctx || !model || !out) return VP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (model->ctx != ctx) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "model belongs to a different context");
+    if (!Y) return fail(ctx, VP_ERR_Y_DATA_MISSING, vp_status_string(VP_ERR_Y_DATA_MISSING));
+    const ModelDesc &md = model->md;
+    if (S <= 0 || md.m <= 0) return fail(ctx, VP_ERR_ZERO_LENGTH_VECTOR, vp_status_string(VP_ERR_ZERO_LENGTH_VECTOR));
+    if (ldY < md.m)
+        return fail(ctx, VP_ERR_INVALID_LENGTH_OF_DATA, "Vectors x and y must have same lengths. Given x length = " +
+                                                            std::to_string(md.m) + " and y length = " + std::to_string(ldY));
+    if (S > INT32_MAX / 2) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "S too large for one problem handle");
+    if (md.q > 0 && !alpha0) return fail(ctx, VP_ERR_INVALID_PARAMETER_COUNT, vp_status_string(VP_ERR_INVALID_PARAMETER_COUNT));
+    cudaSetDevice(ctx->device);
+    vp_problem *pr = new (std::nothrow) vp_problem();
+    if (!pr) return VP_ERR_OUT_OF_MEMORY;
+    pr->ctx = ctx; pr->model = model; pr->S = S;
+    const int dtype = model->dtype;
+    const size_t es = esize(dtype);
+    const int ld = model->ld, m = md.m;
+    // default epsilon = machine epsilon of the scalar (src/problem/builder.rs:282), |eps| otherwise (:248)
+    pr->svd_eps = svd_eps < 0 ? (dtype == VP_F32 ? (double)FLT_EPSILON : DBL_EPSILON) : fabs(svd_eps);
+    pr->red_stride = 64;
+    pr->max_grid = ctx->sm_count * 8;
+
+    auto cleanup = [&](int code, const std::string &msg) {
+        vp_problem_destroy(pr);
+        return fail(ctx, code, msg);
+    };
+#define VP_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return cleanup(_e == cudaErrorMemoryAllocation ? VP_ERR_OUT_OF_MEMORY : VP_ERR_CUDA,       \
+                           std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    } while (0)
+
+    VP_TRY(cudaMalloc(&pr->Yw, es * (size_t)ld * S));
+    VP_TRY(cudaMalloc(&pr->Pq, es * (size_t)ld * md.n));
+    VP_TRY(cudaMalloc(&pr->Pe, es * (size_t)ld * (md.p > 0 ? md.p : 1)));
+    VP_TRY(cudaMalloc(&pr->small, sizeof(PanelSmall)));
+    VP_TRY(cudaMalloc(&pr->C[0], es * (size_t)md.n * S));
+    VP_TRY(cudaMalloc(&pr->C[1], es * (size_t)md.n * S));
+    VP_TRY(cudaMalloc(&pr->partials, sizeof(double) * (size_t)pr->red_stride * pr->max_grid));
+    VP_TRY(cudaMalloc(&pr->ticket, sizeof(unsigned int)));
+    VP_TRY(cudaMemsetAsync(pr->ticket, 0, sizeof(unsigned int), ctx->stream));
+    VP_TRY(cudaMalloc(&pr->out_dev, sizeof(EvalOut)));
+    VP_TRY(cudaMalloc(&pr->alpha_dev, sizeof(double) * VP_MAX_Q));
+    VP_TRY(cudaMalloc(&pr->phi_scratch, sizeof(double) * (size_t)m * md.n));
+    VP_TRY(cudaMallocHost(&pr->out_host, sizeof(EvalOut)));
+    VP_TRY(cudaMallocHost(&pr->alpha_stage, sizeof(double) * VP_MAX_Q));
+    if (w_host) {
+        VP_TRY(cudaMalloc(&pr->w_dev, es * (size_t)m));
+        VP_TRY(cudaMemcpyAsync(pr->w_dev, w_host, es * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // observations -> device buffer with leading dimension ld
+    const cudaMemcpyKind kind = y_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (ldY == ld)
+        VP_TRY(cudaMemcpyAsync(pr->Yw, Y, es * (size_t)ld * S, kind, ctx->stream));
+    else
+        VP_TRY(cudaMemcpy2DAsync(pr->Yw, es * ld, Y, es * (size_t)ldY, es * (size_t)m, (size_t)S, kind, ctx->stream));
+    if (w_host || ld != m) {
+        const long long total = (long long)ld * S;
+        int blocks = (int)((total + 255) / 256 < (long long)ctx->sm_count * 16 ? (total + 255) / 256 : (long long)ctx->sm_count * 16);
+        if (dtype == VP_F32)
+            weight_rows_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float *)pr->Yw, (const float *)pr->w_dev, m, ld, S);
+        else
+            weight_rows_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double *)pr->Yw, (const double *)pr->w_dev, m, ld, S);
+        ctx->launches++;
+        VP_TRY(cudaGetLastError());
+    }
+#undef VP_TRY
+    int rc = plan_stream(pr);
+    if (rc != VP_OK) { vp_problem_destroy(pr); return rc; }
+    // first evaluation at the initial guess (src/problem/builder.rs:321)
+    for (int k = 0; k < md.q; ++k) pr->alpha[k] = alpha0[k];
+    rc = evaluate_sync(pr, pr->alpha, pr->cur);
+    if (rc != VP_OK) { vp_problem_destroy(pr); return rc; }
+    evalout_to_lm(*pr->out_host, md.q, pr->eval);
+    pr->cached = pr->eval.finite != 0;
+    *out = pr;
+    return VP_OK;
+}
+
+extern "C" int vp_problem_create(vp_ctx *ctx, vp_model *model, int64_t S, const void *Y_host, int64_t ldY,
+                                 const void *w_host, double svd_eps, const double *alpha0, vp_problem **out)
+{
+    return problem_create_common(ctx, model, S, Y_host, ldY, false, w_host, svd_eps, alpha0, out);
+}
+
+extern "C" int vp_problem_create_device(vp_ctx *ctx, vp_model *model, int64_t S, const void *Y_device, int64_t ldY,
+                                        const void *w_host, double svd_eps, const double *alpha0, vp_problem **out)
+{
+    return problem_create_common(ctx, model, S, Y_device, ldY, true, w_host, svd_eps, alpha0, out);
+}
+
+extern "C" int vp_problem_destroy(vp_problem *pr)
+{
+    if (!pr) return VP_OK;
+    cudaSetDevice(pr->ctx->device);
+    cudaStreamSynchronize(pr->ctx->stream);
+    cudaFree(pr->Yw); cudaFree(pr->w_dev); cudaFree(pr->Pq); cudaFree(pr->Pe); cudaFree(pr->small);
+    cudaFree(pr->C[0]); cudaFree(pr->C[1]); cudaFree(pr->partials); cudaFree(pr->ticket);
+    cudaFree(pr->out_dev); cudaFree(pr->alpha_dev); cudaFree(pr->phi_scratch);
+    if (pr->out_host) cudaFreeHost(pr->out_host);
+    if (pr->alpha_stage) cudaFreeHost(pr->alpha_stage);
+    delete pr;
+    return VP_OK;
+}
+
+// ----------------------------------------------------------------------------
+// trait-mirroring entry points
+// ----------------------------------------------------------------------------
+extern "C" int vp_set_params(vp_problem *pr, const double *alpha)
+{
+    if (!pr || (!alpha && pr->model->md.q > 0)) return VP_ERR_INVALID_ARGUMENT;
+    const int q = pr->model->md.q;
+    for (int k = 0; k < q; ++k) pr->alpha[k] = alpha[k];
+    const int dst = pr->cur ^ 1;
+    int rc = evaluate_sync(pr, pr->alpha, dst);
+    if (rc != VP_OK) { pr->cached = false; return rc; }
+    pr->cur = dst;
+    evalout_to_lm(*pr->out_host, q, pr->eval);
+    pr->cached = pr->eval.finite != 0;
+    return VP_OK;
+}
+
+extern "C" int vp_params(const vp_problem *pr, double *alpha_out)
+{
+    if (!pr || !alpha_out) return VP_ERR_INVALID_ARGUMENT;
+    for (int k = 0; k < pr->model->md.q; ++k) alpha_out[k] = pr->alpha[k];
+    return VP_OK;
+}
+
+extern "C" int vp_reduce(vp_problem *pr, vp_reduced *out)
+{
+    if (!pr || !out) return VP_ERR_INVALID_ARGUMENT;
+    const int q = pr->model->md.q;
+    memset(out, 0, sizeof(*out));
+    out->rnorm2 = pr->eval.rnorm2;
+    out->finite = pr->eval.finite;
+    out->q = q;
+    for (int k = 0; k < q; ++k) out->g[k] = pr->eval.g[k];
+    for (int i = 0; i < q * q; ++i) out->H[i] = pr->eval.H[i];
+    return pr->cached ? VP_OK : fail(pr->ctx, VP_ERR_NO_CACHED_CALCULATION, vp_status_string(VP_ERR_NO_CACHED_CALCULATION));
+}
+
+// make sure the panel buffers (Pq, Pe) correspond to pr->alpha (a rejected LM
+// trial leaves them at the trial point)
+static int ensure_panel_current(vp_problem *pr)
+{
+    PanelSmall sm;
+    vp_ctx *ctx = pr->ctx;
+    VP_CUDA(ctx, cudaMemcpyAsync(&sm, pr->small, sizeof(sm), cudaMemcpyDeviceToHost, ctx->stream));
+    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool same = true;
+    for (int k = 0; k < pr->model->md.q; ++k) same = same && (sm.alpha[k] == pr->alpha[k]);
+    if (same) return VP_OK;
+    // re-evaluate at the accepted parameters into the spare coefficient buffer
+    const int dst = pr->cur ^ 1;
+    int rc = evaluate_sync(pr, pr->alpha, dst);
+    if (rc != VP_OK) return rc;
+    pr->cur = dst;
+    return VP_OK;
+}
+
+template <typename T>
+static int materialise_t(vp_problem *pr, int what, void *out_host)
+{
+    vp_ctx *ctx = pr->ctx;
+    vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    const size_t mS = (size_t)md.m * pr->S;
+    const size_t count = what == 1 ? mS * md.q : mS;
+    if (count == 0) return VP_OK;
+    T *buf = nullptr;
+    VP_CUDA(ctx, cudaMalloc(&buf, sizeof(T) * count));
+    const int blocks = ctx->sm_count * 8;
+    if (what == 0) {
+        residuals_kernel<T><<<blocks, 256, 0, ctx->stream>>>((const T *)pr->Yw, mo->ld, md.m, (int)pr->S, md.n,
+                                                             (const T *)pr->Pq, buf);
+    } else if (what == 1) {
+        jacobian_kernel<T><<<blocks, 256, 0, ctx->stream>>>(mo->ld, md.m, (int)pr->S, md.n, md.p, md.q,
+                                                            (const T *)pr->Pe, (const T *)pr->C[pr->cur], md, buf);
+    } else {
+        phi_kernel<T><<<32, 256, 0, ctx->stream>>>(md, (const T *)mo->x_dev, pr->alpha_dev, pr->phi_scratch);
+        ctx->launches++;
+        best_fit_kernel<T><<<blocks, 256, 0, ctx->stream>>>(md.m, (int)pr->S, md.n, pr->phi_scratch,
+                                                            (const T *)pr->C[pr->cur], buf);
+    }
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, buf, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, std::string("materialise: ") + cudaGetErrorString(e));
+    return VP_OK;
+}
+
+static int materialise(vp_problem *pr, int what, void *out_host)
+{
+    if (!pr || !out_host) return VP_ERR_INVALID_ARGUMENT;
+    if (!pr->cached) return fail(pr->ctx, VP_ERR_NO_CACHED_CALCULATION, vp_status_string(VP_ERR_NO_CACHED_CALCULATION));
+    cudaSetDevice(pr->ctx->device);
+    int rc = ensure_panel_current(pr);
+    if (rc != VP_OK) return rc;
+    return pr->model->dtype == VP_F32 ? materialise_t<float>(pr, what, out_host) : materialise_t<double>(pr, what, out_host);
+}
+
+extern "C" int vp_residuals(vp_problem *pr, void *out_host) { return materialise(pr, 0, out_host); }
+extern "C" int vp_jacobian(vp_problem *pr, void *out_host) { return materialise(pr, 1, out_host); }
+extern "C" int vp_best_fit(vp_problem *pr, void *out_host) { return materialise(pr, 2, out_host); }
+
+extern "C" int vp_linear_coefficients(vp_problem *pr, void *out_host)
+{
+    if (!pr || !out_host) return VP_ERR_INVALID_ARGUMENT;
+    if (!pr->cached) return fail(pr->ctx, VP_ERR_NO_CACHED_CALCULATION, vp_status_string(VP_ERR_NO_CACHED_CALCULATION));
+    vp_ctx *ctx = pr->ctx;
+    cudaSetDevice(ctx->device);
+    const size_t bytes = esize(pr->model->dtype) * (size_t)pr->model->md.n * pr->S;
+    VP_CUDA(ctx, cudaMemcpyAsync(out_host, pr->C[pr->cur], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VP_OK;
+}
+
+// ----------------------------------------------------------------------------
+// LevMarSolver::fit  (src/solvers/levmar/mod.rs:238-254)
+// ----------------------------------------------------------------------------
+extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *rep)
+{
+    if (!pr || !rep) return VP_ERR_INVALID_ARGUMENT;
+    vp_ctx *ctx = pr->ctx;
+    const int q = pr->model->md.q;
+    const double eps = pr->model->dtype == VP_F32 ? (double)FLT_EPSILON : DBL_EPSILON;
+    LmConfig cfg;
+    cfg.epsmch = eps;
+    cfg.ftol = (opt && opt->ftol > 0) ? opt->ftol : 30.0 * eps;
+    cfg.xtol = (opt && opt->xtol > 0) ? opt->xtol : 30.0 * eps;
+    cfg.gtol = (opt && opt->gtol > 0) ? opt->gtol : 30.0 * eps;
+    cfg.stepbound = (opt && opt->stepbound > 0) ? opt->stepbound : 100.0;
+    const int patience = (opt && opt->patience > 0) ? opt->patience : 100;
+    cfg.maxfev = patience * (q + 1);
+    cfg.scale_diag = (opt && opt->scale_diag >= 0) ? (opt->scale_diag != 0) : 1;
+    memset(rep, 0, sizeof(*rep));
+
+    LmState st;
+    lm_init(st, q, pr->alpha);
+    if (!pr->cached) {
+        // residuals() is None -> the LM crate stops with a User termination
+        rep->termination = VP_TERM_USER;
+        rep->number_of_evaluations = 0;
+        rep->objective_function = NAN;
+        rep->successful = 0;
+        return VP_OK;
+    }
+    // the evaluation at the current parameters is cached (builder / set_params)
+    bool more = lm_advance(st, cfg, pr->eval);
+    while (more) {
+        const int dst = pr->cur ^ 1;
+        int rc = evaluate_sync(pr, st.x_trial, dst);
+        if (rc != VP_OK) return rc;
+        LmEval ev;
+        evalout_to_lm(*pr->out_host, q, ev);
+        more = lm_advance(st, cfg, ev);
+        if (st.last_accepted) {
+            pr->cur = dst;
+            pr->eval = ev;
+            for (int k = 0; k < q; ++k) pr->alpha[k] = st.x[k];
+        }
+    }
+    (void)ctx;
+    rep->termination = st.termination;
+    rep->number_of_evaluations = st.nfev;
+    rep->objective_function = 0.5 * st.fnorm * st.fnorm;
+    rep->successful = lm_successful(st.termination) ? 1 : 0;
+    return VP_OK;
+}
+
+// ----------------------------------------------------------------------------
+// diagnostics: per-kernel device times of one evaluation, CUDA events on the
+// context's stream (used by bench.py for the roofline line)
+// ----------------------------------------------------------------------------
+extern "C" int vp_profile_evaluation(vp_problem *pr, int iters, int64_t flush_bytes, double *panel_us,
+                                     double *stream_us, int64_t *stream_grid, int64_t *stream_smem)
+{
+    if (!pr || iters <= 0) return VP_ERR_INVALID_ARGUMENT;
+    vp_ctx *ctx = pr->ctx;
+    cudaSetDevice(ctx->device);
+    cudaEvent_t e0, e1, e2;
+    VP_CUDA(ctx, cudaEventCreate(&e0));
+    VP_CUDA(ctx, cudaEventCreate(&e1));
+    VP_CUDA(ctx, cudaEventCreate(&e2));
+    void *flush = nullptr;
+    if (flush_bytes > 0) VP_CUDA(ctx, cudaMalloc(&flush, (size_t)flush_bytes));
+    const int q = pr->model->md.q;
+    for (int k = 0; k < q; ++k) pr->alpha_stage[k] = pr->alpha[k];
+    if (q > 0)
+        VP_CUDA(ctx, cudaMemcpyAsync(pr->alpha_dev, pr->alpha_stage, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
+    double tp = 0, ts = 0;
+    int rc = VP_OK;
+    for (int it = 0; it < iters && rc == VP_OK; ++it) {
+        if (flush) cudaMemsetAsync(flush, it & 0xff, (size_t)flush_bytes, ctx->stream);
+        cudaEventRecord(e0, ctx->stream);
+        rc = launch_panel(pr);
+        cudaEventRecord(e1, ctx->stream);
+        if (rc == VP_OK) rc = launch_stream(pr, pr->cur ^ 1);
+        cudaEventRecord(e2, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        tp += a; ts += b;
+    }
+    if (flush) cudaFree(flush);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (rc != VP_OK) return rc;
+    if (panel_us) *panel_us = 1e3 * tp / iters;
+    if (stream_us) *stream_us = 1e3 * ts / iters;
+    if (stream_grid) *stream_grid = pr->plan_grid;
+    if (stream_smem) *stream_smem = (int64_t)pr->plan_smem;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, cudaGetErrorString(e));
+    return VP_OK;
+}

@@ -211,6 +211,12 @@ int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *rep
 int vp_profile_evaluation(vp_problem *problem, int iters, int64_t flush_bytes, double *panel_us,
                           double *stream_us, int64_t *stream_grid, int64_t *stream_smem);
 
+/* One evaluation with the in-kernel timeline enabled (diagnostics): `out`
+ * receives (grid+1)*16 %globaltimer stamps in ns relative to the earliest one,
+ * one row per CTA of K2 (start, panel slice loaded, first tile landed, loop
+ * done, publish begin, published, finalize done, -) and a last row for K1. */
+int vp_debug_timeline(vp_problem *problem, long long *out, int64_t capacity, int64_t *grid_out);
+
 #ifdef __cplusplus
 }
 #endif

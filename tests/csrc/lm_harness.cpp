@@ -1,0 +1,45 @@
+// Host-side harness around the product's lm_step.cuh (which is __host__ __device__), so that the
+// CPU test-suite can drive the exact LM state machine the GPU runs, with evaluations supplied by
+// the test (e.g. H = J^T J, g = J^T r computed from the oracle's explicit J and r).
+// Test infrastructure only.
+#include <cstring>
+#include "../../varpro_b200/csrc/lm_step.cuh"
+
+using namespace vp;
+
+struct Harness {
+    LmState st;
+    LmConfig cfg;
+};
+
+extern "C" {
+Harness *lmh_new(int q, const double *x0, double ftol, double xtol, double gtol, double stepbound, int maxfev,
+                 int scale_diag, double epsmch)
+{
+    Harness *h = new Harness();
+    h->cfg.ftol = ftol; h->cfg.xtol = xtol; h->cfg.gtol = gtol; h->cfg.stepbound = stepbound;
+    h->cfg.maxfev = maxfev; h->cfg.scale_diag = scale_diag; h->cfg.epsmch = epsmch;
+    lm_init(h->st, q, x0);
+    return h;
+}
+void lmh_free(Harness *h) { delete h; }
+// feed an evaluation made at lmh_trial(); returns 1 if another evaluation is needed
+int lmh_advance(Harness *h, double rnorm2, const double *g, const double *H /* q x q col-major */, int finite)
+{
+    LmEval ev;
+    std::memset(&ev, 0, sizeof(ev));
+    const int q = h->st.q;
+    ev.rnorm2 = rnorm2; ev.finite = finite;
+    for (int k = 0; k < q; ++k) ev.g[k] = g[k];
+    for (int i = 0; i < q * q; ++i) ev.H[i] = H[i];
+    return lm_advance(h->st, h->cfg, ev) ? 1 : 0;
+}
+void lmh_trial(const Harness *h, double *x) { for (int k = 0; k < h->st.q; ++k) x[k] = h->st.x_trial[k]; }
+void lmh_accepted(const Harness *h, double *x) { for (int k = 0; k < h->st.q; ++k) x[k] = h->st.x[k]; }
+int lmh_termination(const Harness *h) { return h->st.termination; }
+int lmh_nfev(const Harness *h) { return h->st.nfev; }
+int lmh_last_accepted(const Harness *h) { return h->st.last_accepted; }
+double lmh_fnorm(const Harness *h) { return h->st.fnorm; }
+double lmh_par(const Harness *h) { return h->st.par; }
+double lmh_delta(const Harness *h) { return h->st.delta; }
+}

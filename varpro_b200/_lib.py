@@ -67,6 +67,7 @@ SYMBOLS = {
     "vp_best_fit": (C.c_int, [_vp, _vp]),
     "vp_reduce": (C.c_int, [_vp, C.POINTER(Reduced)]),
     "vp_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),
+    "vp_debug_timeline": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.c_int64, C.POINTER(C.c_int64)]),
     "vp_profile_evaluation": (C.c_int, [_vp, C.c_int, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int64)]),
 }

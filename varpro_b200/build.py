@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvarpro_b200.so")
 SOURCES = ["vp_abi.cu"]
-HEADERS = ["device_common.cuh", "panel_kernel.cuh", "stream_kernel.cuh", "aux_kernels.cuh", "lm_step.cuh",
+HEADERS = ["device_common.cuh", "panel_kernel.cuh", "panel_kernel_hh.cuh", "stream_kernel.cuh", "stream_kernel_dmma.cuh", "aux_kernels.cuh", "lm_step.cuh",
            os.path.join("..", "..", "include", "varpro_b200.h")]
 
 NVCC_FLAGS = [

@@ -28,7 +28,7 @@ __global__ void weight_rows_kernel(T *__restrict__ Y, const T *__restrict__ w, i
 // vec(R): r_s = y_s - Q (Q^T y_s)   (src/solvers/levmar/mod.rs:57-59, 91-95)
 // one warp per column; out is dense m x S.
 template <typename T>
-__global__ void residuals_kernel(const T *__restrict__ Y, int ld, int m, int S, int n,
+__global__ void residuals_kernel(const T *__restrict__ Y, int ld, int ldp, int m, int S, int n,
                                  const T *__restrict__ Pq, T *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
@@ -42,7 +42,7 @@ __global__ void residuals_kernel(const T *__restrict__ Y, int ld, int m, int S, 
             const double yi = (double)y[i];
 #pragma unroll
             for (int k = 0; k < VP_MAX_N; ++k)
-                if (k < n) b[k] += (double)Pq[(size_t)k * ld + i] * yi;
+                if (k < n) b[k] += (double)Pq[(size_t)k * ldp + i] * yi;
         }
 #pragma unroll
         for (int k = 0; k < VP_MAX_N; ++k) b[k] = warp_sum(b[k]);
@@ -50,7 +50,7 @@ __global__ void residuals_kernel(const T *__restrict__ Y, int ld, int m, int S, 
             double r = (double)y[i];
 #pragma unroll
             for (int k = 0; k < VP_MAX_N; ++k)
-                if (k < n) r -= (double)Pq[(size_t)k * ld + i] * b[k];
+                if (k < n) r -= (double)Pq[(size_t)k * ldp + i] * b[k];
             out[(size_t)s * m + i] = (T)r;
         }
     }
@@ -59,7 +59,7 @@ __global__ void residuals_kernel(const T *__restrict__ Y, int ld, int m, int S, 
 // Kaufman Jacobian, column k, RHS s (src/solvers/levmar/mod.rs:101-201):
 //   J[s*m+i, k] = -(P_perp D_k c_s)_i = -sum_{e in k} E_e[i] * C[j(e), s]
 template <typename T>
-__global__ void jacobian_kernel(int ld, int m, int S, int n, int p, int q, const T *__restrict__ Pe,
+__global__ void jacobian_kernel(int ldp, int m, int S, int n, int p, int q, const T *__restrict__ Pe,
                                 const T *__restrict__ C, ModelDesc md, T *__restrict__ out)
 {
     const long long total = (long long)m * S;
@@ -71,7 +71,7 @@ __global__ void jacobian_kernel(int ld, int m, int S, int n, int p, int q, const
             double acc = 0.0;
             for (int e = 0; e < p; ++e)
                 if (md.e_param[e] == k)
-                    acc -= (double)Pe[(size_t)e * ld + i] * (double)C[(size_t)s * n + md.e_basis[e]];
+                    acc -= (double)Pe[(size_t)e * ldp + i] * (double)C[(size_t)s * n + md.e_basis[e]];
             out[(size_t)k * total + idx] = (T)acc;
         }
     }
@@ -85,10 +85,9 @@ __global__ void phi_kernel(ModelDesc md, const T *__restrict__ x, const double *
     const int m = md.m, n = md.n;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < m * n; idx += gridDim.x * blockDim.x) {
         const int i = idx % m, j = idx / m;
-        double a[VP_MAX_BASIS_PARAMS];
-#pragma unroll
-        for (int s = 0; s < VP_MAX_BASIS_PARAMS; ++s) a[s] = s < md.npar[j] ? alpha[md.pidx[j][s]] : 0.0;
-        phi[idx] = basis_value(md.kind[j], (double)x[i], a, md.scale[j]);
+        const double a0 = md.npar[j] > 0 ? alpha[md.pidx[j][0]] : 0.0;
+        const double a1 = md.npar[j] > 1 ? alpha[md.pidx[j][1]] : 0.0;
+        phi[idx] = basis_eval_all(md.kind[j], (double)x[i], a0, a1, md.scale[j]).v;
     }
 }
 

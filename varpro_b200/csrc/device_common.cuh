@@ -35,31 +35,6 @@ __host__ __device__ inline int g_index(int n, int i, int j)
     return 1 + i * n - i * (i - 1) / 2 + (j - i);
 }
 
-// --- basis functions, formulas as the reference writes them ---
-__device__ __forceinline__ double basis_value(int kind, double x, const double *a, double scale)
-{
-    switch (kind) {
-    case VP_BASIS_EXP_DECAY: return exp(-x / a[0]);            // shared_test_code/src/lib.rs:101-106
-    case VP_BASIS_CONSTANT: return 1.0;                        // lib.rs:123
-    case VP_BASIS_EXP_RATE_COS: return exp(-a[0] * x) * cos(a[1] * x); // models.rs:321-322
-    case VP_BASIS_SIN_PHASE: return sin(a[0] * x + a[1]);      // src/test_helpers/mod.rs:27-33
-    case VP_BASIS_LINEAR_X: return scale * x;                  // src/model/builder/test.rs:97,101
-    default: return nan("");
-    }
-}
-
-__device__ __forceinline__ double basis_deriv(int kind, int slot, double x, const double *a)
-{
-    switch (kind) {
-    case VP_BASIS_EXP_DECAY: return exp(-x / a[0]) * x / (a[0] * a[0]); // lib.rs:108-114
-    case VP_BASIS_EXP_RATE_COS:                                          // models.rs:362-385
-        return slot == 0 ? -x * (exp(-a[0] * x) * cos(a[1] * x)) : -x * exp(-a[0] * x) * sin(a[1] * x);
-    case VP_BASIS_SIN_PHASE:                                             // src/test_helpers/mod.rs:36-51
-        return slot == 0 ? x * cos(a[0] * x + a[1]) : cos(a[0] * x + a[1]);
-    default: return 0.0;
-    }
-}
-
 // --- mbarrier + bulk async copy (TMA, SASS: UBLKCP / SYNCS) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -104,6 +79,19 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gsrc, 
             smem_u32(smem_dst)),
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// --- optional in-kernel timeline (debug/profiling aid; no-op when dbg == nullptr) ---
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define VP_DBG_SLOTS 16
+__device__ __forceinline__ void dbg_mark(unsigned long long *dbg, int slot)
+{
+    if (dbg && threadIdx.x == 0) dbg[(size_t)blockIdx.x * VP_DBG_SLOTS + slot] = global_timer_ns();
 }
 
 // --- reductions ---------------------------------------------------------------

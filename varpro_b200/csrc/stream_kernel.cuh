@@ -26,6 +26,7 @@
 #pragma once
 
 #include "device_common.cuh"
+#include "lm_step.cuh"
 #include "panel_kernel.cuh"
 
 namespace vp {
@@ -38,15 +39,33 @@ struct EvalOut {
     int pad;
 };
 
+// Device-resident state of one fit (graph path): the lmder state machine of lm_step.cuh
+// advanced by the last CTA of the streaming kernel, so that a whole fit runs without the host.
+struct FitDevice {
+    LmState st;
+    LmConfig cfg;
+    LmEval accepted; // evaluation belonging to st.x
+    int cur;         // coefficient buffer holding C(st.x): the kernel writes the trial into cur^1
+    int evals;       // evaluations made by the graph (diagnostics)
+    double trace[4 * 48]; // per evaluation: fnorm_trial, par, delta, accepted (diagnostics; VP_TRACE)
+};
+constexpr int FIT_WORDS = (int)((sizeof(FitDevice) + 7) / 8);
+
 template <typename T>
 struct StreamArgs {
     const T *Y;      // m x S weighted observations, ld rows per column
     int ld;          // padded rows (multiple of 16/sizeof(T))
     int S;
-    const T *Pq;     // n x ld
-    const T *Pe;     // p x ld
+    const T *Pq;     // panel [Q | E | 0]: (n+p+1) columns of ldp rows; the last column is all zero
+    const T *Pe;     // = Pq + n*ldp
+    int ldp;         // panel column stride (>= ld and >= the rows a kernel touches; rows >= m are zero)
+    unsigned long long *dbg;   // optional timeline buffer (gridDim.x * VP_DBG_SLOTS), or nullptr
+    int tiles_base, tiles_rem; // CTA b processes tiles_base + (b < tiles_rem) tiles: b, b+grid, b+2*grid, ...
     const PanelSmall *small;
-    T *Cout;         // n x S coefficients (trial buffer)
+    T *C0, *C1;      // n x S coefficient buffers
+    int cdst;        // host-driven path: buffer to write (0/1); graph path: ignored (fit->cur ^ 1)
+    FitDevice *fit;  // graph path: device-resident LM state, or nullptr
+    unsigned long long cond; // graph path: cudaGraphConditionalHandle of the while node
     double *partials; // gridDim.x * red_stride
     int red_stride;
     unsigned int *ticket;
@@ -59,6 +78,14 @@ struct StreamArgs {
 
 constexpr int STREAM_MAX_STAGES = 16;
 
+// coefficient buffer this launch writes: the one NOT holding the accepted coefficients
+template <typename T>
+__device__ __forceinline__ T *stream_cout(const StreamArgs<T> &a)
+{
+    const int dst = a.fit ? (__ldcg(&a.fit->cur) ^ 1) : a.cdst;
+    return dst ? a.C1 : a.C0;
+}
+
 template <typename T> struct VecOf;
 template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
 template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
@@ -66,58 +93,214 @@ template <> struct VecOf<float> { using type = float4; static constexpr int N = 
 template <typename T> __device__ __forceinline__ void vec_unpack(const double2 &v, T (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 template <typename T> __device__ __forceinline__ void vec_unpack(const float4 &v, T (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 
+// Halving fold of NACC = CT*NPV per-lane partial sums across a warp: each of
+// the log2(CT) exchange steps halves the number of values a lane carries, so
+// a lane ends up owning the NPV totals of ONE column; a plain butterfly over
+// the remaining lane bits finishes. ~2.2*NACC shuffles instead of 10*NACC.
+// All indices are compile-time constants (the array must stay in registers).
+template <int NACC, int CNT, int OFF, int NPV>
+__device__ __forceinline__ void warp_fold(double (&red)[NACC], const int lane)
+{
+    if constexpr (CNT > NPV) {
+        constexpr int half = CNT / 2;
+        const bool up = (lane & OFF) != 0;
+#pragma unroll
+        for (int t = 0; t < half; ++t) {
+            const double send = up ? red[t] : red[t + half];
+            const double keep = up ? red[t + half] : red[t];
+            red[t] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        warp_fold<NACC, half, OFF / 2, NPV>(red, lane);
+    } else {
+#pragma unroll
+        for (int off = OFF; off > 0; off >>= 1)
+#pragma unroll
+            for (int k = 0; k < NPV; ++k) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
+    }
+}
+
 // Final fold executed by the last CTA: partials -> (rnorm2, g, H).
+// 16 threads per value: thread (k = tid%16, c0 = tid/16) sums value k over the
+// CTAs c0, c0 + blockDim/16, ... (independent loads in flight), the 16-column
+// table is then folded in a fixed order => bitwise reproducible for a given
+// grid, no shuffles. sh: >= 64 doubles; scratch: >= 16 * blockDim/16 + p*p doubles.
+constexpr int FIN_SCRATCH = 16 * 32 + VP_MAX_P * VP_MAX_P + 64 + 4 * 48; // also holds a FitDevice copy (static_assert below)
+static_assert(FIT_WORDS <= FIN_SCRATCH, "FitDevice must fit in the finalize scratch");
 template <typename T>
-__device__ void stream_finalize(const StreamArgs<T> &a, int n, int p, int nparts, double *sh /* >= 64 doubles */)
+__device__ void stream_finalize(const StreamArgs<T> &a, int n, int p, int nparts, double *sh, double *scratch)
 {
     const int nv = red_count(n, p);
-    const int tid = threadIdx.x;
-    if (tid < nv) {
-        // fixed summation order over CTAs => bitwise reproducible for a given grid
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        int c = 0;
-        for (; c + 4 <= nparts; c += 4) {
-            s0 += __ldcg(a.partials + (size_t)(c + 0) * a.red_stride + tid);
-            s1 += __ldcg(a.partials + (size_t)(c + 1) * a.red_stride + tid);
-            s2 += __ldcg(a.partials + (size_t)(c + 2) * a.red_stride + tid);
-            s3 += __ldcg(a.partials + (size_t)(c + 3) * a.red_stride + tid);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int k = tid & 15, c0 = tid >> 4, nc0 = nt >> 4;
+    double *Msh = scratch + 16 * 32;
+    if (tid < p * p) Msh[tid] = __ldcg(&a.small->M[(tid / p) * VP_MAX_P + (tid % p)]); // Msh[f*p + e]
+    int nonfinite = 0;
+    if (tid == 0) nonfinite = a.small->nonfinite;
+    dbg_mark(a.dbg, 11);
+#pragma unroll 1
+    for (int base = 0; base < nv; base += 16) {
+        double s = 0.0;
+        if (base + k < nv) {
+            // four independent accumulators: the loads of one trip are all in flight together
+            const double *src = a.partials + base + k;
+            const size_t rs = (size_t)a.red_stride;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int c = c0;
+            for (; c + 3 * nc0 < nparts; c += 4 * nc0) {
+                const double l0 = __ldcg(src + (size_t)c * rs), l1 = __ldcg(src + (size_t)(c + nc0) * rs);
+                const double l2 = __ldcg(src + (size_t)(c + 2 * nc0) * rs), l3 = __ldcg(src + (size_t)(c + 3 * nc0) * rs);
+                s0 += l0; s1 += l1; s2 += l2; s3 += l3;
+            }
+            for (; c < nparts; c += nc0) s0 += __ldcg(src + (size_t)c * rs);
+            s = (s0 + s1) + (s2 + s3);
         }
-        for (; c < nparts; ++c) s0 += __ldcg(a.partials + (size_t)c * a.red_stride + tid);
-        sh[tid] = (s0 + s1) + (s2 + s3);
+        scratch[c0 * 16 + k] = s;
+        __syncthreads();
+        dbg_mark(a.dbg, 12);
+        if (tid < 16 && base + tid < nv) {
+            double t = 0.0;
+            for (int c = 0; c < nc0; ++c) t += scratch[c * 16 + tid];
+            sh[base + tid] = t;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (tid == 0) {
-        const PanelSmall *sm = a.small;
         EvalOut *o = a.out;
         const int q = a.q;
         double rn2 = sh[0];
-        int finite = isfinite(rn2) && !sm->nonfinite;
-        for (int k = 0; k < q; ++k) {
+        int finite = isfinite(rn2) && !nonfinite;
+        for (int kk = 0; kk < q; ++kk) {
             double gk = 0.0;
             for (int e = 0; e < p; ++e)
-                if (a.e_param[e] == k) gk -= sh[1 + n * (n + 1) / 2 + e];
-            o->g[k] = gk;
+                if (a.e_param[e] == kk) gk -= sh[1 + n * (n + 1) / 2 + e];
+            o->g[kk] = gk;
             finite = finite && isfinite(gk);
         }
-        for (int k = 0; k < q; ++k)
-            for (int l = 0; l <= k; ++l) {
+        for (int kk = 0; kk < q; ++kk)
+            for (int l = 0; l <= kk; ++l) {
                 double h = 0.0;
                 for (int e = 0; e < p; ++e) {
-                    if (a.e_param[e] != k) continue;
+                    if (a.e_param[e] != kk) continue;
                     for (int f = 0; f < p; ++f) {
                         if (a.e_param[f] != l) continue;
                         int i = a.e_basis[e], j = a.e_basis[f];
                         if (i > j) { int t = i; i = j; j = t; }
-                        h += sm->M[f * VP_MAX_P + e] * sh[g_index(n, i, j)];
+                        h += Msh[f * p + e] * sh[g_index(n, i, j)];
                     }
                 }
-                o->H[l * q + k] = h;
-                o->H[k * q + l] = h;
+                o->H[l * q + kk] = h;
+                o->H[kk * q + l] = h;
                 finite = finite && isfinite(h);
             }
         o->rnorm2 = rn2;
         o->finite = finite;
         *a.ticket = 0; // re-arm for the next launch
+        dbg_mark(a.dbg, 13);
+    }
+    if (a.fit) {
+        // graph path: advance the lmder state machine on a shared-memory copy of the state
+        // (cooperative load/store: one 8-byte word per thread) and steer the while node
+        __syncthreads();
+        unsigned long long *fw = reinterpret_cast<unsigned long long *>(a.fit);
+        unsigned long long *lw = reinterpret_cast<unsigned long long *>(scratch); // FIN_SCRATCH >= FIT_WORDS
+        for (int i = tid; i < FIT_WORDS; i += nt) lw[i] = __ldcg(fw + i);
+        __syncthreads();
+        if (tid == 0) {
+            FitDevice *f = reinterpret_cast<FitDevice *>(lw);
+            LmEval ev;
+            ev.rnorm2 = a.out->rnorm2;
+            ev.finite = a.out->finite;
+            for (int kk = 0; kk < VP_LM_MAXQ; ++kk) ev.g[kk] = kk < a.q ? a.out->g[kk] : 0.0;
+            for (int kk = 0; kk < VP_LM_MAXQ * VP_LM_MAXQ; ++kk) ev.H[kk] = kk < a.q * a.q ? a.out->H[kk] : 0.0;
+            const bool more = lm_advance(f->st, f->cfg, ev);
+            if (f->st.last_accepted) {
+                f->cur ^= 1;
+                f->accepted = ev;
+            }
+            if (f->evals < 48) {
+                double *tr = f->trace + 4 * f->evals;
+                tr[0] = sqrt(ev.rnorm2); tr[1] = f->st.par; tr[2] = f->st.delta; tr[3] = f->st.last_accepted;
+            }
+            f->evals += 1;
+            cudaGraphSetConditional(a.cond, more ? 1u : 0u);
+        }
+        __syncthreads();
+        for (int i = tid; i < FIT_WORDS; i += nt) fw[i] = lw[i];
+        dbg_mark(a.dbg, 15);
+    }
+}
+
+// CTA partial (already reduced, in shared memory) -> global; the last CTA to arrive folds all partials.
+template <typename T>
+__device__ __forceinline__ void stream_epilogue(const StreamArgs<T> &a, int n, int p, const double *cta_vals /* smem, nv */,
+                                                double *sh, double *scratch, int *is_last)
+{
+    const int nv = red_count(n, p);
+    const int tid = threadIdx.x;
+    if (tid < nv) a.partials[(size_t)blockIdx.x * a.red_stride + tid] = cta_vals[tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(a.ticket, 1u);
+        *is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*is_last) {
+        __threadfence();
+        stream_finalize<T>(a, n, p, gridDim.x, sh, scratch);
+    }
+}
+
+// Fold the per-thread accumulators of one CTA (rn2 in every thread; G, V in
+// threads < CT) into the CTA's partial vector, publish it, and let the last CTA
+// finish. Written for few instructions: it runs once per CTA and these kernels
+// live for a few microseconds.
+template <typename T, int N, int P, int CT, int NW>
+__device__ __forceinline__ void cta_publish(const StreamArgs<T> &a, double rn2, const double *Gacc, const double *Vacc,
+                                            double *wsum /* NW */, double *gv /* CT*(NG+P) */, double *sh,
+                                            double *scratch, int *is_last)
+{
+    constexpr int NG = N * (N + 1) / 2, NGP = NG + P, NVR = 1 + NGP;
+    static_assert(NVR <= 32, "the partial row must be written by one warp");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    dbg_mark(a.dbg, 4);
+    const double t = warp_sum(rn2);
+    if (lane == 0) wsum[warp] = t;
+    if (tid < CT) {
+#pragma unroll
+        for (int u = 0; u < NG; ++u) gv[tid * NGP + u] = Gacc[u];
+#pragma unroll
+        for (int e = 0; e < P; ++e) gv[tid * NGP + NG + e] = Vacc[e];
+    }
+    __syncthreads();
+    if (tid < NVR) {
+        double s = 0.0;
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += wsum[w];
+        } else {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) s += gv[c * NGP + tid - 1];
+        }
+        a.partials[(size_t)blockIdx.x * a.red_stride + tid] = s;
+    }
+    // publish: the partial row is written by warp 0; its lane 0 then takes a ticket with
+    // release/acquire semantics at gpu scope (orders the row before the ticket and, in
+    // the last CTA, the ticket before the reads of everybody's rows)
+    dbg_mark(a.dbg, 14);
+    if (warp == 0) {
+        __syncwarp();
+        if (lane == 0) {
+            unsigned int prev;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(a.ticket) : "memory");
+            *is_last = (prev == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    dbg_mark(a.dbg, 5);
+    if (*is_last) {
+        stream_finalize<T>(a, N, P, gridDim.x, sh, scratch);
+        dbg_mark(a.dbg, 6);
     }
 }
 
@@ -140,16 +323,19 @@ stream_kernel(const StreamArgs<T> a)
     __shared__ double part[NW * NACC];
     __shared__ double bu[NACC];
     __shared__ double rinv_s[N * N];
-    __shared__ double fin_scratch[(NW + 1) * NVR + 64];
+    __shared__ double fin_scratch[FIN_SCRATCH];
+    __shared__ double wsum_s[NW];
+    __shared__ double gv_s[CT * (N * (N + 1) / 2 + P)];
+    __shared__ double fin_sh[64];
     __shared__ int is_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld, S = a.S, nst = a.nstages;
     const size_t stage_elems = (size_t)CT * ld;
     T *tiles = reinterpret_cast<T *>(smem_raw);
+    T *Cout = stream_cout(a);
 
-    const int ntiles = (S + CT - 1) / CT;
-    const int my = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my = a.tiles_base + ((int)blockIdx.x < a.tiles_rem ? 1 : 0);
 
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) mbar_init(&full_bar[s], 1);
@@ -157,18 +343,21 @@ stream_kernel(const StreamArgs<T> a)
     }
     __syncthreads();
 
-    auto issue = [&](int i) {
-        const int tile = blockIdx.x + i * gridDim.x;
+    // producer state (thread 0): next tile to fetch and the stage it goes to
+    int next_i = 0, next_st = 0;
+    auto issue = [&]() {
+        const int tile = blockIdx.x + next_i * gridDim.x;
         const int col0 = tile * CT;
         const int nc = min(CT, S - col0);
         const uint32_t bytes = (uint32_t)((size_t)nc * ld * sizeof(T));
-        const int st = i % nst;
-        mbar_arrive_expect_tx(&full_bar[st], bytes);
-        bulk_copy_g2s(tiles + (size_t)st * stage_elems, a.Y + (size_t)col0 * ld, bytes, &full_bar[st]);
+        mbar_arrive_expect_tx(&full_bar[next_st], bytes);
+        bulk_copy_g2s(tiles + (size_t)next_st * stage_elems, a.Y + (size_t)col0 * ld, bytes, &full_bar[next_st]);
+        ++next_i;
+        if (++next_st == nst) next_st = 0;
     };
     // the observations do not depend on the panel: start fetching immediately
     if (tid == 0)
-        for (int i = 0; i < nst && i < my; ++i) issue(i);
+        for (int i = 0; i < nst && i < my; ++i) issue();
 
     // this thread's slice of the panel [Q | E], kept in registers
     T pan[CHUNKS][VEC][NPV];
@@ -183,7 +372,7 @@ stream_kernel(const StreamArgs<T> a)
 #pragma unroll
             for (int v = 0; v < VEC; ++v) tmp[v] = (T)0;
             if (valid[ch]) {
-                const T *src = (k < N) ? (a.Pq + (size_t)k * ld + r0) : (a.Pe + (size_t)(k - N) * ld + r0);
+                const T *src = a.Pq + (size_t)k * a.ldp + r0;
                 vec_unpack<T>(*reinterpret_cast<const VecT *>(src), tmp);
             }
 #pragma unroll
@@ -200,14 +389,15 @@ stream_kernel(const StreamArgs<T> a)
 #pragma unroll
     for (int e = 0; e < (P > 0 ? P : 1); ++e) Vacc[e] = 0.0;
 
+    int st = 0;
+    uint32_t parity = 0;
     for (int i = 0; i < my; ++i) {
-        const int st = i % nst;
-        const uint32_t parity = (uint32_t)((i / nst) & 1);
         const int tile = blockIdx.x + i * gridDim.x;
         const int col0 = tile * CT;
         const int nc = min(CT, S - col0);
         const T *tp = tiles + (size_t)st * stage_elems;
         mbar_wait(&full_bar[st], parity);
+        if (++st == nst) { st = 0; parity ^= 1u; }
 
         // ---- phase 1: partial dot products of the panel with CT columns ----
         T acc[CT][NPV];
@@ -236,33 +426,14 @@ stream_kernel(const StreamArgs<T> a)
         for (int c = 0; c < CT; ++c)
 #pragma unroll
             for (int k = 0; k < NPV; ++k) red[c * NPV + k] = (double)acc[c][k];
-        {
-            int cnt = NACC;
-#pragma unroll
-            for (int h = 0; h < LOG2CT; ++h) {
-                const int off = 16 >> h;
-                const int half = cnt / 2;
-                const bool up = (lane & off) != 0;
-#pragma unroll
-                for (int t = 0; t < half; ++t) {
-                    const double send = up ? red[t] : red[t + half];
-                    const double keep = up ? red[t + half] : red[t];
-                    red[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-                cnt = half;
-            }
-#pragma unroll
-            for (int off = (16 >> LOG2CT); off > 0; off >>= 1)
-#pragma unroll
-                for (int k = 0; k < NPV; ++k) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
-        }
+        warp_fold<NACC, NACC, 16, NPV>(red, lane);
         if ((lane & ((32 >> LOG2CT) - 1)) == 0) {
             const int c = lane >> (5 - LOG2CT);
 #pragma unroll
             for (int k = 0; k < NPV; ++k) part[warp * NACC + c * NPV + k] = red[k];
         }
         __syncthreads(); // (A) every thread is past phase 2 of the previous tile
-        if (tid == 0 && i >= 1 && (i - 1 + nst) < my) issue(i - 1 + nst); // refill the stage tile i-1 used
+        if (tid == 0 && i >= 1 && next_i < my) issue(); // refill the stage tile i-1 used
         if (tid < NACC) {
             double s = 0.0;
 #pragma unroll
@@ -280,7 +451,7 @@ stream_kernel(const StreamArgs<T> a)
 #pragma unroll
                 for (int c2 = r; c2 < N; ++c2) s += rinv_s[c2 * N + r] * bu[tid * NPV + c2];
                 coef[r] = s;
-                a.Cout[(size_t)(col0 + tid) * N + r] = (T)s;
+                Cout[(size_t)(col0 + tid) * N + r] = (T)s;
             }
             int gi = 0;
 #pragma unroll
@@ -325,27 +496,8 @@ stream_kernel(const StreamArgs<T> a)
     }
 
     // ---- CTA partial -> global, last CTA folds -------------------------------
-    {
-        double fin[NVR];
-        fin[0] = rn2;
-#pragma unroll
-        for (int t = 0; t < N * (N + 1) / 2; ++t) fin[1 + t] = (tid < CT) ? Gacc[t] : 0.0;
-#pragma unroll
-        for (int e = 0; e < P; ++e) fin[1 + N * (N + 1) / 2 + e] = (tid < CT) ? Vacc[e] : 0.0;
-        block_sum<NVR>(fin, fin_scratch);
-        if (tid == 0) {
-#pragma unroll
-            for (int t = 0; t < NVR; ++t) a.partials[(size_t)blockIdx.x * a.red_stride + t] = fin[t];
-            __threadfence();
-            const unsigned int prev = atomicAdd(a.ticket, 1u);
-            is_last = (prev == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            stream_finalize<T>(a, N, P, gridDim.x, fin_scratch);
-        }
-    }
+    __syncthreads();
+    cta_publish<T, N, P, CT, NW>(a, rn2, Gacc, Vacc, wsum_s, gv_s, fin_sh, fin_scratch, &is_last);
 }
 
 // -----------------------------------------------------------------------------
@@ -362,11 +514,12 @@ stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m)
     constexpr int NVMAX = 1 + VP_MAX_N * (VP_MAX_N + 1) / 2 + VP_MAX_P;
     __shared__ double acc_s[NVMAX];
     __shared__ double rinv_s[VP_MAX_N * VP_MAX_N];
-    __shared__ double fin_scratch[64 + NVMAX];
+    __shared__ double fin_scratch[FIN_SCRATCH];
+    __shared__ double fin_sh[64];
     __shared__ int is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld;
-    const int nv = red_count(n, p);
+    T *Cout = stream_cout(a);
     for (int t = tid; t < NVMAX; t += THREADS) acc_s[t] = 0.0;
     for (int t = tid; t < VP_MAX_N * VP_MAX_N; t += THREADS) rinv_s[t] = a.small->Rinv[t];
     __syncthreads();
@@ -380,10 +533,10 @@ stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m)
             const double yi = (double)y[i];
 #pragma unroll
             for (int k = 0; k < VP_MAX_N; ++k)
-                if (k < n) d[k] += (double)a.Pq[(size_t)k * ld + i] * yi;
+                if (k < n) d[k] += (double)a.Pq[(size_t)k * a.ldp + i] * yi;
 #pragma unroll
             for (int e = 0; e < VP_MAX_P; ++e)
-                if (e < p) d[VP_MAX_N + e] += (double)a.Pe[(size_t)e * ld + i] * yi;
+                if (e < p) d[VP_MAX_N + e] += (double)a.Pe[(size_t)e * a.ldp + i] * yi;
         }
 #pragma unroll
         for (int k = 0; k < VP_MAX_N + VP_MAX_P; ++k) d[k] = warp_sum(d[k]);
@@ -392,7 +545,7 @@ stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m)
             double r = (double)y[i];
 #pragma unroll
             for (int k = 0; k < VP_MAX_N; ++k)
-                if (k < n) r -= (double)a.Pq[(size_t)k * ld + i] * d[k];
+                if (k < n) r -= (double)a.Pq[(size_t)k * a.ldp + i] * d[k];
             rs += r * r;
         }
         rs = warp_sum(rs);
@@ -402,7 +555,7 @@ stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m)
                 double sacc = 0.0;
                 for (int c2 = r; c2 < n; ++c2) sacc += rinv_s[c2 * VP_MAX_N + r] * d[c2];
                 coef[r] = sacc;
-                a.Cout[(size_t)s * n + r] = (T)sacc;
+                Cout[(size_t)s * n + r] = (T)sacc;
             }
             atomicAdd(&acc_s[0], rs);
             for (int r = 0; r < n; ++r)
@@ -412,17 +565,7 @@ stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m)
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        for (int t = 0; t < nv; ++t) a.partials[(size_t)blockIdx.x * a.red_stride + t] = acc_s[t];
-        __threadfence();
-        const unsigned int prev = atomicAdd(a.ticket, 1u);
-        is_last = (prev == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        stream_finalize<T>(a, n, p, gridDim.x, fin_scratch);
-    }
+    stream_epilogue<T>(a, n, p, acc_s, fin_sh, fin_scratch, &is_last);
 }
 
 } // namespace vp

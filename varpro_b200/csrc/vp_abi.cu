@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/varpro_b200.h"
@@ -17,7 +18,9 @@
 #include "device_common.cuh"
 #include "lm_step.cuh"
 #include "panel_kernel.cuh"
+#include "panel_kernel_hh.cuh"
 #include "stream_kernel.cuh"
+#include "stream_kernel_dmma.cuh"
 
 using namespace vp;
 
@@ -49,8 +52,14 @@ struct vp_problem {
     void *w_dev = nullptr; // m or null
     double svd_eps = 0.0;
     double alpha[VP_MAX_Q] = {0};
-    double *alpha_dev = nullptr;
-    void *Pq = nullptr, *Pe = nullptr;
+    double *alpha_dev = nullptr; // = &fit_dev->st.x_trial[0]: the parameters the next evaluation is made at
+    FitDevice *fit_dev = nullptr; // device-resident LM state (graph path)
+    FitDevice *fit_host = nullptr; // pinned staging copy
+    cudaGraph_t fit_graph = nullptr;
+    cudaGraphExec_t fit_exec = nullptr;
+    cudaGraphConditionalHandle fit_cond = 0;
+    void *Pq = nullptr; // panel [Q | E | 0], (n+p+1) columns of ldp rows
+    int ldp = 0;
     PanelSmall *small = nullptr;
     void *C[2] = {nullptr, nullptr}; // coefficient buffers (n x S); C[cur] belongs to `alpha`
     int cur = 0;
@@ -62,10 +71,15 @@ struct vp_problem {
     EvalOut *out_host = nullptr; // pinned
     double *alpha_stage = nullptr; // pinned
     double *phi_scratch = nullptr; // m x n (best_fit)
+    unsigned long long *dbg = nullptr; // optional in-kernel timeline (vp_debug_timeline)
     LmEval eval{};                 // reduction at `alpha`
     bool cached = false;
     // streaming-kernel launch plan
     int plan_kind = -1; // index into the dispatch table, -1 = generic
+    int plan_dmma = -1; // index into the DMMA dispatch table (fp64 fast path), -1 = not used
+    int plan_lds = 0;   // padded shared-memory column stride of the DMMA path
+    int plan_rows = 0;  // rows the chosen kernel touches (panel must be zero-padded that far)
+    int plan_ct = 1;    // columns per tile
     int plan_grid = 0, plan_nst = 0;
     size_t plan_smem = 0;
 };
@@ -266,6 +280,21 @@ static const StreamKernelEntry g_stream_kernels[] = {
 };
 static const int g_num_stream_kernels = (int)(sizeof(g_stream_kernels) / sizeof(g_stream_kernels[0]));
 
+struct DmmaKernelEntry {
+    int n, p, ksteps, nwarps, exact;
+    const void *fn;
+};
+#define VP_DK(N, P, KS, NW) \
+    {N, P, KS, NW, 1, (const void *)&stream_kernel_dmma<N, P, KS, NW, true>}, \
+    {N, P, KS, NW, 0, (const void *)&stream_kernel_dmma<N, P, KS, NW, false>}
+#define VP_DK_SHAPES(N, P) VP_DK(N, P, 8, 4), VP_DK(N, P, 16, 8), VP_DK(N, P, 32, 8), VP_DK(N, P, 32, 16)
+static const DmmaKernelEntry g_dmma_kernels[] = {
+    VP_DK_SHAPES(3, 2), // double exponential + offset (benches, C1/C2/C5)
+    VP_DK_SHAPES(3, 3), // triple exponential
+    VP_DK_SHAPES(2, 4), // O'Leary exp*cos example
+};
+static const int g_num_dmma_kernels = (int)(sizeof(g_dmma_kernels) / sizeof(g_dmma_kernels[0]));
+
 static int env_int(const char *name, int dflt)
 {
     const char *s = getenv(name);
@@ -283,8 +312,56 @@ static int plan_stream(vp_problem *pr)
     const int force_generic = env_int("VP_STREAM_GENERIC", 0);
     const size_t es = esize(mo->dtype);
     pr->plan_kind = -1;
+    pr->plan_dmma = -1;
+    const char *which = getenv("VP_STREAM_KERNEL"); // "dmma" (default for fp64), "simt", "generic"
+    const bool allow_dmma = !force_generic && mo->dtype == VP_F64 && !(which && (!strcmp(which, "simt") || !strcmp(which, "generic")));
+    if (which && !strcmp(which, "generic")) { /* handled below */ }
+    if (allow_dmma) {
+        int lds = mo->ld;
+        while (lds % 16 != 4) lds += 2; // conflict-free fragment loads (see stream_kernel_dmma.cuh)
+        int pick = -1;
+        for (int i = 0; i < g_num_dmma_kernels; ++i) {
+            const DmmaKernelEntry &k = g_dmma_kernels[i];
+            if (k.n != md.n || k.p != md.p) continue;
+            const int rows = 4 * k.ksteps * k.nwarps;
+            if (rows < mo->ld) continue;
+            if (k.exact != (rows <= lds ? 1 : 0)) continue;
+            if (pick < 0 || rows < 4 * g_dmma_kernels[pick].ksteps * g_dmma_kernels[pick].nwarps) pick = i;
+        }
+        if (pick >= 0) {
+            const DmmaKernelEntry &k = g_dmma_kernels[pick];
+            const size_t stage_bytes = (size_t)DMMA_CT * lds * sizeof(double);
+            cudaFuncAttributes fa{};
+            VP_CUDA(ctx, cudaFuncGetAttributes(&fa, k.fn));
+            const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
+            int nst = (int)(budget / stage_bytes);
+            if (nst > STREAM_MAX_STAGES) nst = STREAM_MAX_STAGES;
+            const int max_st = env_int("VP_STREAM_STAGES", 0);
+            if (max_st >= 2 && nst > max_st) nst = max_st;
+            if (nst >= 2) {
+                const size_t smem = (size_t)nst * stage_bytes;
+                VP_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int occ_real = 0;
+                VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k.fn, k.nwarps * 32, smem));
+                if (occ_real >= 1) {
+                    const long long ntiles = (pr->S + DMMA_CT - 1) / DMMA_CT;
+                    long long grid = (long long)ctx->sm_count * occ_real;
+                    if (grid > ntiles) grid = ntiles;
+                    if (grid > pr->max_grid) grid = pr->max_grid;
+                    pr->plan_dmma = pick;
+                    pr->plan_lds = lds;
+                    pr->plan_rows = 4 * k.ksteps * k.nwarps;
+                    pr->plan_ct = DMMA_CT;
+                    pr->plan_grid = (int)grid;
+                    pr->plan_nst = nst;
+                    pr->plan_smem = smem;
+                    return VP_OK;
+                }
+            }
+        }
+    }
     int best = -1;
-    if (!force_generic) {
+    if (!force_generic && !(which && !strcmp(which, "generic"))) {
         for (int i = 0; i < g_num_stream_kernels; ++i) {
             const StreamKernelEntry &k = g_stream_kernels[i];
             if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p) continue;
@@ -327,6 +404,8 @@ static int plan_stream(vp_problem *pr)
                     if (grid > ntiles) grid = ntiles;
                     if (grid > pr->max_grid) grid = pr->max_grid;
                     pr->plan_kind = best;
+                    pr->plan_rows = k.threads * k.chunks * vec_of(mo->dtype);
+                    pr->plan_ct = k.ct;
                     pr->plan_grid = (int)grid;
                     pr->plan_nst = nst;
                     pr->plan_smem = smem;
@@ -342,8 +421,37 @@ static int plan_stream(vp_problem *pr)
     pr->plan_grid = (int)(grid < cap ? grid : cap);
     pr->plan_nst = 0;
     pr->plan_smem = 0;
+    pr->plan_rows = mo->ld;
+    pr->plan_ct = 1;
     return VP_OK;
 }
+
+// Householder panel kernel instantiations: (n, p) x rows-per-thread, 512 threads
+template <typename T>
+struct PanelHHEntry {
+    int n, p, rpt;
+    void (*fn)(ModelDesc, const T *, const T *, const double *, double, int, T *, PanelSmall *, unsigned long long *);
+};
+constexpr int PANEL_HH_THREADS = 512;
+#define VP_PK(T, N, P, RPT) {N, P, RPT, &panel_kernel_hh<T, N, P, RPT, PANEL_HH_THREADS>}
+#define VP_PK_SHAPES(T, N, P) VP_PK(T, N, P, 1), VP_PK(T, N, P, 2), VP_PK(T, N, P, 4), VP_PK(T, N, P, 8)
+template <typename T> struct PanelHHTable;
+template <> struct PanelHHTable<double> {
+    static const PanelHHEntry<double> *get(int &count)
+    {
+        static const PanelHHEntry<double> t[] = {VP_PK_SHAPES(double, 3, 2), VP_PK_SHAPES(double, 3, 3), VP_PK_SHAPES(double, 2, 4)};
+        count = (int)(sizeof(t) / sizeof(t[0]));
+        return t;
+    }
+};
+template <> struct PanelHHTable<float> {
+    static const PanelHHEntry<float> *get(int &count)
+    {
+        static const PanelHHEntry<float> t[] = {VP_PK_SHAPES(float, 3, 2)};
+        count = (int)(sizeof(t) / sizeof(t[0]));
+        return t;
+    }
+};
 
 template <typename T>
 static int launch_panel_t(vp_problem *pr)
@@ -351,6 +459,21 @@ static int launch_panel_t(vp_problem *pr)
     vp_ctx *ctx = pr->ctx;
     vp_model *mo = pr->model;
     const ModelDesc &md = mo->md;
+    unsigned long long *dbg = pr->dbg ? pr->dbg + (size_t)pr->max_grid * VP_DBG_SLOTS : nullptr;
+    // fast path: register-resident Householder panel
+    if (!env_int("VP_PANEL_GENERIC", 0)) {
+        int count = 0;
+        const PanelHHEntry<T> *tab = PanelHHTable<T>::get(count);
+        for (int i = 0; i < count; ++i) {
+            if (tab[i].n != md.n || tab[i].p != md.p || (long long)tab[i].rpt * PANEL_HH_THREADS < md.m) continue;
+            tab[i].fn<<<1, PANEL_HH_THREADS, 0, ctx->stream>>>(md, (const T *)mo->x_dev, (const T *)pr->w_dev, pr->alpha_dev,
+                                                             pr->svd_eps, pr->ldp, (T *)pr->Pq, pr->small, dbg);
+            ctx->launches++;
+            VP_CUDA(ctx, cudaGetLastError());
+            return VP_OK;
+        }
+    }
+    // generic path: CGS2 round interpreter with the panel in shared memory
     int threads = PANEL_THREADS;
     if (md.m < threads) threads = ((md.m + 31) / 32) * 32;
     const size_t smem = sizeof(double) * ((size_t)(md.n + md.p) * md.m + (size_t)(threads / 32 + 1) * 8 + 64);
@@ -362,26 +485,40 @@ static int launch_panel_t(vp_problem *pr)
         configured = smem;
     }
     panel_kernel<T><<<1, threads, smem, ctx->stream>>>(md, (const T *)mo->x_dev, (const T *)pr->w_dev, pr->alpha_dev,
-                                                       pr->svd_eps, mo->ld, (T *)pr->Pq, (T *)pr->Pe, pr->small);
+                                                       pr->svd_eps, pr->ldp, (T *)pr->Pq, pr->small, dbg);
     ctx->launches++;
     VP_CUDA(ctx, cudaGetLastError());
     return VP_OK;
 }
 
 template <typename T>
-static int launch_stream_t(vp_problem *pr, int cdst)
+static int launch_stream_t(vp_problem *pr, int cdst, bool graph_mode)
 {
     vp_ctx *ctx = pr->ctx;
     vp_model *mo = pr->model;
     const ModelDesc &md = mo->md;
     StreamArgs<T> a{};
     a.Y = (const T *)pr->Yw; a.ld = mo->ld; a.S = (int)pr->S;
-    a.Pq = (const T *)pr->Pq; a.Pe = (const T *)pr->Pe; a.small = pr->small;
-    a.Cout = (T *)pr->C[cdst];
+    a.Pq = (const T *)pr->Pq; a.Pe = (const T *)pr->Pq + (size_t)md.n * pr->ldp; a.ldp = pr->ldp; a.small = pr->small;
+    {
+        const long long ntiles = (pr->S + pr->plan_ct - 1) / pr->plan_ct;
+        a.tiles_base = (int)(ntiles / pr->plan_grid);
+        a.tiles_rem = (int)(ntiles % pr->plan_grid);
+    }
+    a.C0 = (T *)pr->C[0]; a.C1 = (T *)pr->C[1]; a.cdst = cdst;
+    a.fit = graph_mode ? pr->fit_dev : nullptr;
+    a.cond = graph_mode ? (unsigned long long)pr->fit_cond : 0ull;
     a.partials = pr->partials; a.red_stride = pr->red_stride; a.ticket = pr->ticket; a.out = pr->out_dev;
-    a.nstages = pr->plan_nst; a.q = md.q;
+    a.nstages = pr->plan_nst; a.q = md.q; a.dbg = pr->dbg;
     for (int e = 0; e < VP_MAX_P; ++e) { a.e_basis[e] = md.e_basis[e]; a.e_param[e] = md.e_param[e]; }
-    if (pr->plan_kind >= 0) {
+    if (pr->plan_dmma >= 0) {
+        if constexpr (std::is_same<T, double>::value) {
+            const DmmaKernelEntry &k = g_dmma_kernels[pr->plan_dmma];
+            int lds = pr->plan_lds;
+            void *args[] = {(void *)&a, (void *)&lds};
+            VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(pr->plan_grid), dim3(k.nwarps * 32), args, pr->plan_smem, ctx->stream));
+        }
+    } else if (pr->plan_kind >= 0) {
         const StreamKernelEntry &k = g_stream_kernels[pr->plan_kind];
         void *args[] = {(void *)&a};
         VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(pr->plan_grid), dim3(k.threads), args, pr->plan_smem, ctx->stream));
@@ -397,9 +534,9 @@ static int launch_panel(vp_problem *pr)
 {
     return pr->model->dtype == VP_F32 ? launch_panel_t<float>(pr) : launch_panel_t<double>(pr);
 }
-static int launch_stream(vp_problem *pr, int cdst)
+static int launch_stream(vp_problem *pr, int cdst, bool graph_mode = false)
 {
-    return pr->model->dtype == VP_F32 ? launch_stream_t<float>(pr, cdst) : launch_stream_t<double>(pr, cdst);
+    return pr->model->dtype == VP_F32 ? launch_stream_t<float>(pr, cdst, graph_mode) : launch_stream_t<double>(pr, cdst, graph_mode);
 }
 static int launch_eval(vp_problem *pr, int cdst)
 {
@@ -473,8 +610,6 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     } while (0)
 
     VP_TRY(cudaMalloc(&pr->Yw, es * (size_t)ld * S));
-    VP_TRY(cudaMalloc(&pr->Pq, es * (size_t)ld * md.n));
-    VP_TRY(cudaMalloc(&pr->Pe, es * (size_t)ld * (md.p > 0 ? md.p : 1)));
     VP_TRY(cudaMalloc(&pr->small, sizeof(PanelSmall)));
     VP_TRY(cudaMalloc(&pr->C[0], es * (size_t)md.n * S));
     VP_TRY(cudaMalloc(&pr->C[1], es * (size_t)md.n * S));
@@ -482,7 +617,10 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     VP_TRY(cudaMalloc(&pr->ticket, sizeof(unsigned int)));
     VP_TRY(cudaMemsetAsync(pr->ticket, 0, sizeof(unsigned int), ctx->stream));
     VP_TRY(cudaMalloc(&pr->out_dev, sizeof(EvalOut)));
-    VP_TRY(cudaMalloc(&pr->alpha_dev, sizeof(double) * VP_MAX_Q));
+    VP_TRY(cudaMalloc(&pr->fit_dev, sizeof(FitDevice)));
+    VP_TRY(cudaMemsetAsync(pr->fit_dev, 0, sizeof(FitDevice), ctx->stream));
+    VP_TRY(cudaMallocHost(&pr->fit_host, sizeof(FitDevice)));
+    pr->alpha_dev = &pr->fit_dev->st.x_trial[0];
     VP_TRY(cudaMalloc(&pr->phi_scratch, sizeof(double) * (size_t)m * md.n));
     VP_TRY(cudaMallocHost(&pr->out_host, sizeof(EvalOut)));
     VP_TRY(cudaMallocHost(&pr->alpha_stage, sizeof(double) * VP_MAX_Q));
@@ -509,6 +647,13 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
 #undef VP_TRY
     int rc = plan_stream(pr);
     if (rc != VP_OK) { vp_problem_destroy(pr); return rc; }
+    {
+        int ldp = pr->plan_rows > ld ? pr->plan_rows : ld;
+        if (pr->plan_lds > ldp) ldp = pr->plan_lds;
+        pr->ldp = (ldp + 3) / 4 * 4;
+        cudaError_t e = cudaMalloc(&pr->Pq, es * (size_t)pr->ldp * (md.n + md.p + 1));
+        if (e != cudaSuccess) { vp_problem_destroy(pr); return fail(ctx, VP_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }
+    }
     // first evaluation at the initial guess (src/problem/builder.rs:321)
     for (int k = 0; k < md.q; ++k) pr->alpha[k] = alpha0[k];
     rc = evaluate_sync(pr, pr->alpha, pr->cur);
@@ -536,9 +681,12 @@ extern "C" int vp_problem_destroy(vp_problem *pr)
     if (!pr) return VP_OK;
     cudaSetDevice(pr->ctx->device);
     cudaStreamSynchronize(pr->ctx->stream);
-    cudaFree(pr->Yw); cudaFree(pr->w_dev); cudaFree(pr->Pq); cudaFree(pr->Pe); cudaFree(pr->small);
+    cudaFree(pr->Yw); cudaFree(pr->w_dev); cudaFree(pr->Pq); cudaFree(pr->small);
     cudaFree(pr->C[0]); cudaFree(pr->C[1]); cudaFree(pr->partials); cudaFree(pr->ticket);
-    cudaFree(pr->out_dev); cudaFree(pr->alpha_dev); cudaFree(pr->phi_scratch);
+    cudaFree(pr->out_dev); cudaFree(pr->fit_dev); cudaFree(pr->phi_scratch); cudaFree(pr->dbg);
+    if (pr->fit_exec) cudaGraphExecDestroy(pr->fit_exec);
+    if (pr->fit_graph) cudaGraphDestroy(pr->fit_graph);
+    if (pr->fit_host) cudaFreeHost(pr->fit_host);
     if (pr->out_host) cudaFreeHost(pr->out_host);
     if (pr->alpha_stage) cudaFreeHost(pr->alpha_stage);
     delete pr;
@@ -614,11 +762,11 @@ static int materialise_t(vp_problem *pr, int what, void *out_host)
     VP_CUDA(ctx, cudaMalloc(&buf, sizeof(T) * count));
     const int blocks = ctx->sm_count * 8;
     if (what == 0) {
-        residuals_kernel<T><<<blocks, 256, 0, ctx->stream>>>((const T *)pr->Yw, mo->ld, md.m, (int)pr->S, md.n,
+        residuals_kernel<T><<<blocks, 256, 0, ctx->stream>>>((const T *)pr->Yw, mo->ld, pr->ldp, md.m, (int)pr->S, md.n,
                                                              (const T *)pr->Pq, buf);
     } else if (what == 1) {
-        jacobian_kernel<T><<<blocks, 256, 0, ctx->stream>>>(mo->ld, md.m, (int)pr->S, md.n, md.p, md.q,
-                                                            (const T *)pr->Pe, (const T *)pr->C[pr->cur], md, buf);
+        jacobian_kernel<T><<<blocks, 256, 0, ctx->stream>>>(pr->ldp, md.m, (int)pr->S, md.n, md.p, md.q,
+                                                            (const T *)pr->Pq + (size_t)md.n * pr->ldp, (const T *)pr->C[pr->cur], md, buf);
     } else {
         phi_kernel<T><<<32, 256, 0, ctx->stream>>>(md, (const T *)mo->x_dev, pr->alpha_dev, pr->phi_scratch);
         ctx->launches++;
@@ -660,13 +808,46 @@ extern "C" int vp_linear_coefficients(vp_problem *pr, void *out_host)
     return VP_OK;
 }
 
+// Build (once per problem) the CUDA graph of a whole fit: a conditional WHILE node whose body
+// is one evaluation, K1 (panel at the trial parameters) -> K2 (streaming reduce; its last CTA
+// advances the lmder state machine on the device and sets the loop condition).
+static int ensure_fit_graph(vp_problem *pr)
+{
+    if (pr->fit_exec) return VP_OK;
+    vp_ctx *ctx = pr->ctx;
+    if (env_int("VP_DBG_FIT", 0) && !pr->dbg) {
+        const size_t n = ((size_t)pr->max_grid + 1) * VP_DBG_SLOTS;
+        VP_CUDA(ctx, cudaMalloc(&pr->dbg, n * sizeof(unsigned long long)));
+        VP_CUDA(ctx, cudaMemset(pr->dbg, 0, n * sizeof(unsigned long long)));
+    }
+    VP_CUDA(ctx, cudaGraphCreate(&pr->fit_graph, 0));
+    VP_CUDA(ctx, cudaGraphConditionalHandleCreate(&pr->fit_cond, pr->fit_graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = pr->fit_cond;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t node;
+    VP_CUDA(ctx, cudaGraphAddNode(&node, pr->fit_graph, nullptr, 0, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    VP_CUDA(ctx, cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    const int64_t launches_before = ctx->launches;
+    int rc = launch_panel(pr);
+    if (rc == VP_OK) rc = launch_stream(pr, 0, /*graph_mode=*/true);
+    ctx->launches = launches_before; // captured, not launched
+    cudaGraph_t captured = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &captured);
+    if (rc != VP_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    VP_CUDA(ctx, cudaGraphInstantiate(&pr->fit_exec, pr->fit_graph, 0));
+    return VP_OK;
+}
+
 // ----------------------------------------------------------------------------
 // LevMarSolver::fit  (src/solvers/levmar/mod.rs:238-254)
 // ----------------------------------------------------------------------------
 extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *rep)
 {
     if (!pr || !rep) return VP_ERR_INVALID_ARGUMENT;
-    vp_ctx *ctx = pr->ctx;
     const int q = pr->model->md.q;
     const double eps = pr->model->dtype == VP_F32 ? (double)FLT_EPSILON : DBL_EPSILON;
     LmConfig cfg;
@@ -692,20 +873,48 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
     }
     // the evaluation at the current parameters is cached (builder / set_params)
     bool more = lm_advance(st, cfg, pr->eval);
+    const char *mode = getenv("VP_FIT_MODE"); // "graph" (default) or "host"
+    if (more && !(mode && !strcmp(mode, "host"))) {
+        // ---- device-driven loop: one CUDA graph launch per fit ------------------------
+        vp_ctx *ctx = pr->ctx;
+        cudaSetDevice(ctx->device);
+        int rc = ensure_fit_graph(pr);
+        if (rc != VP_OK) return rc;
+        FitDevice *fh = pr->fit_host;
+        memset(fh, 0, sizeof(FitDevice));
+        fh->st = st; fh->cfg = cfg; fh->accepted = pr->eval; fh->cur = pr->cur; fh->evals = 0;
+        VP_CUDA(ctx, cudaMemcpyAsync(pr->fit_dev, fh, sizeof(FitDevice), cudaMemcpyHostToDevice, ctx->stream));
+        VP_CUDA(ctx, cudaGraphLaunch(pr->fit_exec, ctx->stream));
+        VP_CUDA(ctx, cudaMemcpyAsync(fh, pr->fit_dev, sizeof(FitDevice), cudaMemcpyDeviceToHost, ctx->stream));
+        VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        st = fh->st;
+        pr->cur = fh->cur;
+        pr->eval = fh->accepted;
+        for (int k = 0; k < q; ++k) pr->alpha[k] = st.x[k];
+        ctx->launches += 2 * (int64_t)fh->evals;
+        if (env_int("VP_TRACE", 0))
+            for (int i = 0; i < fh->evals && i < 48; ++i)
+                fprintf(stderr, "[vp_fit graph] eval %d fnorm_trial=%.6e par=%.3e delta=%.3e acc=%d\n", i + 2, fh->trace[4 * i],
+                        fh->trace[4 * i + 1], fh->trace[4 * i + 2], (int)fh->trace[4 * i + 3]);
+        more = false;
+    }
     while (more) {
+        // ---- host-driven loop (VP_FIT_MODE=host): one synchronisation per evaluation ---
         const int dst = pr->cur ^ 1;
         int rc = evaluate_sync(pr, st.x_trial, dst);
         if (rc != VP_OK) return rc;
         LmEval ev;
         evalout_to_lm(*pr->out_host, q, ev);
         more = lm_advance(st, cfg, ev);
+        if (env_int("VP_TRACE", 0))
+            fprintf(stderr, "[vp_fit] nfev=%d fnorm_trial=%.6e fnorm=%.6e par=%.3e delta=%.3e acc=%d x_trial=(%.15g, %.15g) g=(%.3e,%.3e)\n",
+                    st.nfev, sqrt(ev.rnorm2), st.fnorm, st.par, st.delta, st.last_accepted, st.x_trial[0], st.x_trial[1], ev.g[0], ev.g[1]);
         if (st.last_accepted) {
             pr->cur = dst;
             pr->eval = ev;
             for (int k = 0; k < q; ++k) pr->alpha[k] = st.x[k];
         }
     }
-    (void)ctx;
     rep->termination = st.termination;
     rep->number_of_evaluations = st.nfev;
     rep->objective_function = 0.5 * st.fnorm * st.fnorm;
@@ -720,36 +929,43 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
 extern "C" int vp_profile_evaluation(vp_problem *pr, int iters, int64_t flush_bytes, double *panel_us,
                                      double *stream_us, int64_t *stream_grid, int64_t *stream_smem)
 {
-    if (!pr || iters <= 0) return VP_ERR_INVALID_ARGUMENT;
+    if (!pr || iters <= 0 || iters > 4096) return VP_ERR_INVALID_ARGUMENT;
     vp_ctx *ctx = pr->ctx;
     cudaSetDevice(ctx->device);
-    cudaEvent_t e0, e1, e2;
-    VP_CUDA(ctx, cudaEventCreate(&e0));
-    VP_CUDA(ctx, cudaEventCreate(&e1));
-    VP_CUDA(ctx, cudaEventCreate(&e2));
+    std::vector<cudaEvent_t> ev(3 * (size_t)iters);
+    for (auto &e : ev) VP_CUDA(ctx, cudaEventCreate(&e));
     void *flush = nullptr;
     if (flush_bytes > 0) VP_CUDA(ctx, cudaMalloc(&flush, (size_t)flush_bytes));
     const int q = pr->model->md.q;
     for (int k = 0; k < q; ++k) pr->alpha_stage[k] = pr->alpha[k];
     if (q > 0)
         VP_CUDA(ctx, cudaMemcpyAsync(pr->alpha_dev, pr->alpha_stage, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
-    double tp = 0, ts = 0;
     int rc = VP_OK;
+    // warm-up: keep the device busy long enough for the clocks to ramp up
+    for (int it = 0; it < 64 && rc == VP_OK; ++it) {
+        rc = launch_panel(pr);
+        if (rc == VP_OK) rc = launch_stream(pr, pr->cur ^ 1);
+    }
+    // timed launches are enqueued back to back; no host synchronisation in between
     for (int it = 0; it < iters && rc == VP_OK; ++it) {
         if (flush) cudaMemsetAsync(flush, it & 0xff, (size_t)flush_bytes, ctx->stream);
-        cudaEventRecord(e0, ctx->stream);
+        cudaEventRecord(ev[3 * it + 0], ctx->stream);
         rc = launch_panel(pr);
-        cudaEventRecord(e1, ctx->stream);
+        cudaEventRecord(ev[3 * it + 1], ctx->stream);
         if (rc == VP_OK) rc = launch_stream(pr, pr->cur ^ 1);
-        cudaEventRecord(e2, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, e0, e1);
-        cudaEventElapsedTime(&b, e1, e2);
-        tp += a; ts += b;
+        cudaEventRecord(ev[3 * it + 2], ctx->stream);
     }
+    cudaStreamSynchronize(ctx->stream);
+    double tp = 0, ts = 0;
+    if (rc == VP_OK)
+        for (int it = 0; it < iters; ++it) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ev[3 * it + 0], ev[3 * it + 1]);
+            cudaEventElapsedTime(&b, ev[3 * it + 1], ev[3 * it + 2]);
+            tp += a; ts += b;
+        }
     if (flush) cudaFree(flush);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    for (auto &e : ev) cudaEventDestroy(e);
     if (rc != VP_OK) return rc;
     if (panel_us) *panel_us = 1e3 * tp / iters;
     if (stream_us) *stream_us = 1e3 * ts / iters;
@@ -757,5 +973,42 @@ extern "C" int vp_profile_evaluation(vp_problem *pr, int iters, int64_t flush_by
     if (stream_smem) *stream_smem = (int64_t)pr->plan_smem;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, cudaGetErrorString(e));
+    return VP_OK;
+}
+
+// One evaluation with the in-kernel timeline enabled: out receives
+// (grid + 1) * VP_DBG_SLOTS %globaltimer stamps in ns (the last row is the panel
+// kernel's), relative to the smallest stamp. Diagnostics only.
+extern "C" int vp_debug_timeline(vp_problem *pr, long long *out, int64_t capacity, int64_t *grid_out)
+{
+    if (!pr || !out) return VP_ERR_INVALID_ARGUMENT;
+    vp_ctx *ctx = pr->ctx;
+    cudaSetDevice(ctx->device);
+    const size_t n = ((size_t)pr->max_grid + 1) * VP_DBG_SLOTS;
+    const bool read_only = pr->dbg != nullptr; // VP_DBG_FIT: stamps of the last evaluation of the last fit
+    if (!pr->dbg) VP_CUDA(ctx, cudaMalloc(&pr->dbg, n * sizeof(unsigned long long)));
+    int rc = VP_OK;
+    for (int it = 0; it < 3 && rc == VP_OK && !read_only; ++it) { // warm, then the recorded one
+        VP_CUDA(ctx, cudaMemsetAsync(pr->dbg, 0, n * sizeof(unsigned long long), ctx->stream));
+        rc = launch_panel(pr);
+        if (rc == VP_OK) rc = launch_stream(pr, pr->cur ^ 1);
+    }
+    std::vector<unsigned long long> h(n);
+    VP_CUDA(ctx, cudaMemcpyAsync(h.data(), pr->dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!read_only) {
+        cudaFree(pr->dbg);
+        pr->dbg = nullptr;
+    }
+    if (rc != VP_OK) return rc;
+    unsigned long long t0 = ~0ull;
+    for (auto v : h) if (v && v < t0) t0 = v;
+    const size_t rows = (size_t)pr->plan_grid;
+    size_t k = 0;
+    for (size_t b = 0; b <= rows && k + VP_DBG_SLOTS <= (size_t)capacity; ++b) {
+        const size_t src = (b < rows ? b : (size_t)pr->max_grid) * VP_DBG_SLOTS;
+        for (int s2 = 0; s2 < VP_DBG_SLOTS; ++s2) out[k++] = h[src + s2] ? (long long)(h[src + s2] - t0) : -1;
+    }
+    if (grid_out) *grid_out = pr->plan_grid;
     return VP_OK;
 }

@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/varpro_b200.h"
@@ -27,6 +28,16 @@ using namespace vp;
 // ----------------------------------------------------------------------------
 // handles
 // ----------------------------------------------------------------------------
+// Size-keyed free lists for device and pinned-host buffers: problems of the same shape are
+// created and destroyed per fit by callers that mirror the reference API (the builder produces
+// a new SeparableProblem every time), and cudaMalloc / cudaMallocHost cost more than a fit.
+struct BufferPool {
+    std::unordered_map<void *, size_t> live;
+    std::vector<std::pair<size_t, void *>> free_list;
+    size_t free_bytes = 0;
+    size_t cap_bytes = 0;
+};
+
 struct vp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -34,7 +45,59 @@ struct vp_ctx {
     int64_t launches = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    BufferPool dev_pool, host_pool;
 };
+
+static cudaError_t pool_alloc(BufferPool &pool, bool host, void **out, size_t bytes)
+{
+    bytes = (bytes + 255) / 256 * 256;
+    for (size_t i = 0; i < pool.free_list.size(); ++i)
+        if (pool.free_list[i].first == bytes) {
+            *out = pool.free_list[i].second;
+            pool.free_list[i] = pool.free_list.back();
+            pool.free_list.pop_back();
+            pool.free_bytes -= bytes;
+            pool.live[*out] = bytes;
+            return cudaSuccess;
+        }
+    cudaError_t e = host ? cudaMallocHost(out, bytes) : cudaMalloc(out, bytes);
+    if (e != cudaSuccess && !pool.free_list.empty()) {
+        // out of memory: drop the cache and retry once
+        for (auto &b : pool.free_list) host ? cudaFreeHost(b.second) : cudaFree(b.second);
+        pool.free_list.clear();
+        pool.free_bytes = 0;
+        cudaGetLastError();
+        e = host ? cudaMallocHost(out, bytes) : cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) pool.live[*out] = bytes;
+    return e;
+}
+
+static void pool_free(BufferPool &pool, bool host, void *p)
+{
+    if (!p) return;
+    auto it = pool.live.find(p);
+    if (it == pool.live.end()) { host ? cudaFreeHost(p) : cudaFree(p); return; }
+    const size_t bytes = it->second;
+    pool.live.erase(it);
+    if (pool.free_bytes + bytes <= pool.cap_bytes) {
+        pool.free_list.emplace_back(bytes, p);
+        pool.free_bytes += bytes;
+    } else {
+        host ? cudaFreeHost(p) : cudaFree(p);
+    }
+}
+
+static void pool_release(BufferPool &pool, bool host)
+{
+    for (auto &b : pool.free_list) host ? cudaFreeHost(b.second) : cudaFree(b.second);
+    pool.free_list.clear();
+    pool.free_bytes = 0;
+}
+#define DEV_ALLOC(ctx, pp, bytes) pool_alloc((ctx)->dev_pool, false, (void **)(pp), (bytes))
+#define HOST_ALLOC(ctx, pp, bytes) pool_alloc((ctx)->host_pool, true, (void **)(pp), (bytes))
+#define DEV_FREE(ctx, p) pool_free((ctx)->dev_pool, false, (void *)(p))
+#define HOST_FREE(ctx, p) pool_free((ctx)->host_pool, true, (void *)(p))
 
 struct vp_model {
     vp_ctx *ctx = nullptr;
@@ -83,6 +146,12 @@ struct vp_problem {
     int plan_grid = 0, plan_nst = 0;
     size_t plan_smem = 0;
 };
+
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
 
 static thread_local std::string g_last_error_noctx;
 
@@ -157,6 +226,8 @@ extern "C" int vp_ctx_create(int device, vp_ctx **out)
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->dev_pool.cap_bytes = (size_t)env_int("VP_POOL_MB", 8192) << 20;
+    ctx->host_pool.cap_bytes = (size_t)64 << 20;
     *out = ctx;
     return VP_OK;
 }
@@ -165,6 +236,8 @@ extern "C" int vp_ctx_destroy(vp_ctx *ctx)
 {
     if (!ctx) return VP_OK;
     cudaSetDevice(ctx->device);
+    pool_release(ctx->dev_pool, false);
+    pool_release(ctx->host_pool, true);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VP_OK;
@@ -237,11 +310,11 @@ extern "C" int vp_model_create(vp_ctx *ctx, int dtype, int64_t m, const void *x_
     const int v = vec_of(dtype);
     mo->ld = (int)((m + v - 1) / v * v);
     cudaSetDevice(ctx->device);
-    cudaError_t e = cudaMalloc(&mo->x_dev, esize(dtype) * (size_t)m);
+    cudaError_t e = DEV_ALLOC(ctx, &mo->x_dev, esize(dtype) * (size_t)m);
     if (e == cudaSuccess) e = cudaMemcpyAsync(mo->x_dev, x_host, esize(dtype) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
-        if (mo->x_dev) cudaFree(mo->x_dev);
+        DEV_FREE(ctx, mo->x_dev);
         delete mo;
         return fail(ctx, VP_ERR_CUDA, std::string("vp_model_create: ") + cudaGetErrorString(e));
     }
@@ -253,7 +326,7 @@ extern "C" int vp_model_destroy(vp_model *model)
 {
     if (!model) return VP_OK;
     cudaSetDevice(model->ctx->device);
-    cudaFree(model->x_dev);
+    DEV_FREE(model->ctx, model->x_dev);
     delete model;
     return VP_OK;
 }
@@ -295,11 +368,6 @@ static const DmmaKernelEntry g_dmma_kernels[] = {
 };
 static const int g_num_dmma_kernels = (int)(sizeof(g_dmma_kernels) / sizeof(g_dmma_kernels[0]));
 
-static int env_int(const char *name, int dflt)
-{
-    const char *s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
 
 // choose the kernel instantiation, stage count and grid for a problem
 static int plan_stream(vp_problem *pr)
@@ -609,23 +677,23 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
                            std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
     } while (0)
 
-    VP_TRY(cudaMalloc(&pr->Yw, es * (size_t)ld * S));
-    VP_TRY(cudaMalloc(&pr->small, sizeof(PanelSmall)));
-    VP_TRY(cudaMalloc(&pr->C[0], es * (size_t)md.n * S));
-    VP_TRY(cudaMalloc(&pr->C[1], es * (size_t)md.n * S));
-    VP_TRY(cudaMalloc(&pr->partials, sizeof(double) * (size_t)pr->red_stride * pr->max_grid));
-    VP_TRY(cudaMalloc(&pr->ticket, sizeof(unsigned int)));
+    VP_TRY(DEV_ALLOC(ctx, &pr->Yw, es * (size_t)ld * S));
+    VP_TRY(DEV_ALLOC(ctx, &pr->small, sizeof(PanelSmall)));
+    VP_TRY(DEV_ALLOC(ctx, &pr->C[0], es * (size_t)md.n * S));
+    VP_TRY(DEV_ALLOC(ctx, &pr->C[1], es * (size_t)md.n * S));
+    VP_TRY(DEV_ALLOC(ctx, &pr->partials, sizeof(double) * (size_t)pr->red_stride * pr->max_grid));
+    VP_TRY(DEV_ALLOC(ctx, &pr->ticket, sizeof(unsigned int)));
     VP_TRY(cudaMemsetAsync(pr->ticket, 0, sizeof(unsigned int), ctx->stream));
-    VP_TRY(cudaMalloc(&pr->out_dev, sizeof(EvalOut)));
-    VP_TRY(cudaMalloc(&pr->fit_dev, sizeof(FitDevice)));
+    VP_TRY(DEV_ALLOC(ctx, &pr->out_dev, sizeof(EvalOut)));
+    VP_TRY(DEV_ALLOC(ctx, &pr->fit_dev, sizeof(FitDevice)));
     VP_TRY(cudaMemsetAsync(pr->fit_dev, 0, sizeof(FitDevice), ctx->stream));
-    VP_TRY(cudaMallocHost(&pr->fit_host, sizeof(FitDevice)));
+    VP_TRY(HOST_ALLOC(ctx, &pr->fit_host, sizeof(FitDevice)));
     pr->alpha_dev = &pr->fit_dev->st.x_trial[0];
-    VP_TRY(cudaMalloc(&pr->phi_scratch, sizeof(double) * (size_t)m * md.n));
-    VP_TRY(cudaMallocHost(&pr->out_host, sizeof(EvalOut)));
-    VP_TRY(cudaMallocHost(&pr->alpha_stage, sizeof(double) * VP_MAX_Q));
+    VP_TRY(DEV_ALLOC(ctx, &pr->phi_scratch, sizeof(double) * (size_t)m * md.n));
+    VP_TRY(HOST_ALLOC(ctx, &pr->out_host, sizeof(EvalOut)));
+    VP_TRY(HOST_ALLOC(ctx, &pr->alpha_stage, sizeof(double) * VP_MAX_Q));
     if (w_host) {
-        VP_TRY(cudaMalloc(&pr->w_dev, es * (size_t)m));
+        VP_TRY(DEV_ALLOC(ctx, &pr->w_dev, es * (size_t)m));
         VP_TRY(cudaMemcpyAsync(pr->w_dev, w_host, es * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
     }
     // observations -> device buffer with leading dimension ld
@@ -651,7 +719,7 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
         int ldp = pr->plan_rows > ld ? pr->plan_rows : ld;
         if (pr->plan_lds > ldp) ldp = pr->plan_lds;
         pr->ldp = (ldp + 3) / 4 * 4;
-        cudaError_t e = cudaMalloc(&pr->Pq, es * (size_t)pr->ldp * (md.n + md.p + 1));
+        cudaError_t e = DEV_ALLOC(ctx, &pr->Pq, es * (size_t)pr->ldp * (md.n + md.p + 1));
         if (e != cudaSuccess) { vp_problem_destroy(pr); return fail(ctx, VP_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }
     }
     // first evaluation at the initial guess (src/problem/builder.rs:321)
@@ -681,14 +749,14 @@ extern "C" int vp_problem_destroy(vp_problem *pr)
     if (!pr) return VP_OK;
     cudaSetDevice(pr->ctx->device);
     cudaStreamSynchronize(pr->ctx->stream);
-    cudaFree(pr->Yw); cudaFree(pr->w_dev); cudaFree(pr->Pq); cudaFree(pr->small);
-    cudaFree(pr->C[0]); cudaFree(pr->C[1]); cudaFree(pr->partials); cudaFree(pr->ticket);
-    cudaFree(pr->out_dev); cudaFree(pr->fit_dev); cudaFree(pr->phi_scratch); cudaFree(pr->dbg);
+    vp_ctx *ctx = pr->ctx;
+    DEV_FREE(ctx, pr->Yw); DEV_FREE(ctx, pr->w_dev); DEV_FREE(ctx, pr->Pq); DEV_FREE(ctx, pr->small);
+    DEV_FREE(ctx, pr->C[0]); DEV_FREE(ctx, pr->C[1]); DEV_FREE(ctx, pr->partials); DEV_FREE(ctx, pr->ticket);
+    DEV_FREE(ctx, pr->out_dev); DEV_FREE(ctx, pr->fit_dev); DEV_FREE(ctx, pr->phi_scratch);
+    cudaFree(pr->dbg);
     if (pr->fit_exec) cudaGraphExecDestroy(pr->fit_exec);
     if (pr->fit_graph) cudaGraphDestroy(pr->fit_graph);
-    if (pr->fit_host) cudaFreeHost(pr->fit_host);
-    if (pr->out_host) cudaFreeHost(pr->out_host);
-    if (pr->alpha_stage) cudaFreeHost(pr->alpha_stage);
+    HOST_FREE(ctx, pr->fit_host); HOST_FREE(ctx, pr->out_host); HOST_FREE(ctx, pr->alpha_stage);
     delete pr;
     return VP_OK;
 }
@@ -759,7 +827,7 @@ static int materialise_t(vp_problem *pr, int what, void *out_host)
     const size_t count = what == 1 ? mS * md.q : mS;
     if (count == 0) return VP_OK;
     T *buf = nullptr;
-    VP_CUDA(ctx, cudaMalloc(&buf, sizeof(T) * count));
+    VP_CUDA(ctx, DEV_ALLOC(ctx, &buf, sizeof(T) * count));
     const int blocks = ctx->sm_count * 8;
     if (what == 0) {
         residuals_kernel<T><<<blocks, 256, 0, ctx->stream>>>((const T *)pr->Yw, mo->ld, pr->ldp, md.m, (int)pr->S, md.n,
@@ -777,7 +845,7 @@ static int materialise_t(vp_problem *pr, int what, void *out_host)
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, buf, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(buf);
+    DEV_FREE(ctx, buf);
     if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, std::string("materialise: ") + cudaGetErrorString(e));
     return VP_OK;
 }

@@ -1,49 +1,98 @@
 """Compile the CUDA extension (C-ABI shared library) in-tree for sm_100a.
 
-The built libvarpro_b200.so is git-ignored but travels to the GPU box with the
-gpurun snapshot. nvcc cross-compiles without a GPU.
+The templated kernels are instantiated in separate translation units (csrc/inst.cu compiled once
+per entry of VP_KERNEL_GROUPS in csrc/kernel_tables.h) which are built in parallel and linked with
+the host side (csrc/vp_abi.cu) into libvarpro_b200.so. Objects go to varpro_b200/_build/ (git-ignored,
+gpurun-ignored); the .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
 
+import concurrent.futures as cf
+import hashlib
 import os
+import re
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libvarpro_b200.so")
-SOURCES = ["vp_abi.cu"]
-HEADERS = ["device_common.cuh", "panel_kernel.cuh", "panel_kernel_hh.cuh", "stream_kernel.cuh", "stream_kernel_dmma.cuh", "aux_kernels.cuh", "lm_step.cuh",
-           os.path.join("..", "..", "include", "varpro_b200.h")]
+HEADER = os.path.join(HERE, "..", "include", "varpro_b200.h")
 
-NVCC_FLAGS = [
-    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
-]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+LINK_LIBS: list[str] = []
+
+
+def _groups():
+    txt = open(os.path.join(CSRC, "kernel_tables.h")).read()
+    return re.findall(r"X\((\w+),\s*(\w+),\s*(\w+),\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".cu"))] + [HEADER]
+
+
+def _units():
+    """(object path, source, extra flags) of every translation unit."""
+    units = [(os.path.join(OBJ, "vp_abi.o"), os.path.join(CSRC, "vp_abi.cu"), [])]
+    for tag, ctype, dt, n, p, part in _groups():
+        flags = [f"-DVP_INST_TAG={tag}", f"-DVP_INST_T={ctype}", f"-DVP_INST_DT={dt}", f"-DVP_INST_N={n}",
+                 f"-DVP_INST_P={p}", f"-DVP_INST_PART={part}"]
+        units.append((os.path.join(OBJ, f"inst_{tag}.o"), os.path.join(CSRC, "inst.cu"), flags))
+    return units
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for d in sorted(_deps()):
+        h.update(d.encode())
+        h.update(open(d, "rb").read())
+    h.update(" ".join(NVCC_FLAGS + LINK_LIBS).encode())
+    return h.hexdigest()
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    stamp = os.path.join(HERE, "libvarpro_b200.stamp")
+    if not os.path.exists(LIB) or not os.path.exists(stamp):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return open(stamp).read().strip() != _stamp()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc, *flags, "-ccbin", "/usr/bin/g++", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+def _compile(nvcc, obj, src, flags, verbose):
+    cmd = [nvcc, *NVCC_FLAGS, *flags, "-c", "-o", obj, src]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
+    return r.returncode, r.stdout + r.stderr, obj
+
+
+def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(OBJ, exist_ok=True)
+    units = _units()
+    jobs = jobs or max(1, min(len(units), os.cpu_count() or 1))
+    failed = []
+    with cf.ThreadPoolExecutor(jobs) as ex:
+        for rc, out, obj in ex.map(lambda u: _compile(nvcc, u[0], u[1], u[2], verbose), units):
+            if rc != 0:
+                failed.append(obj)
+                sys.stderr.write(out)
+            elif verbose:
+                sys.stderr.write(f"== {os.path.basename(obj)}\n{out}")
+    if failed:
+        raise RuntimeError("nvcc failed building " + ", ".join(os.path.basename(f) for f in failed))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", LIB,
+           *[u[0] for u in units], *LINK_LIBS]
+    r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libvarpro_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libvarpro_b200.so")
+    open(os.path.join(HERE, "libvarpro_b200.stamp"), "w").write(_stamp())
     return LIB
 
 

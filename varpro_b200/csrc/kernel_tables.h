@@ -1,0 +1,45 @@
+// kernel_tables.h -- registry of the templated sm_100a kernel instantiations.
+//
+// The instantiations live in separate translation units (inst.cu compiled once per
+// (dtype, n, p, part) so that nvcc can build them in parallel); each unit exports one
+// vp_kernel_group_<tag>() returning its entries. vp_abi.cu concatenates the groups and
+// launches through cudaLaunchKernel on the host stub addresses.
+#pragma once
+
+struct StreamKernelEntry {
+    int dtype, n, p, threads, chunks, ct;
+    const void *fn;
+};
+struct DmmaKernelEntry {
+    int n, p, ksteps, nwarps, exact;
+    const void *fn;
+};
+struct PanelHHEntry {
+    int dtype, n, p, rpt, threads;
+    const void *fn;
+};
+struct KernelGroup {
+    const StreamKernelEntry *simt; int nsimt;
+    const DmmaKernelEntry *dmma;   int ndmma;
+    const PanelHHEntry *panel;     int npanel;
+};
+typedef const KernelGroup *(*KernelGroupFn)();
+
+// (tag, C type, vp_dtype, n, p, part): part 0 = SIMT streaming, 1 = DMMA streaming, 2 = Householder panel.
+// The model shapes with a compiled fast path; everything else runs the generic kernels.
+#define VP_KERNEL_GROUPS(X)                 \
+    X(f64_3_2_simt, double, VP_F64, 3, 2, 0) /* double exponential + offset (benches, C1/C2/C5) */ \
+    X(f64_3_2_dmma, double, VP_F64, 3, 2, 1) \
+    X(f64_3_2_panel, double, VP_F64, 3, 2, 2) \
+    X(f32_3_2_simt, float, VP_F32, 3, 2, 0)  /* the same in fp32 (C4) */ \
+    X(f32_3_2_panel, float, VP_F32, 3, 2, 2) \
+    X(f64_3_3_simt, double, VP_F64, 3, 3, 0) /* triple exponential (C3 shape) */ \
+    X(f64_3_3_dmma, double, VP_F64, 3, 3, 1) \
+    X(f64_3_3_panel, double, VP_F64, 3, 3, 2) \
+    X(f64_2_4_simt, double, VP_F64, 2, 4, 0) /* O'Leary exp*cos example */ \
+    X(f64_2_4_dmma, double, VP_F64, 2, 4, 1) \
+    X(f64_2_4_panel, double, VP_F64, 2, 4, 2)
+
+#define VP_DECLARE_GROUP(tag, T, DT, N, P, PART) const KernelGroup *vp_kernel_group_##tag();
+VP_KERNEL_GROUPS(VP_DECLARE_GROUP)
+#undef VP_DECLARE_GROUP

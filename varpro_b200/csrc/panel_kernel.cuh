@@ -58,7 +58,7 @@ struct PanelRound {
 // small, and the transcendental is shared between value and derivatives.
 // Formulas as the reference writes them.
 struct BasisVals { double v, d0, d1; };
-__device__ __noinline__ BasisVals basis_eval_all(int kind, double x, double a0, double a1, double scale)
+static __device__ __noinline__ BasisVals basis_eval_all(int kind, double x, double a0, double a1, double scale)
 {
     double earg = 0.0, targ = 0.0;
     if (kind == VP_BASIS_EXP_DECAY) earg = -x / a0;

@@ -77,6 +77,7 @@ struct StreamArgs {
 };
 
 constexpr int STREAM_MAX_STAGES = 16;
+constexpr int DMMA_CT = 8; // columns per tile of stream_kernel_dmma (stream_kernel_dmma.cuh)
 
 // coefficient buffer this launch writes: the one NOT holding the accepted coefficients
 template <typename T>

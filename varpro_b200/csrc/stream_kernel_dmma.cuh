@@ -35,7 +35,6 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, const double 
                  : "d"(a), "d"(b));
 }
 
-constexpr int DMMA_CT = 8;
 
 // KSTEPS: k-steps (4 rows each) per warp; NWARPS warps cover 4*KSTEPS*NWARPS >= ld rows.
 // EXACT: 4*KSTEPS*NWARPS <= lds, so no row predicate is needed on the fragment loads.

@@ -17,11 +17,10 @@
 #include "../../include/varpro_b200.h"
 #include "aux_kernels.cuh"
 #include "device_common.cuh"
+#include "kernel_tables.h"
 #include "lm_step.cuh"
 #include "panel_kernel.cuh"
-#include "panel_kernel_hh.cuh"
 #include "stream_kernel.cuh"
-#include "stream_kernel_dmma.cuh"
 
 using namespace vp;
 
@@ -334,40 +333,29 @@ extern "C" int vp_model_destroy(vp_model *model)
 // ----------------------------------------------------------------------------
 // streaming-kernel dispatch table
 // ----------------------------------------------------------------------------
-struct StreamKernelEntry {
-    int dtype, n, p, threads, chunks, ct;
-    const void *fn;
-};
-
-#define VP_SK(T, DT, N, P, THREADS, CHUNKS, CT) \
-    {DT, N, P, THREADS, CHUNKS, CT, (const void *)&stream_kernel<T, N, P, CHUNKS, CT, THREADS>}
-#define VP_SK_SHAPES(T, DT, N, P)                                                  \
-    VP_SK(T, DT, N, P, 128, 1, 4), VP_SK(T, DT, N, P, 128, 4, 4), VP_SK(T, DT, N, P, 128, 4, 8), \
-        VP_SK(T, DT, N, P, 256, 4, 4), VP_SK(T, DT, N, P, 256, 8, 4)
-
-static const StreamKernelEntry g_stream_kernels[] = {
-    VP_SK_SHAPES(double, VP_F64, 3, 2), // double exponential + offset (benches, C1/C2/C5)
-    VP_SK_SHAPES(float, VP_F32, 3, 2),  // the same in fp32 (C4)
-    VP_SK_SHAPES(double, VP_F64, 3, 3), // triple exponential
-    VP_SK_SHAPES(double, VP_F64, 2, 4), // O'Leary exp*cos example
-};
-static const int g_num_stream_kernels = (int)(sizeof(g_stream_kernels) / sizeof(g_stream_kernels[0]));
-
-struct DmmaKernelEntry {
-    int n, p, ksteps, nwarps, exact;
-    const void *fn;
-};
-#define VP_DK(N, P, KS, NW) \
-    {N, P, KS, NW, 1, (const void *)&stream_kernel_dmma<N, P, KS, NW, true>}, \
-    {N, P, KS, NW, 0, (const void *)&stream_kernel_dmma<N, P, KS, NW, false>}
-#define VP_DK_SHAPES(N, P) VP_DK(N, P, 8, 4), VP_DK(N, P, 16, 8), VP_DK(N, P, 32, 8), VP_DK(N, P, 32, 16)
-static const DmmaKernelEntry g_dmma_kernels[] = {
-    VP_DK_SHAPES(3, 2), // double exponential + offset (benches, C1/C2/C5)
-    VP_DK_SHAPES(3, 3), // triple exponential
-    VP_DK_SHAPES(2, 4), // O'Leary exp*cos example
-};
-static const int g_num_dmma_kernels = (int)(sizeof(g_dmma_kernels) / sizeof(g_dmma_kernels[0]));
-
+// The templated fast-path kernels are instantiated in separate translation units (inst.cu, one per
+// model shape and kernel family; see kernel_tables.h); gather their entries once.
+static std::vector<StreamKernelEntry> g_stream_kernels;
+static std::vector<DmmaKernelEntry> g_dmma_kernels;
+static std::vector<PanelHHEntry> g_panel_kernels;
+static int g_num_stream_kernels = 0, g_num_dmma_kernels = 0;
+static void gather_kernel_tables()
+{
+    static bool done = false;
+    if (done) return;
+#define VP_GATHER(tag, T, DT, N, P, PART)                                                        \
+    {                                                                                            \
+        const KernelGroup *g = vp_kernel_group_##tag();                                          \
+        g_stream_kernels.insert(g_stream_kernels.end(), g->simt, g->simt + g->nsimt);            \
+        g_dmma_kernels.insert(g_dmma_kernels.end(), g->dmma, g->dmma + g->ndmma);                \
+        g_panel_kernels.insert(g_panel_kernels.end(), g->panel, g->panel + g->npanel);           \
+    }
+    VP_KERNEL_GROUPS(VP_GATHER)
+#undef VP_GATHER
+    g_num_stream_kernels = (int)g_stream_kernels.size();
+    g_num_dmma_kernels = (int)g_dmma_kernels.size();
+    done = true;
+}
 
 // choose the kernel instantiation, stage count and grid for a problem
 static int plan_stream(vp_problem *pr)
@@ -379,6 +367,7 @@ static int plan_stream(vp_problem *pr)
     const int want_occ = env_int("VP_STREAM_OCC", 2);
     const int force_generic = env_int("VP_STREAM_GENERIC", 0);
     const size_t es = esize(mo->dtype);
+    gather_kernel_tables();
     pr->plan_kind = -1;
     pr->plan_dmma = -1;
     const char *which = getenv("VP_STREAM_KERNEL"); // "dmma" (default for fp64), "simt", "generic"
@@ -494,33 +483,6 @@ static int plan_stream(vp_problem *pr)
     return VP_OK;
 }
 
-// Householder panel kernel instantiations: (n, p) x rows-per-thread, 512 threads
-template <typename T>
-struct PanelHHEntry {
-    int n, p, rpt;
-    void (*fn)(ModelDesc, const T *, const T *, const double *, double, int, T *, PanelSmall *, unsigned long long *);
-};
-constexpr int PANEL_HH_THREADS = 512;
-#define VP_PK(T, N, P, RPT) {N, P, RPT, &panel_kernel_hh<T, N, P, RPT, PANEL_HH_THREADS>}
-#define VP_PK_SHAPES(T, N, P) VP_PK(T, N, P, 1), VP_PK(T, N, P, 2), VP_PK(T, N, P, 4), VP_PK(T, N, P, 8)
-template <typename T> struct PanelHHTable;
-template <> struct PanelHHTable<double> {
-    static const PanelHHEntry<double> *get(int &count)
-    {
-        static const PanelHHEntry<double> t[] = {VP_PK_SHAPES(double, 3, 2), VP_PK_SHAPES(double, 3, 3), VP_PK_SHAPES(double, 2, 4)};
-        count = (int)(sizeof(t) / sizeof(t[0]));
-        return t;
-    }
-};
-template <> struct PanelHHTable<float> {
-    static const PanelHHEntry<float> *get(int &count)
-    {
-        static const PanelHHEntry<float> t[] = {VP_PK_SHAPES(float, 3, 2)};
-        count = (int)(sizeof(t) / sizeof(t[0]));
-        return t;
-    }
-};
-
 template <typename T>
 static int launch_panel_t(vp_problem *pr)
 {
@@ -530,14 +492,18 @@ static int launch_panel_t(vp_problem *pr)
     unsigned long long *dbg = pr->dbg ? pr->dbg + (size_t)pr->max_grid * VP_DBG_SLOTS : nullptr;
     // fast path: register-resident Householder panel
     if (!env_int("VP_PANEL_GENERIC", 0)) {
-        int count = 0;
-        const PanelHHEntry<T> *tab = PanelHHTable<T>::get(count);
-        for (int i = 0; i < count; ++i) {
-            if (tab[i].n != md.n || tab[i].p != md.p || (long long)tab[i].rpt * PANEL_HH_THREADS < md.m) continue;
-            tab[i].fn<<<1, PANEL_HH_THREADS, 0, ctx->stream>>>(md, (const T *)mo->x_dev, (const T *)pr->w_dev, pr->alpha_dev,
-                                                             pr->svd_eps, pr->ldp, (T *)pr->Pq, pr->small, dbg);
+        for (const PanelHHEntry &k : g_panel_kernels) {
+            if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p || (long long)k.rpt * k.threads < md.m) continue;
+            ModelDesc mdc = md;
+            const void *xp = mo->x_dev, *wp = pr->w_dev;
+            const double *ap = pr->alpha_dev;
+            double eps = pr->svd_eps;
+            int ldp = pr->ldp;
+            void *pq = pr->Pq;
+            PanelSmall *sm = pr->small;
+            void *args[] = {&mdc, &xp, &wp, &ap, &eps, &ldp, &pq, &sm, &dbg};
+            VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(1), dim3(k.threads), args, 0, ctx->stream));
             ctx->launches++;
-            VP_CUDA(ctx, cudaGetLastError());
             return VP_OK;
         }
     }

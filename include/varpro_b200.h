@@ -198,8 +198,41 @@ int vp_best_fit(vp_problem *problem, void *out_host);
 /* ||r||^2, J^T r and J^T J of the current parameters without materialising r or J */
 int vp_reduce(vp_problem *problem, vp_reduced *out);
 
+/* ---- multi-GPU: column-sharded global fit ------------------------------------
+ * BASELINE config 5 / SURVEY.md 8(e): the S right-hand sides of ONE global fit
+ * (shared alpha) are partitioned contiguously over the GPUs of a box, one
+ * process per GPU. Every rank builds a vp_problem from ITS columns and attaches
+ * the communicator; from then on every evaluation (vp_set_params, vp_fit, ...)
+ * is collective: each GPU reduces its columns to (||r||^2, J^T r, J^T J), the
+ * <= 74 doubles are exchanged in one shot through NVLink peer mappings inside
+ * the evaluation kernel (no host round trip, no extra launch) and summed in
+ * rank order, so all ranks take bitwise identical LM steps. All ranks must make
+ * the same sequence of calls. The reference has no distributed code; this is
+ * the natural sharding of src/solvers/levmar/mod.rs:42-201 over columns of Y.
+ *
+ * Setup: (1) every rank calls vp_comm_create and receives the 64-byte CUDA IPC
+ * handle of its mailbox; (2) the host all-gathers the handles in rank order
+ * (torch.distributed / MPI / any transport); (3) every rank calls
+ * vp_comm_connect with the world*64 bytes. world == 1 needs no connect. */
+#define VP_COMM_HANDLE_BYTES 64
+typedef struct vp_comm vp_comm;
+int vp_comm_create(vp_ctx *ctx, int rank, int world, vp_comm **out, void *local_handle_out);
+int vp_comm_connect(vp_comm *comm, const void *all_handles);
+int vp_comm_destroy(vp_comm *comm);
+/* comm == NULL detaches. Re-evaluates at the current parameters (collective). */
+int vp_problem_set_comm(vp_problem *problem, vp_comm *comm);
+
 /* ---- solve: replaces LevMarSolver::fit (src/solvers/levmar/mod.rs:238-254) */
 int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *report);
+/* Fit n independent problems of one context (throughput mode): what a caller of the reference
+ * does in a loop over LevMarSolver::fit (e.g. benches/multiple_right_hand_sides.rs:97-101 per
+ * criterion iteration). The fits run concurrently, each as one persistent kernel on
+ * #SMs / min(n, max_concurrent) SMs (max_concurrent <= 0: as many as there are SMs), so the
+ * latency-bound phases of one fit overlap the HBM streaming of the others. Results are
+ * identical to n calls of vp_fit up to the summation order of the per-CTA partial sums.
+ * reports: n entries. Returns the first error, VP_OK otherwise. */
+int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *options, vp_fit_report *reports,
+                int32_t max_concurrent);
 
 /* ---- diagnostics ---------------------------------------------------------
  * Device time (CUDA events on the context's stream, microseconds, averaged over

@@ -44,6 +44,30 @@ for _ in range(3):
     dt = time.time() - t0
     print(f"fit again: {1e3*dt:.2f} ms nfev {res.minimization_report.number_of_evaluations} -> {1e6*dt/res.minimization_report.number_of_evaluations:.1f} us/eval")
 
+def dump_timeline(title):
+    cap = (148 * 8 + 1) * 16
+    buf = (C.c_longlong * cap)()
+    g = C.c_int64()
+    st = _lib.load().vp_debug_timeline(gp._h, buf, cap, C.byref(g))
+    assert st == 0
+    t = np.array(buf[: (g.value + 1) * 16], dtype=np.int64).reshape(-1, 16)
+    k2 = t[:-1]
+    print(title)
+    names = {8: "eval_start", 9: "basis_evaluated", 10: "panel_done", 1: "frags_loaded", 2: "first_tile", 3: "loop_done",
+             4: "publish_begin", 14: "partial_written", 5: "published", 11: "fin_prefetch", 12: "fin_partials",
+             13: "fin_assembled", 7: "before_lm", 15: "lm_step_done", 6: "released/acquired"}
+    for i, nm in names.items():
+        col = k2[:, i][k2[:, i] >= 0]
+        if len(col):
+            print(f"  {nm:18s} min {col.min():7d} median {int(np.median(col)):7d} max {col.max():7d} (n={len(col)})")
+
+
+if os.environ.get("FIT_TIMELINE"):
+    os.environ["VP_DBG_FIT"] = "1"
+    gp.set_params(wl["alpha0"])
+    res = vb.LevMarSolver.default().fit(gp)
+    dump_timeline("persistent fit, last evaluation (ns relative to the earliest stamp):")
+
 if os.environ.get("TIMELINE"):
     import numpy as np
     cap = (148 * 8 + 1) * 16

@@ -220,3 +220,81 @@ def test_nonfinite_parameters_give_none_and_numerical_termination():
     with pytest.raises(vb.FitError) as ei:
         vb.LevMarSolver.default().fit(gp)
     assert not ei.value.result.was_successful()
+
+
+def test_fused_kernel_matches_split_kernels(monkeypatch):
+    """fit_kernel_dmma (panel fused into the streaming pass) against K1 + K2 launched separately."""
+    wl = W.c2(S=200)
+    fused = W.make_gpu_problem(wl)
+    monkeypatch.setenv("VP_EVAL_KERNEL", "split")
+    split = W.make_gpu_problem(wl)
+    monkeypatch.delenv("VP_EVAL_KERNEL")
+    for alpha in ([2.0, 6.5], [1.1, 2.9]):
+        fused.set_params(alpha)
+        split.set_params(alpha)
+        rf, rs = fused.reduce(), split.reduce()
+        assert abs(rf["rnorm2"] - rs["rnorm2"]) <= 1e-12 * rs["rnorm2"]
+        assert np.max(np.abs(rf["H"] - rs["H"])) <= 1e-12 * np.abs(rs["H"]).max()
+        assert np.max(np.abs(rf["g"] - rs["g"])) <= 1e-9 * np.abs(rs["g"]).max()
+        Cf, Cs = fused.linear_coefficients(), split.linear_coefficients()
+        assert np.max(np.abs(Cf - Cs)) <= 1e-12 * np.abs(Cs).max()
+
+
+@pytest.mark.parametrize("mode", ["persistent", "graph", "host"])
+def test_fit_modes_agree(monkeypatch, mode):
+    """The persistent whole-fit kernel, the CUDA-graph loop and the host-driven loop run the same
+    lmder state machine on the same reductions."""
+    import varpro_b200 as vb
+    wl = W.c2(S=96)
+    monkeypatch.setenv("VP_FIT_MODE", mode)
+    if mode != "persistent":
+        monkeypatch.setenv("VP_EVAL_KERNEL", "split")
+    gp = W.make_gpu_problem(wl)
+    res = vb.LevMarSolver.default().fit(gp)
+    assert res.was_successful()
+    assert np.allclose(np.sort(res.nonlinear_parameters()), [1.0, 3.0], rtol=0, atol=1e-8)
+    C = res.linear_coefficients()
+    if res.nonlinear_parameters()[0] > res.nonlinear_parameters()[1]:
+        C = C[[1, 0, 2]]
+    assert np.max(np.abs(C - wl["C_true"])) <= 1e-6
+
+
+def test_sharded_fit_world1_exercises_the_mailbox_protocol():
+    """A communicator of world size 1: every evaluation goes through the NVLink mailbox exchange
+    (with itself) inside the kernel; results must equal the plain problem bit for bit."""
+    import varpro_b200 as vb
+    from varpro_b200 import sharding
+    wl = W.c2(S=128)
+    plain = W.make_gpu_problem(wl)
+    comm = sharding.Communicator(0, 1)
+    sh = comm.attach(W.make_gpu_problem(wl))
+    rp, rs = plain.reduce(), sh.reduce()
+    assert rp["rnorm2"] == rs["rnorm2"] and np.array_equal(rp["H"], rs["H"]) and np.array_equal(rp["g"], rs["g"])
+    a = vb.LevMarSolver.default().fit(plain)
+    b = vb.LevMarSolver.default().fit(sh)
+    assert np.array_equal(a.nonlinear_parameters(), b.nonlinear_parameters())
+    assert a.minimization_report.number_of_evaluations == b.minimization_report.number_of_evaluations
+    sh.close()
+    comm.close()
+
+
+def test_fit_many_equals_sequential_fits():
+    """vp_fit_many (concurrent persistent kernels on SM slices) against one vp_fit per problem."""
+    import varpro_b200 as vb
+    solver = vb.LevMarSolver.default()
+    wls = [W.c2(S=64 + 8 * k, seed=100 + k) for k in range(6)] + [W.mrhs20(3), W.lmfit_case(True)]
+    seq = [solver.fit(W.make_gpu_problem(wl)) for wl in wls]
+    many = solver.fit_many([W.make_gpu_problem(wl) for wl in wls])
+    for wl, a, b in zip(wls, seq, many):
+        assert b.was_successful()
+        pa, pb = np.sort(a.nonlinear_parameters()), np.sort(b.nonlinear_parameters())
+        assert np.max(np.abs(pa - pb) / np.abs(pa)) <= REL_PARAM
+        Yn = np.linalg.norm(wl["Y"])
+        rn_a = np.sqrt(2 * a.minimization_report.objective_function)
+        rn_b = np.sqrt(2 * b.minimization_report.objective_function)
+        assert abs(rn_a - rn_b) <= REL_RNORM * Yn
+    # more problems than SMs: the surplus queues behind the running fits
+    wl = W.mrhs20(2)
+    res = solver.fit_many([W.make_gpu_problem(wl) for _ in range(200)])
+    assert all(r.was_successful() for r in res)
+    assert all(np.allclose(np.sort(r.nonlinear_parameters()), [1.0, 3.0], atol=1e-8) for r in res)

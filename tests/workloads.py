@@ -141,7 +141,7 @@ def make_oracle(wl, alpha0=None, Y=None):
 _KIND_TO_FN = None
 
 
-def make_gpu_problem(wl, alpha0=None, Y=None, dtype=np.float64):
+def make_gpu_problem(wl, alpha0=None, Y=None, dtype=np.float64, device=0, ctx_slot=0):
     """Build the same problem through the product's reference-facing API."""
     import varpro_b200 as vb
     fns = {0: vb.ExpDecay, 1: vb.Constant, 2: vb.ExpRateCos, 3: vb.SinPhase}
@@ -160,4 +160,4 @@ def make_gpu_problem(wl, alpha0=None, Y=None, dtype=np.float64):
     pb = pb.observations(Yv[:, 0] if single else Yv)
     if wl.get("weights") is not None:
         pb = pb.weights(wl["weights"])
-    return pb.build()
+    return pb.device(device, ctx_slot).build()

@@ -66,7 +66,12 @@ SYMBOLS = {
     "vp_linear_coefficients": (C.c_int, [_vp, _vp]),
     "vp_best_fit": (C.c_int, [_vp, _vp]),
     "vp_reduce": (C.c_int, [_vp, C.POINTER(Reduced)]),
+    "vp_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _pp, _vp]),
+    "vp_comm_connect": (C.c_int, [_vp, _vp]),
+    "vp_comm_destroy": (C.c_int, [_vp]),
+    "vp_problem_set_comm": (C.c_int, [_vp, _vp]),
     "vp_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),
+    "vp_fit_many": (C.c_int, [_pp, C.c_int64, C.POINTER(LmOptions), C.POINTER(FitReport), C.c_int32]),
     "vp_debug_timeline": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.c_int64, C.POINTER(C.c_int64)]),
     "vp_profile_evaluation": (C.c_int, [_vp, C.c_int, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int64)]),

@@ -166,6 +166,7 @@ def LinearX(scale=1.0):
 # ---------------------------------------------------------------------------
 class _Ctx:
     _by_device = {}
+    _lock = __import__("threading").Lock()
 
     def __init__(self, device: int):
         lib = _lib.load()
@@ -177,10 +178,13 @@ class _Ctx:
         self.device = device
 
     @classmethod
-    def get(cls, device: int = 0) -> "_Ctx":
-        if device not in cls._by_device:
-            cls._by_device[device] = _Ctx(device)
-        return cls._by_device[device]
+    def get(cls, device: int = 0, slot: int = 0) -> "_Ctx":
+        """One library context (= one CUDA stream, used by one host thread at a time) per
+        (device, slot). Host threads that want their copies and fits to overlap use different slots."""
+        with cls._lock:
+            if (device, slot) not in cls._by_device:
+                cls._by_device[(device, slot)] = _Ctx(device)
+            return cls._by_device[(device, slot)]
 
     def kernel_launches(self) -> int:
         return int(_lib.load().vp_ctx_kernel_launches(self.h))
@@ -334,9 +338,9 @@ class SeparableProblem:
     """Device-resident SeparableProblem (src/problem.rs:57-107). Created by the builder."""
 
     def __init__(self, model: SeparableModel, Y: np.ndarray, weights, eps, single_rhs, device=0,
-                 y_device_ptr=None, S=None, ldY=None):
+                 y_device_ptr=None, S=None, ldY=None, ctx_slot=0):
         lib = _lib.load()
-        self._ctx = _Ctx.get(device)
+        self._ctx = _Ctx.get(device, ctx_slot)
         self.model_host = model
         self.single_rhs = single_rhs
         self.dtype = model.dtype
@@ -474,8 +478,9 @@ class SeparableProblemBuilder:
         self._eps = abs(float(eps))
         return self
 
-    def device(self, ordinal: int):
+    def device(self, ordinal: int, ctx_slot: int = 0):
         self._device = int(ordinal)
+        self._ctx_slot = int(ctx_slot)
         return self
 
     def build(self) -> SeparableProblem:  # :278-324
@@ -494,7 +499,8 @@ class SeparableProblemBuilder:
             raise InvalidLengthOfWeights("The weights must have the same length as the data y.", 5)
         eps = -1.0 if self._eps is None else self._eps  # default: machine epsilon of the scalar (:282)
         Yf = np.asfortranarray(Y, dtype=self._model.dtype)
-        return SeparableProblem(self._model, Yf, self._w, eps, self._single, self._device)
+        return SeparableProblem(self._model, Yf, self._w, eps, self._single, self._device,
+                                ctx_slot=getattr(self, "_ctx_slot", 0))
 
 
 # ---------------------------------------------------------------------------
@@ -615,3 +621,23 @@ class LevMarSolver:
         if not result.was_successful():
             raise FitError(result)
         return result
+
+    def fit_many(self, problems: Sequence[SeparableProblem], max_concurrent: int = 0) -> List[FitResult]:
+        """Fit independent problems concurrently (vp_fit_many): the loop a caller of the reference
+        writes around LevMarSolver::fit, executed as concurrent persistent kernels on slices of the
+        SMs. Returns one FitResult per problem in order; unsuccessful fits are returned (not raised)
+        -- check `was_successful()` as with the reference's Err(FitResult)."""
+        problems = list(problems)
+        if not problems:
+            return []
+        n = len(problems)
+        handles = (C.c_void_p * n)(*[p._h for p in problems])
+        reps = (_lib.FitReport * n)()
+        _check(_lib.load().vp_fit_many(handles, n, C.byref(self._solver._o), reps, int(max_concurrent)),
+               problems[0]._ctx.h)
+        out = []
+        for p, rep in zip(problems, reps):
+            p.model_host._params = p.params()
+            out.append(FitResult(p, MinimizationReport(TerminationReason(rep.termination),
+                                                       rep.number_of_evaluations, rep.objective_function)))
+        return out

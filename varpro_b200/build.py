@@ -2,8 +2,8 @@
 
 The templated kernels are instantiated in separate translation units (csrc/inst.cu compiled once
 per entry of VP_KERNEL_GROUPS in csrc/kernel_tables.h) which are built in parallel and linked with
-the host side (csrc/vp_abi.cu) into libvarpro_b200.so. Objects go to varpro_b200/_build/ (git-ignored,
-gpurun-ignored); the .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+the host side (csrc/vp_abi.cu) into libvarpro_b200.so. Objects go to gpurun_out/_obj/ (scratch: git-ignored,
+never shipped) and are reused when neither their source, nor a header, nor the flags changed; the .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
@@ -17,7 +17,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
+OBJ = os.path.join(HERE, "..", "gpurun_out", "_obj")  # scratch: never pushed to the GPU box, never committed
 LIB = os.path.join(HERE, "libvarpro_b200.so")
 HEADER = os.path.join(HERE, "..", "include", "varpro_b200.h")
 
@@ -39,18 +39,23 @@ def _units():
     """(object path, source, extra flags) of every translation unit."""
     units = [(os.path.join(OBJ, "vp_abi.o"), os.path.join(CSRC, "vp_abi.cu"), [])]
     for tag, ctype, dt, n, p, part in _groups():
+        variant = re.search(r"(\d+)$", tag)
         flags = [f"-DVP_INST_TAG={tag}", f"-DVP_INST_T={ctype}", f"-DVP_INST_DT={dt}", f"-DVP_INST_N={n}",
-                 f"-DVP_INST_P={p}", f"-DVP_INST_PART={part}"]
+                 f"-DVP_INST_P={p}", f"-DVP_INST_PART={part}", f"-DVP_INST_VARIANT={variant.group(1) if variant else 0}"]
         units.append((os.path.join(OBJ, f"inst_{tag}.o"), os.path.join(CSRC, "inst.cu"), flags))
     return units
 
 
-def _stamp():
+def _stamp(src=None, flags=()):
+    """Hash of everything an object (src given) or the whole library (src None) depends on: every
+    header, the unit's own source (all sources for the library) and the flags."""
     h = hashlib.sha256()
     for d in sorted(_deps()):
-        h.update(d.encode())
+        if d.endswith(".cu") and src is not None and os.path.abspath(d) != os.path.abspath(src):
+            continue
+        h.update(os.path.basename(d).encode())
         h.update(open(d, "rb").read())
-    h.update(" ".join(NVCC_FLAGS + LINK_LIBS).encode())
+    h.update(" ".join(list(NVCC_FLAGS) + list(LINK_LIBS) + list(flags)).encode())
     return h.hexdigest()
 
 
@@ -62,6 +67,16 @@ def needs_build() -> bool:
 
 
 def _compile(nvcc, obj, src, flags, verbose):
+    stamp = _stamp(src, flags)
+    if os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read() == stamp and not verbose:
+        return 0, "", obj
+    r = _compile_run(nvcc, obj, src, flags, verbose)
+    if r[0] == 0:
+        open(obj + ".stamp", "w").write(stamp)
+    return r
+
+
+def _compile_run(nvcc, obj, src, flags, verbose):
     cmd = [nvcc, *NVCC_FLAGS, *flags, "-c", "-o", obj, src]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
@@ -72,6 +87,10 @@ def _compile(nvcc, obj, src, flags, verbose):
 def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -> str:
     if not force and not needs_build():
         return LIB
+    if force:
+        for f in (os.listdir(OBJ) if os.path.isdir(OBJ) else []):
+            if f.endswith(".stamp"):
+                os.remove(os.path.join(OBJ, f))
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
     units = _units()

@@ -1,6 +1,7 @@
 // inst.cu -- one group of kernel instantiations; compiled once per entry of VP_KERNEL_GROUPS with
 //   -DVP_INST_TAG=<tag> -DVP_INST_T=<double|float> -DVP_INST_DT=<VP_F64|VP_F32> -DVP_INST_N=n -DVP_INST_P=p -DVP_INST_PART=<0|1|2>
 #include "kernel_tables.h"
+#include "fit_kernel_dmma.cuh"
 #include "panel_kernel_hh.cuh"
 #include "stream_kernel.cuh"
 #include "stream_kernel_dmma.cuh"
@@ -18,18 +19,27 @@ typedef VP_INST_T T_;
     {VP_INST_DT, N_, P_, THREADS, CHUNKS, CT, (const void *)&stream_kernel<T_, N_, P_, CHUNKS, CT, THREADS>}
 static const StreamKernelEntry simt_tab[] = {VP_SK(128, 1, 4), VP_SK(128, 4, 4), VP_SK(128, 4, 8), VP_SK(256, 4, 4),
                                              VP_SK(256, 8, 4)};
-static const KernelGroup group = {simt_tab, (int)(sizeof(simt_tab) / sizeof(simt_tab[0])), nullptr, 0, nullptr, 0};
+static const KernelGroup group = {simt_tab, (int)(sizeof(simt_tab) / sizeof(simt_tab[0])), nullptr, 0, nullptr, 0, nullptr, 0};
 #elif VP_INST_PART == 1
-#define VP_DK(KS, NW)                                                               \
-    {N_, P_, KS, NW, 1, (const void *)&stream_kernel_dmma<N_, P_, KS, NW, true>},  \
-    {N_, P_, KS, NW, 0, (const void *)&stream_kernel_dmma<N_, P_, KS, NW, false>}
-static const DmmaKernelEntry dmma_tab[] = {VP_DK(8, 4), VP_DK(16, 8), VP_DK(32, 8), VP_DK(32, 16)};
-static const KernelGroup group = {nullptr, 0, dmma_tab, (int)(sizeof(dmma_tab) / sizeof(dmma_tab[0])), nullptr, 0};
+// EXACT (unpredicated fragment loads) only for the 1024-row tiling the benchmark shapes use
+#define VP_DK(KS, NW, EX) {N_, P_, KS, NW, EX, (const void *)&stream_kernel_dmma<N_, P_, KS, NW, (EX) != 0>}
+static const DmmaKernelEntry dmma_tab[] = {VP_DK(8, 4, 0), VP_DK(16, 8, 0), VP_DK(32, 8, 0), VP_DK(32, 8, 1), VP_DK(32, 16, 0)};
+static const KernelGroup group = {nullptr, 0, dmma_tab, (int)(sizeof(dmma_tab) / sizeof(dmma_tab[0])), nullptr, 0, nullptr, 0};
+#elif VP_INST_PART == 3
+#define VP_FK(KS, NW, EX) {N_, P_, KS, NW, EX, (const void *)&fit_kernel_dmma<N_, P_, KS, NW, (EX) != 0>}
+#if VP_INST_VARIANT == 0
+static const FitKernelEntry fit_tab[] = {VP_FK(8, 4, 0), VP_FK(16, 8, 0)};
+#elif VP_INST_VARIANT == 1
+static const FitKernelEntry fit_tab[] = {VP_FK(32, 8, 0), VP_FK(32, 8, 1)};
+#else
+static const FitKernelEntry fit_tab[] = {VP_FK(32, 16, 0)};
+#endif
+static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, fit_tab, (int)(sizeof(fit_tab) / sizeof(fit_tab[0]))};
 #else
 constexpr int PANEL_HH_THREADS = 512;
 #define VP_PK(RPT) {VP_INST_DT, N_, P_, RPT, PANEL_HH_THREADS, (const void *)&panel_kernel_hh<T_, N_, P_, RPT, PANEL_HH_THREADS>}
 static const PanelHHEntry panel_tab[] = {VP_PK(1), VP_PK(2), VP_PK(4), VP_PK(8)};
-static const KernelGroup group = {nullptr, 0, nullptr, 0, panel_tab, (int)(sizeof(panel_tab) / sizeof(panel_tab[0]))};
+static const KernelGroup group = {nullptr, 0, nullptr, 0, panel_tab, (int)(sizeof(panel_tab) / sizeof(panel_tab[0])), nullptr, 0};
 #endif
 
 const KernelGroup *VP_CAT(vp_kernel_group_, VP_INST_TAG)() { return &group; }

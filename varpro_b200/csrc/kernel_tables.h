@@ -18,27 +18,42 @@ struct PanelHHEntry {
     int dtype, n, p, rpt, threads;
     const void *fn;
 };
+struct FitKernelEntry { // fit_kernel_dmma: fused panel + streaming reduce (+ whole LM loop)
+    int n, p, ksteps, nwarps, exact;
+    const void *fn;
+};
 struct KernelGroup {
     const StreamKernelEntry *simt; int nsimt;
     const DmmaKernelEntry *dmma;   int ndmma;
     const PanelHHEntry *panel;     int npanel;
+    const FitKernelEntry *fit;     int nfit;
 };
 typedef const KernelGroup *(*KernelGroupFn)();
 
-// (tag, C type, vp_dtype, n, p, part): part 0 = SIMT streaming, 1 = DMMA streaming, 2 = Householder panel.
+// (tag, C type, vp_dtype, n, p, part): part 0 = SIMT streaming, 1 = DMMA streaming, 2 = Householder panel,
+// 3 = fused evaluation / persistent fit kernel.
 // The model shapes with a compiled fast path; everything else runs the generic kernels.
 #define VP_KERNEL_GROUPS(X)                 \
     X(f64_3_2_simt, double, VP_F64, 3, 2, 0) /* double exponential + offset (benches, C1/C2/C5) */ \
     X(f64_3_2_dmma, double, VP_F64, 3, 2, 1) \
     X(f64_3_2_panel, double, VP_F64, 3, 2, 2) \
+    X(f64_3_2_fit0, double, VP_F64, 3, 2, 3) \
+    X(f64_3_2_fit1, double, VP_F64, 3, 2, 3) \
+    X(f64_3_2_fit2, double, VP_F64, 3, 2, 3) \
     X(f32_3_2_simt, float, VP_F32, 3, 2, 0)  /* the same in fp32 (C4) */ \
     X(f32_3_2_panel, float, VP_F32, 3, 2, 2) \
     X(f64_3_3_simt, double, VP_F64, 3, 3, 0) /* triple exponential (C3 shape) */ \
     X(f64_3_3_dmma, double, VP_F64, 3, 3, 1) \
     X(f64_3_3_panel, double, VP_F64, 3, 3, 2) \
+    X(f64_3_3_fit0, double, VP_F64, 3, 3, 3) \
+    X(f64_3_3_fit1, double, VP_F64, 3, 3, 3) \
+    X(f64_3_3_fit2, double, VP_F64, 3, 3, 3) \
     X(f64_2_4_simt, double, VP_F64, 2, 4, 0) /* O'Leary exp*cos example */ \
     X(f64_2_4_dmma, double, VP_F64, 2, 4, 1) \
-    X(f64_2_4_panel, double, VP_F64, 2, 4, 2)
+    X(f64_2_4_panel, double, VP_F64, 2, 4, 2) \
+    X(f64_2_4_fit0, double, VP_F64, 2, 4, 3) \
+    X(f64_2_4_fit1, double, VP_F64, 2, 4, 3) \
+    X(f64_2_4_fit2, double, VP_F64, 2, 4, 3)
 
 #define VP_DECLARE_GROUP(tag, T, DT, N, P, PART) const KernelGroup *vp_kernel_group_##tag();
 VP_KERNEL_GROUPS(VP_DECLARE_GROUP)

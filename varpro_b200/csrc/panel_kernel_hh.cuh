@@ -111,37 +111,21 @@ __device__ __forceinline__ void hh_steps(double (&a)[RPT][N + P], double (&beta)
     }
 }
 
-template <typename T, int N, int P, int RPT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
-                const double *__restrict__ alpha_dev, double svd_eps, int ldp, T *__restrict__ Pq,
-                PanelSmall *__restrict__ small, unsigned long long *dbg)
+// Evaluate the weighted basis functions and derivative columns for this thread's rows
+// (straight-line code, static register indices).
+template <int N, int P, int RPT, int THREADS>
+__device__ __forceinline__ int panel_hh_eval(const ModelDesc &md, const double (&xi_r)[RPT], const double (&wi_r)[RPT],
+                                             const double *alpha_s, double (&a)[RPT][N + P], double (&d0)[RPT][P > 0 ? P : 1])
 {
-    constexpr int NPV = N + P;
-    constexpr int NW = THREADS / 32;
-    constexpr int NVV = N * (N - 1) / 2; // strict upper triangle of V^T V
-    constexpr int NMM = P * (P + 1) / 2; // upper triangle of M
-    constexpr int KMAX = (NPV > 8) ? NPV : 8;
-    __shared__ double red[2][NW * KMAX];
-    __shared__ double top[N][NPV];   // rows 0..n-1 of the working matrix (R, Q^T D and v entries)
-    __shared__ double alpha_s[VP_MAX_Q];
     const int tid = threadIdx.x;
     const int m = md.m;
-
-    dbg_mark(dbg, 0);
-    if (tid < VP_MAX_Q) alpha_s[tid] = tid < md.q ? alpha_dev[tid] : 0.0;
-    __syncthreads();
-
-    // ---- 1. evaluate: thread owns rows tid + r*THREADS ---------------------------------
-    double a[RPT][NPV]; // working matrix rows
-    double d0[RPT][P > 0 ? P : 1]; // the untouched weighted derivative columns
     int bad = 0;
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const int i = tid + r * THREADS;
         const bool in = i < m;
-        const double xi = in ? (double)x[i] : 0.0;
-        const double wi = in ? (w ? (double)w[i] : 1.0) : 0.0;
+        const double xi = xi_r[r];
+        const double wi = wi_r[r];
         int e = 0;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -166,6 +150,31 @@ panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
             }
         }
     }
+    return bad;
+}
+
+
+// The panel computation for one parameter vector, executed by all THREADS threads of a CTA.
+// xi/wi: the thread's rows i = tid + r*THREADS of the independent variable and the weights
+// (wi = 0 for i >= m). alpha_s: the q parameters (shared memory). Pq (ldp rows per column) and
+// `small` may point to global OR shared memory (generic addressing): panel_kernel_hh publishes
+// them to HBM for the streaming kernel, fit_kernel_dmma keeps them in the CTA.
+// red/top: shared scratch. The caller synchronises before anybody reads Pq / small.
+template <typename T, int N, int P, int RPT, int THREADS>
+__device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)[RPT][N + P], double (&d0)[RPT][P > 0 ? P : 1],
+                                                int bad, const double *alpha_s, const double svd_eps, const int ldp, T *Pq,
+                                                PanelSmall *small,
+                                                double (*red)[(THREADS / 32) * ((N + P > 8) ? N + P : 8)],
+                                                double (*top)[N + P], unsigned long long *dbg)
+{
+    constexpr int NPV = N + P;
+    constexpr int NW = THREADS / 32;
+    constexpr int NVV = N * (N - 1) / 2; // strict upper triangle of V^T V
+    constexpr int NMM = P * (P + 1) / 2; // upper triangle of M
+    constexpr int KMAX = (NPV > 8) ? NPV : 8;
+    const int tid = threadIdx.x;
+    const int m = md.m;
+
     bad = __syncthreads_or(bad);
     dbg_mark(dbg, 1);
 
@@ -378,6 +387,46 @@ panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
     }
     if (tid >= 64 && tid < 64 + VP_MAX_Q) small->alpha[tid - 64] = alpha_s[tid - 64];
     dbg_mark(dbg, 4);
+}
+
+template <typename T, int N, int P, int RPT, int THREADS>
+__device__ __forceinline__ void panel_hh_body(const ModelDesc &md, const double (&xi_r)[RPT], const double (&wi_r)[RPT],
+                                              const double *alpha_s, const double svd_eps, const int ldp, T *Pq,
+                                              PanelSmall *small,
+                                              double (*red)[(THREADS / 32) * ((N + P > 8) ? N + P : 8)],
+                                              double (*top)[N + P], unsigned long long *dbg)
+{
+    double a[RPT][N + P];           // working matrix rows
+    double d0[RPT][P > 0 ? P : 1];  // the untouched weighted derivative columns
+    const int bad = panel_hh_eval<N, P, RPT, THREADS>(md, xi_r, wi_r, alpha_s, a, d0);
+    panel_hh_factor<T, N, P, RPT, THREADS>(md, a, d0, bad, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg);
+}
+
+template <typename T, int N, int P, int RPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
+                const double *__restrict__ alpha_dev, double svd_eps, int ldp, T *__restrict__ Pq,
+                PanelSmall *__restrict__ small, unsigned long long *dbg)
+{
+    constexpr int NPV = N + P;
+    constexpr int NW = THREADS / 32;
+    constexpr int KMAX = (NPV > 8) ? NPV : 8;
+    __shared__ double red[2][NW * KMAX];
+    __shared__ double top[N][NPV];   // rows 0..n-1 of the working matrix (R, Q^T D and v entries)
+    __shared__ double alpha_s[VP_MAX_Q];
+    const int tid = threadIdx.x;
+    dbg_mark(dbg, 0);
+    if (tid < VP_MAX_Q) alpha_s[tid] = tid < md.q ? alpha_dev[tid] : 0.0;
+    double xi[RPT], wi[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = tid + r * THREADS;
+        const bool in = i < md.m;
+        xi[r] = in ? (double)x[i] : 0.0;
+        wi[r] = in ? (w ? (double)w[i] : 1.0) : 0.0;
+    }
+    __syncthreads();
+    panel_hh_body<T, N, P, RPT, THREADS>(md, xi, wi, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg);
 }
 
 } // namespace vp

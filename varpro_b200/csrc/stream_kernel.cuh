@@ -127,14 +127,19 @@ __device__ __forceinline__ void warp_fold(double (&red)[NACC], const int lane)
 // grid, no shuffles. sh: >= 64 doubles; scratch: >= 16 * blockDim/16 + p*p doubles.
 constexpr int FIN_SCRATCH = 16 * 32 + VP_MAX_P * VP_MAX_P + 64 + 4 * 48; // also holds a FitDevice copy (static_assert below)
 static_assert(FIT_WORDS <= FIN_SCRATCH, "FitDevice must fit in the finalize scratch");
-template <typename T>
+// SMEM_SMALL: a.small points to shared memory (fit_kernel_dmma keeps the panel's small outputs in
+// the CTA) -- plain loads instead of ld.global.cg. GRAPH_TAIL: run the CUDA-graph LM tail.
+template <typename T, bool SMEM_SMALL = false, bool GRAPH_TAIL = true>
 __device__ void stream_finalize(const StreamArgs<T> &a, int n, int p, int nparts, double *sh, double *scratch)
 {
     const int nv = red_count(n, p);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int k = tid & 15, c0 = tid >> 4, nc0 = nt >> 4;
     double *Msh = scratch + 16 * 32;
-    if (tid < p * p) Msh[tid] = __ldcg(&a.small->M[(tid / p) * VP_MAX_P + (tid % p)]); // Msh[f*p + e]
+    if (tid < p * p) { // Msh[f*p + e]
+        const double *msrc = &a.small->M[(tid / p) * VP_MAX_P + (tid % p)];
+        Msh[tid] = SMEM_SMALL ? *msrc : __ldcg(msrc);
+    }
     int nonfinite = 0;
     if (tid == 0) nonfinite = a.small->nonfinite;
     dbg_mark(a.dbg, 11);
@@ -198,7 +203,7 @@ __device__ void stream_finalize(const StreamArgs<T> &a, int n, int p, int nparts
         *a.ticket = 0; // re-arm for the next launch
         dbg_mark(a.dbg, 13);
     }
-    if (a.fit) {
+    if (GRAPH_TAIL && a.fit) {
         // graph path: advance the lmder state machine on a shared-memory copy of the state
         // (cooperative load/store: one 8-byte word per thread) and steer the while node
         __syncthreads();
@@ -257,9 +262,8 @@ __device__ __forceinline__ void stream_epilogue(const StreamArgs<T> &a, int n, i
 // finish. Written for few instructions: it runs once per CTA and these kernels
 // live for a few microseconds.
 template <typename T, int N, int P, int CT, int NW>
-__device__ __forceinline__ void cta_publish(const StreamArgs<T> &a, double rn2, const double *Gacc, const double *Vacc,
-                                            double *wsum /* NW */, double *gv /* CT*(NG+P) */, double *sh,
-                                            double *scratch, int *is_last)
+__device__ __forceinline__ void cta_publish_partial(const StreamArgs<T> &a, double rn2, const double *Gacc, const double *Vacc,
+                                                    double *wsum /* NW */, double *gv /* CT*(NG+P) */, int *is_last)
 {
     constexpr int NG = N * (N + 1) / 2, NGP = NG + P, NVR = 1 + NGP;
     static_assert(NVR <= 32, "the partial row must be written by one warp");
@@ -299,6 +303,14 @@ __device__ __forceinline__ void cta_publish(const StreamArgs<T> &a, double rn2, 
     }
     __syncthreads();
     dbg_mark(a.dbg, 5);
+}
+
+template <typename T, int N, int P, int CT, int NW>
+__device__ __forceinline__ void cta_publish(const StreamArgs<T> &a, double rn2, const double *Gacc, const double *Vacc,
+                                            double *wsum /* NW */, double *gv /* CT*(NG+P) */, double *sh,
+                                            double *scratch, int *is_last)
+{
+    cta_publish_partial<T, N, P, CT, NW>(a, rn2, Gacc, Vacc, wsum, gv, is_last);
     if (*is_last) {
         stream_finalize<T>(a, N, P, gridDim.x, sh, scratch);
         dbg_mark(a.dbg, 6);

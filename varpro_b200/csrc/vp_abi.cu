@@ -21,6 +21,7 @@
 #include "lm_step.cuh"
 #include "panel_kernel.cuh"
 #include "stream_kernel.cuh"
+#include "fit_kernel_dmma.cuh"
 
 using namespace vp;
 
@@ -45,6 +46,8 @@ struct vp_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     BufferPool dev_pool, host_pool;
+    std::vector<cudaStream_t> side_streams; // vp_fit_many: one per concurrent fit
+    cudaEvent_t fork_event = nullptr, join_event = nullptr;
 };
 
 static cudaError_t pool_alloc(BufferPool &pool, bool host, void **out, size_t bytes)
@@ -106,8 +109,22 @@ struct vp_model {
     int ld = 0; // padded row count (multiple of 16/sizeof(T))
 };
 
+// Column-sharded global fit across the GPUs of one box (one process per GPU): this rank's
+// mailbox (device memory exported through CUDA IPC) plus the peers' mailboxes mapped over NVLink.
+struct vp_comm {
+    vp_ctx *ctx = nullptr;
+    int world = 1, rank = 0;
+    bool connected = false;
+    CommMailbox *local_box = nullptr;
+    unsigned long long *epoch = nullptr; // device
+    int *error = nullptr;                // device
+    void *peer[COMM_MAX_WORLD] = {nullptr};
+    CommArgs args{};
+};
+
 struct vp_problem {
     vp_ctx *ctx = nullptr;
+    vp_comm *comm = nullptr;
     vp_model *model = nullptr;
     int64_t S = 0;
     void *Yw = nullptr;    // ld x S
@@ -144,6 +161,11 @@ struct vp_problem {
     int plan_ct = 1;    // columns per tile
     int plan_grid = 0, plan_nst = 0;
     size_t plan_smem = 0;
+    // fused evaluation / persistent fit kernel (fit_kernel_dmma), -1 = not available
+    int plan_fit = -1;
+    int fit_grid = 0, fit_nst = 0;
+    size_t fit_smem = 0;
+    FitBcast *bcast = nullptr;
 };
 
 static int env_int(const char *name, int dflt)
@@ -237,6 +259,9 @@ extern "C" int vp_ctx_destroy(vp_ctx *ctx)
     cudaSetDevice(ctx->device);
     pool_release(ctx->dev_pool, false);
     pool_release(ctx->host_pool, true);
+    for (cudaStream_t s2 : ctx->side_streams) cudaStreamDestroy(s2);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
+    if (ctx->join_event) cudaEventDestroy(ctx->join_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return VP_OK;
@@ -338,6 +363,7 @@ extern "C" int vp_model_destroy(vp_model *model)
 static std::vector<StreamKernelEntry> g_stream_kernels;
 static std::vector<DmmaKernelEntry> g_dmma_kernels;
 static std::vector<PanelHHEntry> g_panel_kernels;
+static std::vector<FitKernelEntry> g_fit_kernels;
 static int g_num_stream_kernels = 0, g_num_dmma_kernels = 0;
 static void gather_kernel_tables()
 {
@@ -349,12 +375,51 @@ static void gather_kernel_tables()
         g_stream_kernels.insert(g_stream_kernels.end(), g->simt, g->simt + g->nsimt);            \
         g_dmma_kernels.insert(g_dmma_kernels.end(), g->dmma, g->dmma + g->ndmma);                \
         g_panel_kernels.insert(g_panel_kernels.end(), g->panel, g->panel + g->npanel);           \
+        g_fit_kernels.insert(g_fit_kernels.end(), g->fit, g->fit + g->nfit);                     \
     }
     VP_KERNEL_GROUPS(VP_GATHER)
 #undef VP_GATHER
     g_num_stream_kernels = (int)g_stream_kernels.size();
     g_num_dmma_kernels = (int)g_dmma_kernels.size();
     done = true;
+}
+
+// the fused evaluation / persistent fit kernel matching a DMMA plan (same tiling), if instantiated
+static int plan_fit_kernel(vp_problem *pr, const DmmaKernelEntry &dk, int lds)
+{
+    vp_ctx *ctx = pr->ctx;
+    pr->plan_fit = -1;
+    const char *which = getenv("VP_EVAL_KERNEL"); // "fused" (default) or "split" (K1 + K2)
+    if (which && !strcmp(which, "split")) return VP_OK;
+    for (size_t i = 0; i < g_fit_kernels.size(); ++i) {
+        const FitKernelEntry &k = g_fit_kernels[i];
+        if (k.n != dk.n || k.p != dk.p || k.ksteps != dk.ksteps || k.nwarps != dk.nwarps || k.exact != dk.exact) continue;
+        const size_t stage_bytes = (size_t)DMMA_CT * lds * sizeof(double);
+        cudaFuncAttributes fa{};
+        VP_CUDA(ctx, cudaFuncGetAttributes(&fa, k.fn));
+        if (fa.sharedSizeBytes + 1024 + 2 * stage_bytes > 227 * 1024) return VP_OK;
+        const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
+        int nst = (int)(budget / stage_bytes);
+        if (nst > STREAM_MAX_STAGES) nst = STREAM_MAX_STAGES;
+        const int max_st = env_int("VP_STREAM_STAGES", 0);
+        if (max_st >= 2 && nst > max_st) nst = max_st;
+        if (nst < 2) return VP_OK;
+        const size_t smem = (size_t)nst * stage_bytes;
+        VP_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.nwarps * 32, smem));
+        if (occ < 1) return VP_OK;
+        const long long ntiles = (pr->S + DMMA_CT - 1) / DMMA_CT;
+        long long grid = (long long)ctx->sm_count * occ; // co-resident by construction (cooperative launch checks it)
+        if (grid > ntiles) grid = ntiles;
+        if (grid > pr->max_grid) grid = pr->max_grid;
+        pr->plan_fit = (int)i;
+        pr->fit_grid = (int)grid;
+        pr->fit_nst = nst;
+        pr->fit_smem = smem;
+        return VP_OK;
+    }
+    return VP_OK;
 }
 
 // choose the kernel instantiation, stage count and grid for a problem
@@ -382,8 +447,9 @@ static int plan_stream(vp_problem *pr)
             if (k.n != md.n || k.p != md.p) continue;
             const int rows = 4 * k.ksteps * k.nwarps;
             if (rows < mo->ld) continue;
-            if (k.exact != (rows <= lds ? 1 : 0)) continue;
-            if (pick < 0 || rows < 4 * g_dmma_kernels[pick].ksteps * g_dmma_kernels[pick].nwarps) pick = i;
+            if (k.exact && rows > lds) continue; // the unpredicated variant needs rows <= lds
+            const int prow = pick < 0 ? 0 : 4 * g_dmma_kernels[pick].ksteps * g_dmma_kernels[pick].nwarps;
+            if (pick < 0 || rows < prow || (rows == prow && k.exact && !g_dmma_kernels[pick].exact)) pick = i;
         }
         if (pick >= 0) {
             const DmmaKernelEntry &k = g_dmma_kernels[pick];
@@ -412,7 +478,7 @@ static int plan_stream(vp_problem *pr)
                     pr->plan_grid = (int)grid;
                     pr->plan_nst = nst;
                     pr->plan_smem = smem;
-                    return VP_OK;
+                    return plan_fit_kernel(pr, k, lds);
                 }
             }
         }
@@ -564,6 +630,49 @@ static int launch_stream_t(vp_problem *pr, int cdst, bool graph_mode)
     return VP_OK;
 }
 
+// One launch of fit_kernel_dmma: a single fused evaluation (fit_mode = false; result in out_dev,
+// coefficients into buffer cdst) or a whole fit (fit_mode = true; cooperative launch, state in fit_dev).
+static int launch_fused(vp_problem *pr, int cdst, bool fit_mode, cudaStream_t stream = nullptr, int grid = 0)
+{
+    vp_ctx *ctx = pr->ctx;
+    vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    const FitKernelEntry &k = g_fit_kernels[pr->plan_fit];
+    if (!stream) stream = ctx->stream;
+    if (grid <= 0 || grid > pr->fit_grid) grid = pr->fit_grid;
+    StreamArgs<double> a{};
+    a.Y = (const double *)pr->Yw; a.ld = mo->ld; a.S = (int)pr->S;
+    a.Pq = nullptr; a.Pe = nullptr; a.ldp = pr->ldp; a.small = nullptr;
+    {
+        const long long ntiles = (pr->S + DMMA_CT - 1) / DMMA_CT;
+        a.tiles_base = (int)(ntiles / grid);
+        a.tiles_rem = (int)(ntiles % grid);
+    }
+    a.C0 = (double *)pr->C[0]; a.C1 = (double *)pr->C[1]; a.cdst = cdst;
+    a.fit = fit_mode ? pr->fit_dev : nullptr;
+    a.cond = 0ull;
+    a.partials = pr->partials; a.red_stride = pr->red_stride; a.ticket = pr->ticket; a.out = pr->out_dev;
+    a.nstages = pr->fit_nst; a.q = md.q; a.dbg = pr->dbg;
+    for (int e = 0; e < VP_MAX_P; ++e) { a.e_basis[e] = md.e_basis[e]; a.e_param[e] = md.e_param[e]; }
+    FitArgs f{};
+    f.md = md;
+    f.x = (const double *)mo->x_dev; f.w = (const double *)pr->w_dev;
+    f.svd_eps = pr->svd_eps;
+    f.alpha_dev = pr->alpha_dev;
+    f.bc = pr->bcast;
+    if (pr->comm) f.comm = pr->comm->args;
+    int lds = pr->plan_lds;
+    void *args[] = {(void *)&a, (void *)&lds, (void *)&f};
+    if (fit_mode) {
+        VP_CUDA(ctx, cudaMemsetAsync(pr->bcast, 0, sizeof(FitBcast), stream));
+        VP_CUDA(ctx, cudaLaunchCooperativeKernel(k.fn, dim3(grid), dim3(k.nwarps * 32), args, pr->fit_smem, stream));
+    } else {
+        VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(grid), dim3(k.nwarps * 32), args, pr->fit_smem, stream));
+    }
+    ctx->launches++;
+    return VP_OK;
+}
+
 static int launch_panel(vp_problem *pr)
 {
     return pr->model->dtype == VP_F32 ? launch_panel_t<float>(pr) : launch_panel_t<double>(pr);
@@ -574,8 +683,21 @@ static int launch_stream(vp_problem *pr, int cdst, bool graph_mode = false)
 }
 static int launch_eval(vp_problem *pr, int cdst)
 {
+    if (pr->plan_fit >= 0) return launch_fused(pr, cdst, false);
     int rc = launch_panel(pr);
     return rc != VP_OK ? rc : launch_stream(pr, cdst);
+}
+
+// after a collective evaluation: did the NVLink exchange time out?
+static int comm_check(vp_problem *pr)
+{
+    if (!pr->comm) return VP_OK;
+    int err = 0;
+    vp_ctx *ctx = pr->ctx;
+    VP_CUDA(ctx, cudaMemcpyAsync(&err, pr->comm->error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) return fail(ctx, VP_ERR_COMM, "timed out waiting for a peer GPU's contribution (ranks must make the same sequence of calls)");
+    return VP_OK;
 }
 
 // Evaluate at `alpha` into coefficient buffer `cdst`; result in pr->out_host.
@@ -591,7 +713,7 @@ static int evaluate_sync(vp_problem *pr, const double *alpha, int cdst)
     if (rc != VP_OK) return rc;
     VP_CUDA(ctx, cudaMemcpyAsync(pr->out_host, pr->out_dev, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
     VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VP_OK;
+    return comm_check(pr);
 }
 
 static void evalout_to_lm(const EvalOut &o, int q, LmEval &ev)
@@ -654,10 +776,12 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     VP_TRY(DEV_ALLOC(ctx, &pr->fit_dev, sizeof(FitDevice)));
     VP_TRY(cudaMemsetAsync(pr->fit_dev, 0, sizeof(FitDevice), ctx->stream));
     VP_TRY(HOST_ALLOC(ctx, &pr->fit_host, sizeof(FitDevice)));
+    VP_TRY(DEV_ALLOC(ctx, &pr->bcast, sizeof(FitBcast)));
+    VP_TRY(cudaMemsetAsync(pr->bcast, 0, sizeof(FitBcast), ctx->stream));
     pr->alpha_dev = &pr->fit_dev->st.x_trial[0];
     VP_TRY(DEV_ALLOC(ctx, &pr->phi_scratch, sizeof(double) * (size_t)m * md.n));
     VP_TRY(HOST_ALLOC(ctx, &pr->out_host, sizeof(EvalOut)));
-    VP_TRY(HOST_ALLOC(ctx, &pr->alpha_stage, sizeof(double) * VP_MAX_Q));
+    VP_TRY(HOST_ALLOC(ctx, &pr->alpha_stage, sizeof(double) * VP_MAX_Q + sizeof(FitBcast)));
     if (w_host) {
         VP_TRY(DEV_ALLOC(ctx, &pr->w_dev, es * (size_t)m));
         VP_TRY(cudaMemcpyAsync(pr->w_dev, w_host, es * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
@@ -718,7 +842,7 @@ extern "C" int vp_problem_destroy(vp_problem *pr)
     vp_ctx *ctx = pr->ctx;
     DEV_FREE(ctx, pr->Yw); DEV_FREE(ctx, pr->w_dev); DEV_FREE(ctx, pr->Pq); DEV_FREE(ctx, pr->small);
     DEV_FREE(ctx, pr->C[0]); DEV_FREE(ctx, pr->C[1]); DEV_FREE(ctx, pr->partials); DEV_FREE(ctx, pr->ticket);
-    DEV_FREE(ctx, pr->out_dev); DEV_FREE(ctx, pr->fit_dev); DEV_FREE(ctx, pr->phi_scratch);
+    DEV_FREE(ctx, pr->out_dev); DEV_FREE(ctx, pr->fit_dev); DEV_FREE(ctx, pr->phi_scratch); DEV_FREE(ctx, pr->bcast);
     cudaFree(pr->dbg);
     if (pr->fit_exec) cudaGraphExecDestroy(pr->fit_exec);
     if (pr->fit_graph) cudaGraphDestroy(pr->fit_graph);
@@ -764,23 +888,17 @@ extern "C" int vp_reduce(vp_problem *pr, vp_reduced *out)
     return pr->cached ? VP_OK : fail(pr->ctx, VP_ERR_NO_CACHED_CALCULATION, vp_status_string(VP_ERR_NO_CACHED_CALCULATION));
 }
 
-// make sure the panel buffers (Pq, Pe) correspond to pr->alpha (a rejected LM
-// trial leaves them at the trial point)
+// The materialisers read the panel [Q | E] from HBM: build it with K1 at the accepted parameters
+// (the fused kernel keeps the panel on chip, and a rejected LM trial leaves K1's buffers at the
+// trial point). The coefficients C[cur] already belong to pr->alpha.
 static int ensure_panel_current(vp_problem *pr)
 {
-    PanelSmall sm;
     vp_ctx *ctx = pr->ctx;
-    VP_CUDA(ctx, cudaMemcpyAsync(&sm, pr->small, sizeof(sm), cudaMemcpyDeviceToHost, ctx->stream));
-    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    bool same = true;
-    for (int k = 0; k < pr->model->md.q; ++k) same = same && (sm.alpha[k] == pr->alpha[k]);
-    if (same) return VP_OK;
-    // re-evaluate at the accepted parameters into the spare coefficient buffer
-    const int dst = pr->cur ^ 1;
-    int rc = evaluate_sync(pr, pr->alpha, dst);
-    if (rc != VP_OK) return rc;
-    pr->cur = dst;
-    return VP_OK;
+    const int q = pr->model->md.q;
+    for (int k = 0; k < q; ++k) pr->alpha_stage[k] = pr->alpha[k];
+    if (q > 0)
+        VP_CUDA(ctx, cudaMemcpyAsync(pr->alpha_dev, pr->alpha_stage, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
+    return launch_panel(pr);
 }
 
 template <typename T>
@@ -842,6 +960,99 @@ extern "C" int vp_linear_coefficients(vp_problem *pr, void *out_host)
     return VP_OK;
 }
 
+// ----------------------------------------------------------------------------
+// vp_comm: column-sharded global fit over the GPUs of one box
+// ----------------------------------------------------------------------------
+extern "C" int vp_comm_create(vp_ctx *ctx, int rank, int world, vp_comm **out, void *local_handle_out)
+{
+    if (!ctx || !out || !local_handle_out) return VP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(ctx, VP_ERR_INVALID_ARGUMENT, "vp_comm_create: need 0 <= rank < world <= 8");
+    static_assert(sizeof(cudaIpcMemHandle_t) == VP_COMM_HANDLE_BYTES, "handle size");
+    cudaSetDevice(ctx->device);
+    vp_comm *c = new (std::nothrow) vp_comm();
+    if (!c) return VP_ERR_OUT_OF_MEMORY;
+    c->ctx = ctx; c->world = world; c->rank = rank;
+    // plain cudaMalloc (not the pool): the allocation is exported through CUDA IPC
+    cudaError_t e = cudaMalloc(&c->local_box, sizeof(CommMailbox));
+    if (e == cudaSuccess) e = cudaMemset(c->local_box, 0, sizeof(CommMailbox));
+    if (e == cudaSuccess) e = cudaMalloc(&c->epoch, 256);
+    if (e == cudaSuccess) e = cudaMemset(c->epoch, 0, 256);
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(&h, c->local_box);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(c->local_box); cudaFree(c->epoch);
+        delete c;
+        return fail(ctx, VP_ERR_COMM, std::string("vp_comm_create: ") + cudaGetErrorString(e));
+    }
+    c->error = reinterpret_cast<int *>(c->epoch + 8);
+    memcpy(local_handle_out, &h, sizeof(h));
+    c->peer[rank] = c->local_box;
+    if (world == 1) { // nothing to map
+        c->args.world = 1; c->args.rank = 0; c->args.epoch = c->epoch; c->args.error = c->error;
+        c->args.box[0] = c->local_box;
+        c->connected = true;
+    }
+    *out = c;
+    return VP_OK;
+}
+
+extern "C" int vp_comm_connect(vp_comm *c, const void *all_handles)
+{
+    if (!c || !all_handles) return VP_ERR_INVALID_ARGUMENT;
+    if (c->connected) return VP_OK;
+    vp_ctx *ctx = c->ctx;
+    cudaSetDevice(ctx->device);
+    const unsigned char *hs = static_cast<const unsigned char *>(all_handles);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)r * VP_COMM_HANDLE_BYTES, sizeof(h));
+        cudaError_t e = cudaIpcOpenMemHandle(&c->peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(ctx, VP_ERR_COMM, "vp_comm_connect: cannot map the mailbox of rank " + std::to_string(r) + ": " +
+                                              cudaGetErrorString(e));
+    }
+    c->args.world = c->world; c->args.rank = c->rank; c->args.epoch = c->epoch; c->args.error = c->error;
+    for (int r = 0; r < c->world; ++r) c->args.box[r] = static_cast<CommMailbox *>(c->peer[r]);
+    c->connected = true;
+    return VP_OK;
+}
+
+extern "C" int vp_comm_destroy(vp_comm *c)
+{
+    if (!c) return VP_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    cudaFree(c->local_box);
+    cudaFree(c->epoch);
+    delete c;
+    return VP_OK;
+}
+
+extern "C" int vp_problem_set_comm(vp_problem *pr, vp_comm *c)
+{
+    if (!pr) return VP_ERR_INVALID_ARGUMENT;
+    vp_ctx *ctx = pr->ctx;
+    if (c && (c->ctx != ctx || !c->connected)) return fail(ctx, VP_ERR_COMM, "vp_problem_set_comm: communicator not connected / wrong context");
+    if (c && pr->plan_fit < 0)
+        return fail(ctx, VP_ERR_COMM, "column-sharded fits need the fused fp64 kernel (no instantiation for this model shape)");
+    pr->comm = c;
+    // the evaluation made at creation covered this rank's columns only: redo it collectively
+    const int dst = pr->cur ^ 1;
+    int rc = evaluate_sync(pr, pr->alpha, dst);
+    if (rc != VP_OK) { pr->cached = false; return rc; }
+    pr->cur = dst;
+    evalout_to_lm(*pr->out_host, pr->model->md.q, pr->eval);
+    pr->cached = pr->eval.finite != 0;
+    return VP_OK;
+}
+
 // Build (once per problem) the CUDA graph of a whole fit: a conditional WHILE node whose body
 // is one evaluation, K1 (panel at the trial parameters) -> K2 (streaming reduce; its last CTA
 // advances the lmder state machine on the device and sets the loop condition).
@@ -879,12 +1090,10 @@ static int ensure_fit_graph(vp_problem *pr)
 // ----------------------------------------------------------------------------
 // LevMarSolver::fit  (src/solvers/levmar/mod.rs:238-254)
 // ----------------------------------------------------------------------------
-extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *rep)
+static void lm_config_from_options(const vp_problem *pr, const vp_lm_options *opt, LmConfig &cfg)
 {
-    if (!pr || !rep) return VP_ERR_INVALID_ARGUMENT;
     const int q = pr->model->md.q;
     const double eps = pr->model->dtype == VP_F32 ? (double)FLT_EPSILON : DBL_EPSILON;
-    LmConfig cfg;
     cfg.epsmch = eps;
     cfg.ftol = (opt && opt->ftol > 0) ? opt->ftol : 30.0 * eps;
     cfg.xtol = (opt && opt->xtol > 0) ? opt->xtol : 30.0 * eps;
@@ -893,6 +1102,65 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
     const int patience = (opt && opt->patience > 0) ? opt->patience : 100;
     cfg.maxfev = patience * (q + 1);
     cfg.scale_diag = (opt && opt->scale_diag >= 0) ? (opt->scale_diag != 0) : 1;
+}
+
+static void fill_report(const LmState &st, vp_fit_report *rep)
+{
+    rep->termination = st.termination;
+    rep->number_of_evaluations = st.nfev;
+    rep->objective_function = 0.5 * st.fnorm * st.fnorm;
+    rep->successful = lm_successful(st.termination) ? 1 : 0;
+}
+
+// Persistent-kernel fit, asynchronous halves. begin: upload the LM state (already advanced past the
+// cached evaluation at the starting point) and enqueue the ONE cooperative launch plus the
+// read-back on `stream`; end (after the stream has been synchronised): adopt the final state.
+static int fit_persistent_begin(vp_problem *pr, const LmState &st, const LmConfig &cfg, cudaStream_t stream, int grid)
+{
+    vp_ctx *ctx = pr->ctx;
+    if (env_int("VP_DBG_FIT", 0) && !pr->dbg) { // in-kernel timeline of the last evaluation (vp_debug_timeline reads it)
+        const size_t nd = ((size_t)pr->max_grid + 1) * VP_DBG_SLOTS;
+        VP_CUDA(ctx, cudaMalloc(&pr->dbg, nd * sizeof(unsigned long long)));
+        VP_CUDA(ctx, cudaMemset(pr->dbg, 0, nd * sizeof(unsigned long long)));
+    }
+    FitDevice *fh = pr->fit_host;
+    memset(fh, 0, sizeof(FitDevice));
+    fh->st = st; fh->cfg = cfg; fh->accepted = pr->eval; fh->cur = pr->cur; fh->evals = 0;
+    VP_CUDA(ctx, cudaMemcpyAsync(pr->fit_dev, fh, sizeof(FitDevice), cudaMemcpyHostToDevice, stream));
+    int rc = launch_fused(pr, 0, /*fit_mode=*/true, stream, grid);
+    if (rc != VP_OK) return rc;
+    VP_CUDA(ctx, cudaMemcpyAsync(fh, pr->fit_dev, sizeof(FitDevice), cudaMemcpyDeviceToHost, stream));
+    FitBcast *bh = reinterpret_cast<FitBcast *>(pr->alpha_stage + VP_MAX_Q); // pinned staging (allocated with alpha_stage)
+    VP_CUDA(ctx, cudaMemcpyAsync(bh, pr->bcast, sizeof(FitBcast), cudaMemcpyDeviceToHost, stream));
+    return VP_OK;
+}
+
+static int fit_persistent_end(vp_problem *pr, LmState &st)
+{
+    vp_ctx *ctx = pr->ctx;
+    const int q = pr->model->md.q;
+    FitDevice *fh = pr->fit_host;
+    const FitBcast *bh = reinterpret_cast<const FitBcast *>(pr->alpha_stage + VP_MAX_Q);
+    if (bh->error) return fail(ctx, VP_ERR_CUDA, "vp_fit: grid-wide wait timed out inside the persistent fit kernel");
+    int rc = comm_check(pr);
+    if (rc != VP_OK) return rc;
+    st = fh->st;
+    pr->cur = fh->cur;
+    pr->eval = fh->accepted;
+    for (int k = 0; k < q; ++k) pr->alpha[k] = st.x[k];
+    if (env_int("VP_TRACE", 0))
+        for (int i = 0; i < fh->evals && i < 48; ++i)
+            fprintf(stderr, "[vp_fit persistent] eval %d fnorm_trial=%.6e par=%.3e delta=%.3e acc=%d\n", i + 2, fh->trace[4 * i],
+                    fh->trace[4 * i + 1], fh->trace[4 * i + 2], (int)fh->trace[4 * i + 3]);
+    return VP_OK;
+}
+
+extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *rep)
+{
+    if (!pr || !rep) return VP_ERR_INVALID_ARGUMENT;
+    const int q = pr->model->md.q;
+    LmConfig cfg;
+    lm_config_from_options(pr, opt, cfg);
     memset(rep, 0, sizeof(*rep));
 
     LmState st;
@@ -907,7 +1175,19 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
     }
     // the evaluation at the current parameters is cached (builder / set_params)
     bool more = lm_advance(st, cfg, pr->eval);
-    const char *mode = getenv("VP_FIT_MODE"); // "graph" (default) or "host"
+    const char *mode = getenv("VP_FIT_MODE"); // "persistent" (default when the fused kernel exists), "graph" or "host"
+    if (more && pr->plan_fit >= 0 && !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph")))) {
+        // ---- persistent grid: the whole fit is ONE cooperative kernel launch ------------------
+        vp_ctx *ctx = pr->ctx;
+        cudaSetDevice(ctx->device);
+        int rc = fit_persistent_begin(pr, st, cfg, ctx->stream, 0);
+        if (rc != VP_OK) return rc;
+        VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        rc = fit_persistent_end(pr, st);
+        if (rc != VP_OK) return rc;
+        more = false;
+    }
+    if (more && pr->comm) return fail(pr->ctx, VP_ERR_COMM, "column-sharded fits run on the persistent fit kernel only");
     if (more && !(mode && !strcmp(mode, "host"))) {
         // ---- device-driven loop: one CUDA graph launch per fit ------------------------
         vp_ctx *ctx = pr->ctx;
@@ -949,11 +1229,82 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
             for (int k = 0; k < q; ++k) pr->alpha[k] = st.x[k];
         }
     }
-    rep->termination = st.termination;
-    rep->number_of_evaluations = st.nfev;
-    rep->objective_function = 0.5 * st.fnorm * st.fnorm;
-    rep->successful = lm_successful(st.termination) ? 1 : 0;
+    fill_report(st, rep);
     return VP_OK;
+}
+
+// Many independent fits at once (throughput mode). A single fit on the whole GPU is latency
+// bound: per evaluation the panel, the grid-wide reduction and the serial LM step cost more than
+// streaming 33.5 MB does. Independent problems are therefore run CONCURRENTLY, each as its own
+// persistent fit kernel on a slice of the SMs (grid = #SMs / n, at least 1 CTA), on separate
+// streams: while one fit sits in its LM step the others keep HBM busy, and the panel is
+// recomputed by few CTAs instead of 148. Problems that cannot use the persistent kernel are
+// fitted one after the other with vp_fit.
+extern "C" int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *opt, vp_fit_report *reports,
+                           int32_t max_concurrent)
+{
+    if (n < 0 || (n > 0 && (!problems || !reports))) return VP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return VP_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (!problems[i] || problems[i]->ctx != problems[0]->ctx) return VP_ERR_INVALID_ARGUMENT;
+    vp_ctx *ctx = problems[0]->ctx;
+    cudaSetDevice(ctx->device);
+    const char *mode = getenv("VP_FIT_MODE");
+    const bool persistent_ok = !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph")));
+    int64_t width = max_concurrent > 0 ? max_concurrent : ctx->sm_count;
+    if (width > n) width = n;
+    if (width > ctx->sm_count) width = ctx->sm_count;
+    // SMs per fit: the first (sm_count % width) fits get one more, so that all SMs are used
+    const int grid_base = (int)(ctx->sm_count / width) > 0 ? (int)(ctx->sm_count / width) : 1;
+    const int grid_rem = (int)(ctx->sm_count / width) > 0 ? (int)(ctx->sm_count % width) : 0;
+    while ((int64_t)ctx->side_streams.size() < width) {
+        cudaStream_t s2 = nullptr;
+        VP_CUDA(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        ctx->side_streams.push_back(s2);
+    }
+    if (!ctx->fork_event) VP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    if (!ctx->join_event) VP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
+    // the side streams start after everything already enqueued on the context's stream ...
+    VP_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
+    for (int64_t w = 0; w < width; ++w) VP_CUDA(ctx, cudaStreamWaitEvent(ctx->side_streams[w], ctx->fork_event, 0));
+    std::vector<LmState> states((size_t)n);
+    std::vector<char> launched((size_t)n, 0);
+    int first_error = VP_OK;
+    for (int64_t i = 0; i < n; ++i) {
+        vp_problem *pr = problems[i];
+        memset(&reports[i], 0, sizeof(vp_fit_report));
+        LmConfig cfg;
+        lm_config_from_options(pr, opt, cfg);
+        LmState &st = states[(size_t)i];
+        lm_init(st, pr->model->md.q, pr->alpha);
+        if (!pr->cached || pr->plan_fit < 0 || pr->comm || !persistent_ok) continue; // handled by vp_fit below
+        if (!lm_advance(st, cfg, pr->eval)) { launched[(size_t)i] = 2; continue; }   // terminated at the starting point
+        const int grid = grid_base + ((i % width) < grid_rem ? 1 : 0);
+        int rc = fit_persistent_begin(pr, st, cfg, ctx->side_streams[(size_t)(i % width)], grid);
+        if (rc != VP_OK) { if (first_error == VP_OK) first_error = rc; continue; }
+        launched[(size_t)i] = 1;
+    }
+    // ... and the context's stream continues after all of them (events recorded by the caller on
+    // the context's stream therefore bracket the whole batch)
+    for (int64_t w = 0; w < width; ++w) {
+        VP_CUDA(ctx, cudaEventRecord(ctx->join_event, ctx->side_streams[w]));
+        VP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_event, 0));
+    }
+    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        vp_problem *pr = problems[i];
+        if (launched[(size_t)i] == 1) {
+            int rc = fit_persistent_end(pr, states[(size_t)i]);
+            if (rc != VP_OK) { if (first_error == VP_OK) first_error = rc; continue; }
+            fill_report(states[(size_t)i], &reports[i]);
+        } else if (launched[(size_t)i] == 2) {
+            fill_report(states[(size_t)i], &reports[i]);
+        } else if (first_error == VP_OK || pr->plan_fit < 0) {
+            int rc = vp_fit(pr, opt, &reports[i]);
+            if (rc != VP_OK && first_error == VP_OK) first_error = rc;
+        }
+    }
+    return first_error;
 }
 
 // ----------------------------------------------------------------------------
@@ -976,7 +1327,10 @@ extern "C" int vp_profile_evaluation(vp_problem *pr, int iters, int64_t flush_by
         VP_CUDA(ctx, cudaMemcpyAsync(pr->alpha_dev, pr->alpha_stage, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
     int rc = VP_OK;
     // warm-up: keep the device busy long enough for the clocks to ramp up
+    const bool fused = pr->plan_fit >= 0;
+    if (pr->comm) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "vp_profile_evaluation: not for column-sharded problems");
     for (int it = 0; it < 64 && rc == VP_OK; ++it) {
+        if (fused) { rc = launch_fused(pr, pr->cur ^ 1, false); continue; }
         rc = launch_panel(pr);
         if (rc == VP_OK) rc = launch_stream(pr, pr->cur ^ 1);
     }
@@ -984,9 +1338,9 @@ extern "C" int vp_profile_evaluation(vp_problem *pr, int iters, int64_t flush_by
     for (int it = 0; it < iters && rc == VP_OK; ++it) {
         if (flush) cudaMemsetAsync(flush, it & 0xff, (size_t)flush_bytes, ctx->stream);
         cudaEventRecord(ev[3 * it + 0], ctx->stream);
-        rc = launch_panel(pr);
+        if (!fused) rc = launch_panel(pr);
         cudaEventRecord(ev[3 * it + 1], ctx->stream);
-        if (rc == VP_OK) rc = launch_stream(pr, pr->cur ^ 1);
+        if (rc == VP_OK) rc = fused ? launch_fused(pr, pr->cur ^ 1, false) : launch_stream(pr, pr->cur ^ 1);
         cudaEventRecord(ev[3 * it + 2], ctx->stream);
     }
     cudaStreamSynchronize(ctx->stream);
@@ -1003,8 +1357,8 @@ extern "C" int vp_profile_evaluation(vp_problem *pr, int iters, int64_t flush_by
     if (rc != VP_OK) return rc;
     if (panel_us) *panel_us = 1e3 * tp / iters;
     if (stream_us) *stream_us = 1e3 * ts / iters;
-    if (stream_grid) *stream_grid = pr->plan_grid;
-    if (stream_smem) *stream_smem = (int64_t)pr->plan_smem;
+    if (stream_grid) *stream_grid = fused ? pr->fit_grid : pr->plan_grid;
+    if (stream_smem) *stream_smem = (int64_t)(fused ? pr->fit_smem : pr->plan_smem);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, cudaGetErrorString(e));
     return VP_OK;
@@ -1024,8 +1378,7 @@ extern "C" int vp_debug_timeline(vp_problem *pr, long long *out, int64_t capacit
     int rc = VP_OK;
     for (int it = 0; it < 3 && rc == VP_OK && !read_only; ++it) { // warm, then the recorded one
         VP_CUDA(ctx, cudaMemsetAsync(pr->dbg, 0, n * sizeof(unsigned long long), ctx->stream));
-        rc = launch_panel(pr);
-        if (rc == VP_OK) rc = launch_stream(pr, pr->cur ^ 1);
+        rc = launch_eval(pr, pr->cur ^ 1);
     }
     std::vector<unsigned long long> h(n);
     VP_CUDA(ctx, cudaMemcpyAsync(h.data(), pr->dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1037,12 +1390,12 @@ extern "C" int vp_debug_timeline(vp_problem *pr, long long *out, int64_t capacit
     if (rc != VP_OK) return rc;
     unsigned long long t0 = ~0ull;
     for (auto v : h) if (v && v < t0) t0 = v;
-    const size_t rows = (size_t)pr->plan_grid;
+    const size_t rows = (size_t)(pr->plan_fit >= 0 ? pr->fit_grid : pr->plan_grid);
     size_t k = 0;
     for (size_t b = 0; b <= rows && k + VP_DBG_SLOTS <= (size_t)capacity; ++b) {
         const size_t src = (b < rows ? b : (size_t)pr->max_grid) * VP_DBG_SLOTS;
         for (int s2 = 0; s2 < VP_DBG_SLOTS; ++s2) out[k++] = h[src + s2] ? (long long)(h[src + s2] - t0) : -1;
     }
-    if (grid_out) *grid_out = pr->plan_grid;
+    if (grid_out) *grid_out = (int64_t)rows;
     return VP_OK;
 }

@@ -1,10 +1,9 @@
 #!/bin/bash
-# ncu evidence: launch list of the bench command + one full capture of the streaming kernel (kept < 64 MiB).
+# ncu evidence for the bench command: launch list + one full capture of a whole-fit launch of the
+# persistent kernel (kept < 64 MiB) + one of a single-evaluation launch.
 TAG=${1:-r01}
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 30 -c 1 -f -o gpurun_out/${TAG}_k2 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
-S=4096 TIMELINE=1 timeout 300 python scripts/gpu_probe.py > gpurun_out/${TAG}_probe_4096.log 2>&1
-S=131072 timeout 300 python scripts/gpu_probe.py > gpurun_out/${TAG}_probe_131072.log 2>&1
-VP_TRACE=1 S=4096 timeout 300 python scripts/gpu_probe.py 2>&1 | grep "vp_fit" | head -60 > gpurun_out/${TAG}_trace.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
+# bench launch order per warm-up batch: 20 single-evaluation launches (problem builds), then 20 whole-fit launches
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fit_kernel -s 25 -c 1 -f -o gpurun_out/${TAG}_fit python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out

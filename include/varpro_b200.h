@@ -234,6 +234,28 @@ int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *rep
 int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *options, vp_fit_report *reports,
                 int32_t max_concurrent);
 
+/* ---- independent batch (BASELINE config 3) -------------------------------------
+ * P independent single-RHS problems that share the model structure, x and the
+ * weights but have their own observations (column p of Y), nonlinear parameters
+ * (column p of alpha0, q x P column-major) and linear coefficients: the loop
+ *   for p in 0..P { LevMarSolver::fit(SeparableProblemBuilder::new(model_p).observations(y_p).build()) }
+ * over the reference API (src/problem/builder.rs:116-324, src/solvers/levmar/mod.rs:238-254),
+ * executed as ONE kernel launch: one CTA fits one problem from start to finish (y_p is
+ * read from HBM once, Phi(alpha_p) is regenerated on the fly, per-problem LM state) and
+ * then takes the next. fp64 models. vp_batch_fit starts from the current parameters
+ * (alpha0 at first, the previous result afterwards; vp_batch_set_params overrides);
+ * reports (P entries) may be NULL. */
+typedef struct vp_batch vp_batch;
+int vp_batch_create(vp_ctx *ctx, vp_model *model, int64_t P, const void *Y_host, int64_t ldY, const void *w_host,
+                    double svd_eps, const double *alpha0, vp_batch **out);
+int vp_batch_create_device(vp_ctx *ctx, vp_model *model, int64_t P, const void *Y_device, int64_t ldY,
+                           const void *w_host, double svd_eps, const double *alpha0, vp_batch **out);
+int vp_batch_destroy(vp_batch *batch);
+int vp_batch_fit(vp_batch *batch, const vp_lm_options *options, vp_fit_report *reports);
+int vp_batch_params(vp_batch *batch, double *alpha_out);            /* q x P */
+int vp_batch_set_params(vp_batch *batch, const double *alpha);      /* q x P */
+int vp_batch_linear_coefficients(vp_batch *batch, double *C_out);   /* n x P */
+
 /* ---- diagnostics ---------------------------------------------------------
  * Device time (CUDA events on the context's stream, microseconds, averaged over
  * `iters`) of the two kernels of one evaluation at the current parameters:

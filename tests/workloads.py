@@ -161,3 +161,20 @@ def make_gpu_problem(wl, alpha0=None, Y=None, dtype=np.float64, device=0, ctx_sl
     if wl.get("weights") is not None:
         pb = pb.weights(wl["weights"])
     return pb.device(device, ctx_slot).build()
+
+
+def c4(S=16384, seed=16384, dtype=np.float32):
+    """BASELINE config 4: x, y0 = the reference's weighted lmfit asset
+    (test_assets/weighted_multiexp_decay), w = 1/sqrt(y0) shared by all right-hand sides; column 0 = y0
+    (pinned by the lmfit goldens), columns s >= 1 = Phi(2.4, 6.0) c_s + N(0, 0.01^2) with
+    c_s = (2.2, 6.8, 1.6) * U[0.5, 1.5)^3. Global fit from alpha0 = (1, 7); cast to `dtype`."""
+    d = np.load(os.path.join(GOLDEN, "lmfit_weighted_multiexp_decay.npz"))
+    x, y0 = d["x"], d["y"]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    Phi = np.stack([np.exp(-x / 2.4), np.exp(-x / 6.0), np.ones_like(x)], axis=1)
+    Cs = np.array([2.2, 6.8, 1.6])[:, None] * rng.uniform(0.5, 1.5, size=(3, S))
+    Y = Phi @ Cs + rng.normal(0.0, 0.01, size=(x.shape[0], S))
+    Y[:, 0] = y0
+    w = 1.0 / np.sqrt(y0)
+    return dict(x=x.astype(dtype), Y=np.asfortranarray(Y.astype(dtype)), basis=DOUBLE_EXP, q=2, alpha0=[1.0, 7.0],
+                weights=w.astype(dtype), C_gen=Cs)

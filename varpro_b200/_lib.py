@@ -72,6 +72,13 @@ SYMBOLS = {
     "vp_problem_set_comm": (C.c_int, [_vp, _vp]),
     "vp_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),
     "vp_fit_many": (C.c_int, [_pp, C.c_int64, C.POINTER(LmOptions), C.POINTER(FitReport), C.c_int32]),
+    "vp_batch_create": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),
+    "vp_batch_create_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),
+    "vp_batch_destroy": (C.c_int, [_vp]),
+    "vp_batch_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),
+    "vp_batch_params": (C.c_int, [_vp, _dp]),
+    "vp_batch_set_params": (C.c_int, [_vp, _dp]),
+    "vp_batch_linear_coefficients": (C.c_int, [_vp, _dp]),
     "vp_debug_timeline": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.c_int64, C.POINTER(C.c_int64)]),
     "vp_profile_evaluation": (C.c_int, [_vp, C.c_int, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int64)]),

@@ -641,3 +641,98 @@ class LevMarSolver:
             out.append(FitResult(p, MinimizationReport(TerminationReason(rep.termination),
                                                        rep.number_of_evaluations, rep.objective_function)))
         return out
+
+
+# ---------------------------------------------------------------------------
+# independent batch (BASELINE config 3): P single-RHS problems in one launch
+# ---------------------------------------------------------------------------
+class BatchFitResult:
+    """Per-problem results of IndependentBatch.fit: arrays over the P problems."""
+
+    def __init__(self, params, coefficients, terminations, evaluations, objectives):
+        self.nonlinear_parameters = params            # (P, q)
+        self.linear_coefficients = coefficients       # (n, P)
+        self.terminations = [TerminationReason(int(t)) for t in terminations]
+        self.number_of_evaluations = evaluations      # (P,)
+        self.objective_function = objectives          # (P,) 0.5*||r_w||^2
+        self.successful = np.array([t.was_successful() for t in self.terminations])
+
+
+class IndependentBatch:
+    """P independent problems sharing the model structure, x and weights (vp_batch): the loop
+    `for p: LevMarSolver.fit(SeparableProblemBuilder.new(model_p).observations(Y[:, p]).build())`
+    over the reference API, as one kernel launch. `initial_parameters`: (P, q)."""
+
+    def __init__(self, model: SeparableModel, Y, initial_parameters, weights=None, eps=-1.0, device=0,
+                 y_device_ptr=None, P=None):
+        lib = _lib.load()
+        if model.dtype != np.float64:
+            raise VarproError("IndependentBatch: fp64 models only")
+        self._ctx = _Ctx.get(device)
+        self._m, self._n, self._q = model.output_len(), model.base_function_count(), model.parameter_count()
+        self._model_h = C.c_void_p()
+        self._h = C.c_void_p()
+        _check(lib.vp_model_create(self._ctx.h, VP_F64, self._m, model.x.ctypes.data_as(C.c_void_p), self._q, self._n,
+                                   model._descs(), C.byref(self._model_h)), self._ctx.h)
+        a0 = np.ascontiguousarray(initial_parameters, dtype=np.float64)  # (P, q) row-major == q x P column-major
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        wp = None if w is None else w.ctypes.data_as(C.c_void_p)
+        try:
+            if y_device_ptr is not None:
+                self._P = int(P)
+                if a0.shape != (self._P, self._q):
+                    raise InvalidParameterCount("initial_parameters must have shape (P, q)")
+                _check(lib.vp_batch_create_device(self._ctx.h, self._model_h, self._P, C.c_void_p(y_device_ptr), self._m, wp,
+                                                  float(eps), a0.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self._h)),
+                       self._ctx.h)
+            else:
+                Yf = np.asfortranarray(Y, dtype=np.float64)
+                if Yf.ndim != 2 or Yf.shape[0] != self._m:
+                    raise InvalidLengthOfData(f"Vectors x and y must have same lengths. Given x length = {self._m} "
+                                              f"and y length = {Yf.shape[0]}")
+                self._P = Yf.shape[1]
+                if a0.shape != (self._P, self._q):
+                    raise InvalidParameterCount("initial_parameters must have shape (P, q)")
+                _check(lib.vp_batch_create(self._ctx.h, self._model_h, self._P, Yf.ctypes.data_as(C.c_void_p), self._m, wp,
+                                           float(eps), a0.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self._h)),
+                       self._ctx.h)
+        except Exception:
+            lib.vp_model_destroy(self._model_h)
+            self._model_h = C.c_void_p()
+            raise
+
+    def set_params(self, parameters):
+        a = np.ascontiguousarray(parameters, dtype=np.float64)
+        if a.shape != (self._P, self._q):
+            raise InvalidParameterCount("parameters must have shape (P, q)")
+        _check(_lib.load().vp_batch_set_params(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), self._ctx.h)
+
+    def fit(self, solver: Optional["LevMarSolver"] = None, reports: bool = True) -> Optional[BatchFitResult]:
+        lib = _lib.load()
+        opts = (solver or LevMarSolver())._solver._o
+        reps = (_lib.FitReport * self._P)() if reports else None
+        _check(lib.vp_batch_fit(self._h, C.byref(opts), reps), self._ctx.h)
+        if not reports:
+            return None
+        alpha = np.empty((self._P, self._q), dtype=np.float64)
+        Cc = np.empty((self._n, self._P), dtype=np.float64, order="F")
+        _check(lib.vp_batch_params(self._h, alpha.ctypes.data_as(C.POINTER(C.c_double))), self._ctx.h)
+        _check(lib.vp_batch_linear_coefficients(self._h, Cc.ctypes.data_as(C.POINTER(C.c_double))), self._ctx.h)
+        rr = np.frombuffer(reps, dtype=np.dtype([("termination", "<i4"), ("nfev", "<i4"), ("obj", "<f8"),
+                                                  ("ok", "<i4"), ("res", "<i4")]))
+        return BatchFitResult(alpha, Cc, rr["termination"].copy(), rr["nfev"].copy(), rr["obj"].copy())
+
+    def close(self):
+        lib = _lib.load()
+        if getattr(self, "_h", None) and self._h.value:
+            lib.vp_batch_destroy(self._h)
+            self._h = C.c_void_p()
+        if getattr(self, "_model_h", None) and self._model_h.value:
+            lib.vp_model_destroy(self._model_h)
+            self._model_h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

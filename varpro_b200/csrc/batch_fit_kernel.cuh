@@ -1,0 +1,308 @@
+// batch_fit_kernel.cuh -- K4: independent-batch evaluator + fit (BASELINE config 3).
+//
+// P independent problems share the model structure, the independent variable x and the weights,
+// but each has its OWN observations y_p, nonlinear parameters alpha_p and linear coefficients c_p:
+// what a user of the reference writes as a loop over SingleRhs problems,
+//   for p in 0..P { LevMarSolver::default().fit(SeparableProblemBuilder::new(model_p).observations(y_p).build()) }
+// (src/problem/builder.rs:116-324, src/solvers/levmar/mod.rs:238-254 per problem).
+//
+// One CTA fits one problem at a time, start to finish, and then takes the next one from a global
+// counter (fits need different numbers of evaluations): y_p is read from HBM ONCE per fit and stays
+// in registers; per evaluation the CTA
+//   1. regenerates Phi_w(alpha_p), D(alpha_p) from x into a shared-memory working matrix (m x (n+p))
+//      -- materialising Phi for 65 536 problems would take 6.4 GB --
+//   2. runs n Householder steps on [Phi_w | D | y] (y carried along in registers): one fused block
+//      reduction per step (panel_kernel_hh.cuh explains the identities),
+//   3. one more reduction over the rows >= n of the rotated system gives everything the LM step
+//      needs:  ||r||^2 = sum y~_i^2,  u_e = D~_e . y~,  M_ef = D~_e . D~_f   and the top rows give
+//      c = R1^-1 y~[0:n];  then  g_k = -sum_{e in k} c_j(e) u_e,  H_kl = sum M_ef c_j(e) c_j(f)
+//      (the S = 1 case of the formulas in stream_kernel.cuh; no explicit Q or E is formed),
+//   4. thread 0 advances the lmder state machine (lm_step.cuh) in shared memory.
+// Bound: fp64 ALU / exp and block-reduction latency, not HBM (32 KB of y per fit against ~15
+// evaluations of ~0.5 MFLOP each).
+#pragma once
+
+#include "device_common.cuh"
+#include "lm_step.cuh"
+#include "panel_kernel_hh.cuh"
+
+namespace vp {
+
+struct BatchArgs {
+    ModelDesc md;
+    const double *x;      // m
+    const double *w;      // m or nullptr
+    const double *Y;      // ld x P observations (unweighted), column p = problem p
+    long long ld;
+    long long P;
+    double svd_eps;
+    LmConfig cfg;
+    const double *alpha0; // q x P
+    double *alpha_out;    // q x P
+    double *C_out;        // n x P
+    double *obj_out;      // P: 0.5 * ||r_w||^2
+    int *term_out;        // P: Termination
+    int *nfev_out;        // P
+    unsigned long long *next; // work counter (zeroed by the host)
+    int mpad;             // rows of the shared-memory working matrix (>= m, multiple of 2)
+};
+
+template <int N, int P, int RPT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+batch_fit_kernel(const BatchArgs a)
+{
+    constexpr int NPV = N + P;
+    constexpr int NW = THREADS / 32;
+    constexpr int NTAIL = 1 + P + P * (P + 1) / 2; // ||r||^2, u_e, M_ef (upper)
+    constexpr int KMAX = (NTAIL > NPV + 1) ? NTAIL : NPV + 1;
+    extern __shared__ __align__(16) double colm[]; // NPV columns of mpad doubles
+    __shared__ double red[2][NW * KMAX];
+    __shared__ double top[N][NPV + 1]; // rows 0..n-1 of the rotated system (R, Q^T D, Q^T y)
+    __shared__ double alpha_s[VP_MAX_Q];
+    __shared__ LmState st_s;
+    __shared__ LmEval ev_s;
+    __shared__ double coef_s[N], coef_acc[N];
+    __shared__ long long prob_s;
+    __shared__ int more_s;
+
+    const int tid = threadIdx.x;
+    const int m = a.md.m, mpad = a.mpad, q = a.md.q;
+
+    // the thread's rows of x and w (shared by all problems)
+    double xi[RPT], wi[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = tid + r * THREADS;
+        const bool in = i < m;
+        xi[r] = in ? a.x[i] : 0.0;
+        wi[r] = in ? (a.w ? a.w[i] : 1.0) : 0.0;
+    }
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) prob_s = (long long)atomicAdd(a.next, 1ull);
+        __syncthreads();
+        const long long prob = prob_s;
+        if (prob >= a.P) break;
+
+        // y_p: HBM -> registers, once per fit; weighted like builder.rs:307
+        double y[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = tid + r * THREADS;
+            y[r] = (i < m) ? wi[r] * __ldcs(&a.Y[(size_t)prob * a.ld + i]) : 0.0;
+        }
+        if (tid == 0) {
+            double x0[VP_MAX_Q];
+            for (int k = 0; k < VP_MAX_Q; ++k) x0[k] = k < q ? a.alpha0[(size_t)prob * q + k] : 0.0;
+            lm_init(st_s, q, x0);
+            more_s = 1;
+        }
+        __syncthreads();
+
+        while (more_s) {
+            if (tid < VP_MAX_Q) alpha_s[tid] = tid < q ? st_s.x_trial[tid] : 0.0;
+            __syncthreads();
+
+            // ---- 1. Phi_w, D into the working matrix (rolled over basis functions, rows unrolled) ----
+            int bad = 0;
+            {
+                int e = 0;
+#pragma unroll 1
+                for (int j = 0; j < N; ++j) {
+                    const int kind = a.md.kind[j], np = a.md.npar[j];
+                    const double a0 = np > 0 ? alpha_s[a.md.pidx[j][0]] : 0.0;
+                    const double a1 = np > 1 ? alpha_s[a.md.pidx[j][1]] : 0.0;
+                    const double scale = a.md.scale[j];
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        const int i = tid + r * THREADS;
+                        double v, da = 0.0, db = 0.0;
+                        if (kind == VP_BASIS_EXP_DECAY) {
+                            const double ex = exp(-xi[r] / a0);
+                            v = ex; da = ex * xi[r] / (a0 * a0);
+                        } else if (kind == VP_BASIS_EXP_RATE_COS) {
+                            const double ex = exp(-a0 * xi[r]);
+                            double sn, cs;
+                            sincos(a1 * xi[r], &sn, &cs);
+                            v = ex * cs; da = -xi[r] * (ex * cs); db = -xi[r] * ex * sn;
+                        } else if (kind == VP_BASIS_SIN_PHASE) {
+                            double sn, cs;
+                            sincos(a0 * xi[r] + a1, &sn, &cs);
+                            v = sn; da = xi[r] * cs; db = cs;
+                        } else {
+                            v = kind == VP_BASIS_CONSTANT ? 1.0 : (kind == VP_BASIS_LINEAR_X ? scale * xi[r] : nan(""));
+                        }
+                        if (i < m) {
+                            const double pv = wi[r] * v, pa = wi[r] * da, pb = wi[r] * db;
+                            bad |= !isfinite(pv) | ((np > 0) & !isfinite(pa)) | ((np > 1) & !isfinite(pb));
+                            colm[(size_t)j * mpad + i] = pv;
+                            if (np > 0) colm[(size_t)(N + e) * mpad + i] = pa;
+                            if (np > 1) colm[(size_t)(N + e + 1) * mpad + i] = pb;
+                        }
+                    }
+                    e += np;
+                }
+            }
+            bad = __syncthreads_or(bad);
+
+            // ---- 2. Householder steps on [Phi_w | D | y] (y in registers) ----------------------------
+            double yt[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) yt[r] = y[r];
+            double rdiag[N];
+            int dropped = 0;
+#pragma unroll
+            for (int J = 0; J < N; ++J) {
+                const int K = NPV - J + 1; // sigma, dots with the columns to the right, dot with y
+                double s[NPV + 1];
+#pragma unroll
+                for (int k = 0; k < NPV + 1; ++k) s[k] = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int i = tid + r * THREADS;
+                    if (i >= J && i < m) {
+                        const double aj = colm[(size_t)J * mpad + i];
+#pragma unroll
+                        for (int k = 0; k < NPV - J; ++k) s[k] = fma(aj, colm[(size_t)(J + k) * mpad + i], s[k]);
+                        s[NPV - J] = fma(aj, yt[r], s[NPV - J]);
+                    }
+                }
+                if (tid == J) { // row J is owned by thread J (r = 0): publish it
+#pragma unroll
+                    for (int k = 0; k < NPV; ++k) top[J][k] = colm[(size_t)k * mpad + J];
+                    top[J][NPV] = yt[0];
+                }
+                {
+                    double sv[KMAX];
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) sv[k] = (k < K) ? s[k] : 0.0;
+                    block_sum_once<KMAX, NW>(sv, red[J & 1]);
+#pragma unroll
+                    for (int k = 0; k < NPV + 1; ++k) s[k] = sv[k < KMAX ? k : 0];
+                }
+                const double sigma = s[0];
+                const double ajj = top[J][J];
+                const double nrm = sqrt(sigma);
+                const bool keep = isfinite(nrm) && nrm > a.svd_eps;
+                const double al = (ajj >= 0.0) ? -nrm : nrm;
+                const double vnorm2 = 2.0 * (sigma - ajj * al);
+                const double bt = (keep && vnorm2 > 0.0) ? 2.0 / vnorm2 : 0.0;
+                rdiag[J] = keep ? al : 0.0;
+                if (!keep) dropped |= 1 << J;
+                const double vjj = ajj - al;
+                double tau[NPV + 1];
+#pragma unroll
+                for (int k = 1; k < NPV - J; ++k) tau[k] = bt * (s[k] - al * top[J][J + k]);
+                const double tau_y = bt * (s[NPV - J] - al * top[J][NPV]);
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int i = tid + r * THREADS;
+                    if (i >= J && i < m) {
+                        const double vi = (i > J) ? colm[(size_t)J * mpad + i] : vjj;
+#pragma unroll
+                        for (int k = 1; k < NPV - J; ++k)
+                            colm[(size_t)(J + k) * mpad + i] = fma(-tau[k], vi, colm[(size_t)(J + k) * mpad + i]);
+                        yt[r] = fma(-tau_y, vi, yt[r]);
+                    }
+                }
+                __syncthreads(); // everyone has read top[J]; its owner rewrites it with the final row
+                if (tid == J) {
+#pragma unroll
+                    for (int k = J + 1; k < NPV; ++k) top[J][k] = colm[(size_t)k * mpad + J]; // R[J][k], (Q^T D)[J][:]
+                    top[J][NPV] = yt[0];                                                        // (Q^T y)[J]
+                }
+            }
+
+            // ---- 3. tail reduction: rows >= n (plus the rows of dropped columns) --------------------
+            {
+                double tv[KMAX];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) tv[k] = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int i = tid + r * THREADS;
+                    const bool tail = (i < m) && (i >= N || ((dropped >> i) & 1));
+                    if (tail) {
+                        const double yv = yt[r];
+                        tv[0] = fma(yv, yv, tv[0]);
+                        double de[P > 0 ? P : 1];
+#pragma unroll
+                        for (int e = 0; e < P; ++e) {
+                            de[e] = colm[(size_t)(N + e) * mpad + i];
+                            tv[1 + e] = fma(de[e], yv, tv[1 + e]);
+                        }
+                        int t = 1 + P;
+#pragma unroll
+                        for (int e = 0; e < P; ++e)
+#pragma unroll
+                            for (int f2 = e; f2 < P; ++f2) { tv[t] = fma(de[e], de[f2], tv[t]); ++t; }
+                    }
+                }
+                block_sum_once<KMAX, NW>(tv, red[N & 1]);
+                // ---- 4. thread 0: coefficients, (||r||^2, g, H), LM step -------------------------------
+                if (tid == 0) {
+                    double coef[N];
+#pragma unroll
+                    for (int i = N - 1; i >= 0; --i) {
+                        double sacc = top[i][NPV];
+#pragma unroll
+                        for (int k = i + 1; k < N; ++k) sacc -= top[i][k] * coef[k];
+                        coef[i] = ((dropped >> i) & 1) ? 0.0 : sacc / rdiag[i];
+                    }
+                    LmEval &ev = ev_s;
+                    ev.rnorm2 = tv[0];
+                    int finite = !bad && isfinite(tv[0]);
+                    for (int k = 0; k < VP_LM_MAXQ; ++k) ev.g[k] = 0.0;
+                    for (int k = 0; k < VP_LM_MAXQ * VP_LM_MAXQ; ++k) ev.H[k] = 0.0;
+                    double Mm[P > 0 ? P : 1][P > 0 ? P : 1];
+                    {
+                        int t = 1 + P;
+#pragma unroll
+                        for (int e = 0; e < P; ++e)
+#pragma unroll
+                            for (int f2 = e; f2 < P; ++f2) { Mm[e][f2] = tv[t]; Mm[f2][e] = tv[t]; ++t; }
+                    }
+#pragma unroll
+                    for (int e = 0; e < P; ++e) {
+                        double ce = 0.0;
+#pragma unroll
+                        for (int r = 0; r < N; ++r) ce = (a.md.e_basis[e] == r) ? coef[r] : ce;
+                        const int ke = a.md.e_param[e];
+                        ev.g[ke] -= ce * tv[1 + e];
+#pragma unroll
+                        for (int f2 = 0; f2 < P; ++f2) {
+                            double cf = 0.0;
+#pragma unroll
+                            for (int r = 0; r < N; ++r) cf = (a.md.e_basis[f2] == r) ? coef[r] : cf;
+                            ev.H[a.md.e_param[f2] * q + ke] += Mm[e][f2] * ce * cf;
+                        }
+                    }
+                    for (int k = 0; k < q; ++k) finite = finite && isfinite(ev.g[k]);
+                    for (int k = 0; k < q * q; ++k) finite = finite && isfinite(ev.H[k]);
+                    ev.finite = finite;
+#pragma unroll
+                    for (int r = 0; r < N; ++r) coef_s[r] = coef[r];
+                    const bool more = lm_advance(st_s, a.cfg, ev);
+                    if (st_s.last_accepted) {
+#pragma unroll
+                        for (int r = 0; r < N; ++r) coef_acc[r] = coef_s[r];
+                    }
+                    more_s = more ? 1 : 0;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- results of this problem ---------------------------------------------------------------
+        if (tid == 0) {
+            for (int k = 0; k < q; ++k) a.alpha_out[(size_t)prob * q + k] = st_s.x[k];
+            for (int r = 0; r < N; ++r) a.C_out[(size_t)prob * N + r] = coef_acc[r];
+            a.obj_out[prob] = 0.5 * st_s.fnorm * st_s.fnorm;
+            a.term_out[prob] = st_s.termination;
+            a.nfev_out[prob] = st_s.nfev;
+        }
+    }
+}
+
+} // namespace vp

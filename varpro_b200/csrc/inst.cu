@@ -1,6 +1,7 @@
 // inst.cu -- one group of kernel instantiations; compiled once per entry of VP_KERNEL_GROUPS with
 //   -DVP_INST_TAG=<tag> -DVP_INST_T=<double|float> -DVP_INST_DT=<VP_F64|VP_F32> -DVP_INST_N=n -DVP_INST_P=p -DVP_INST_PART=<0|1|2>
 #include "kernel_tables.h"
+#include "batch_fit_kernel.cuh"
 #include "fit_kernel_dmma.cuh"
 #include "panel_kernel_hh.cuh"
 #include "stream_kernel.cuh"
@@ -19,7 +20,7 @@ typedef VP_INST_T T_;
     {VP_INST_DT, N_, P_, THREADS, CHUNKS, CT, (const void *)&stream_kernel<T_, N_, P_, CHUNKS, CT, THREADS>}
 static const StreamKernelEntry simt_tab[] = {VP_SK(128, 1, 4), VP_SK(128, 4, 4), VP_SK(128, 4, 8), VP_SK(256, 4, 4),
                                              VP_SK(256, 8, 4)};
-static const KernelGroup group = {simt_tab, (int)(sizeof(simt_tab) / sizeof(simt_tab[0])), nullptr, 0, nullptr, 0, nullptr, 0};
+static const KernelGroup group = {simt_tab, (int)(sizeof(simt_tab) / sizeof(simt_tab[0])), nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0};
 #elif VP_INST_PART == 1
 // EXACT (unpredicated fragment loads) only for the 1024-row tiling the benchmark shapes use
 #define VP_DK(KS, NW, EX) {N_, P_, KS, NW, EX, (const void *)&stream_kernel_dmma<N_, P_, KS, NW, (EX) != 0>}
@@ -35,6 +36,11 @@ static const FitKernelEntry fit_tab[] = {VP_FK(32, 8, 0), VP_FK(32, 8, 1)};
 static const FitKernelEntry fit_tab[] = {VP_FK(32, 16, 0)};
 #endif
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, fit_tab, (int)(sizeof(fit_tab) / sizeof(fit_tab[0]))};
+#elif VP_INST_PART == 4
+constexpr int BATCH_THREADS = 512;
+#define VP_BK(RPT) {N_, P_, RPT, BATCH_THREADS, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS>}
+static const BatchKernelEntry batch_tab[] = {VP_BK(1), VP_BK(2), VP_BK(4), VP_BK(8)};
+static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, batch_tab, (int)(sizeof(batch_tab) / sizeof(batch_tab[0]))};
 #else
 constexpr int PANEL_HH_THREADS = 512;
 #define VP_PK(RPT) {VP_INST_DT, N_, P_, RPT, PANEL_HH_THREADS, (const void *)&panel_kernel_hh<T_, N_, P_, RPT, PANEL_HH_THREADS>}

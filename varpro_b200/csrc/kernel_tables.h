@@ -22,16 +22,21 @@ struct FitKernelEntry { // fit_kernel_dmma: fused panel + streaming reduce (+ wh
     int n, p, ksteps, nwarps, exact;
     const void *fn;
 };
+struct BatchKernelEntry { // batch_fit_kernel: one CTA fits one independent problem at a time
+    int n, p, rpt, threads;
+    const void *fn;
+};
 struct KernelGroup {
     const StreamKernelEntry *simt; int nsimt;
     const DmmaKernelEntry *dmma;   int ndmma;
     const PanelHHEntry *panel;     int npanel;
     const FitKernelEntry *fit;     int nfit;
+    const BatchKernelEntry *batch; int nbatch;
 };
 typedef const KernelGroup *(*KernelGroupFn)();
 
 // (tag, C type, vp_dtype, n, p, part): part 0 = SIMT streaming, 1 = DMMA streaming, 2 = Householder panel,
-// 3 = fused evaluation / persistent fit kernel.
+// 3 = fused evaluation / persistent fit kernel, 4 = independent-batch fit kernel.
 // The model shapes with a compiled fast path; everything else runs the generic kernels.
 #define VP_KERNEL_GROUPS(X)                 \
     X(f64_3_2_simt, double, VP_F64, 3, 2, 0) /* double exponential + offset (benches, C1/C2/C5) */ \
@@ -53,7 +58,10 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_2_4_panel, double, VP_F64, 2, 4, 2) \
     X(f64_2_4_fit0, double, VP_F64, 2, 4, 3) \
     X(f64_2_4_fit1, double, VP_F64, 2, 4, 3) \
-    X(f64_2_4_fit2, double, VP_F64, 2, 4, 3)
+    X(f64_2_4_fit2, double, VP_F64, 2, 4, 3) \
+    X(f64_3_3_batch, double, VP_F64, 3, 3, 4) \
+    X(f64_3_2_batch, double, VP_F64, 3, 2, 4) \
+    X(f64_2_4_batch, double, VP_F64, 2, 4, 4)
 
 #define VP_DECLARE_GROUP(tag, T, DT, N, P, PART) const KernelGroup *vp_kernel_group_##tag();
 VP_KERNEL_GROUPS(VP_DECLARE_GROUP)

@@ -24,8 +24,9 @@ criterion bench builds the problem in its un-timed setup closure and times `fit`
 `--impl reference` times that CPU restatement with all host threads instead (the Rust crate
 cannot be built in this image: no cargo/rustc).
 
-N > 1 (torchrun): every rank fits its own independent problems (weak scaling, no data-path
-collective); value = total fits / max-over-ranks time.
+N > 1 (torchrun): every rank fits its own copy of the same K independent problems (weak scaling: fixed
+per-GPU work, no data-path collective); value = total fits / max-over-ranks time. A `sharded_global_fit`
+object reports BASELINE config 5 (one global fit, 131 072 columns per GPU, in-kernel NVLink exchange).
 """
 from __future__ import annotations
 
@@ -157,7 +158,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
     K, Wm = args.steps, max(args.warmup, 3)
-    wl = c2_workload(seed=(2314093240213841123 + 7919 * rank) % (2 ** 63))
+    wl = c2_workload()  # every rank fits the same set of problems: fixed per-GPU work (weak scaling)
     solver = vb.LevMarSolver.default()
 
     def build(device_problem=True):
@@ -220,34 +221,40 @@ def run_gpu(args, rank, world, local_rank):
     probs.clear()
 
     # ---- e2e: host buffers -> build -> fit -> read back, every step ------------------------
-    # Two host threads (one library context = one stream each) alternate steps so that the H2D copy
-    # of one step overlaps the fit of the other; every step still pays its own copies.
-    NTH = 2
+    # A few host threads (one library context = one stream each) each take chunks of steps: build the
+    # chunk's problems from pinned host memory (one H2D of Y per step), fit them together
+    # (vp_fit_many), read every step's parameters and coefficients back (D2H). The copies of one
+    # thread overlap the fits of another; every step still pays its own copies.
+    NTH = int(os.environ.get("VP_E2E_THREADS", "3"))
+    CH = int(os.environ.get("VP_E2E_CHUNK", "1"))  # steps a worker builds, fits together (vp_fit_many) and reads back
     Yh = [torch.from_numpy(np.ascontiguousarray(wl["Y"].T)).pin_memory() for _ in range(NTH)]  # (S, m) row-major == m x S col-major
     Yv = [y.numpy().T for y in Yh]  # Fortran-ordered views of the pinned buffers
     h2d = Yh[0].numel() * 8 + M * 8
     d2h = N_BASIS * S_C2 * 8 + Q * 8
 
-    def e2e_step(slot):
-        p = W.make_gpu_problem(wl, Y=Yv[slot], device=local_rank, ctx_slot=1 + slot)
-        r = solver.fit(p)
-        a, c = r.nonlinear_parameters(), r.linear_coefficients()
-        p.close()
-        return a, c
+    def e2e_chunk(slot, nsteps):
+        ps = [W.make_gpu_problem(wl, Y=Yv[slot], device=local_rank, ctx_slot=1 + slot) for _ in range(nsteps)]  # H2D per step
+        rs = solver.fit_many(ps)
+        out = [(r.nonlinear_parameters(), r.linear_coefficients()) for r in rs]  # D2H per step
+        for p in ps:
+            p.close()
+        return out
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(NTH)
 
     def e2e_run(nsteps):
-        futs = [pool.submit(e2e_step, i % NTH) for i in range(nsteps)]
-        return [f.result() for f in futs]
+        chunks = [min(CH, nsteps - i) for i in range(0, nsteps, CH)]
+        futs = [pool.submit(e2e_chunk, i % NTH, c) for i, c in enumerate(chunks)]
+        return [o for f in futs for o in f.result()]
 
-    e2e_run(max(Wm, NTH))
+    e2e_run(max(Wm, NTH * CH))
     barrier()
     t0 = time.perf_counter()
     outs = e2e_run(K)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    assert len(outs) == K
     a, c = outs[-1]
     pool.shutdown()
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -305,7 +312,8 @@ def run_gpu(args, rank, world, local_rank):
                                     "per evaluation round (larger than the 126 MB L2 for K >= 4)",
                        "evals_per_fit_mean": float(np.mean(nfev)), "fit_mode": os.environ.get("VP_FIT_MODE", "persistent")},
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_threads": NTH, "steps_per_chunk": CH},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "fit_kernel_dmma<3,2,32,8> (persistent fit: panel + Y-streaming reduce + LM step)",

@@ -234,6 +234,18 @@ int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *rep
 int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *options, vp_fit_report *reports,
                 int32_t max_concurrent);
 
+/* ---- fit statistics: replaces FitStatistics::try_calculate (src/statistics/mod.rs:352-441) ----
+ * The reference computes statistics for a single right-hand side only
+ * (src/solvers/levmar/mod.rs:269-278); here the same calculation is applied to EVERY
+ * column s with the shared nonlinear parameters (BASELINE config 4):
+ *   cov_out          (n+q)^2 doubles per column, column-major blocks, ordering (c..., alpha...)
+ *                    as in the reference (:66-76, :507-510): chi2_s * (H_s^T H_s)^-1
+ *   reduced_chi2_out S doubles or NULL: ||r_w,s||^2 / (m - n - q)
+ *   conf_sigma_out   m x S doubles or NULL: sqrt(j_i^T Cov_s j_i) (:415-430); the caller
+ *                    scales by the Student-t quantile for a confidence band (:285-288)
+ * Errors: VP_ERR_UNDERDETERMINED (m <= n+q, :377-379), VP_ERR_MATRIX_INVERSION (:399). */
+int vp_statistics(vp_problem *problem, double *cov_out, double *reduced_chi2_out, double *conf_sigma_out);
+
 /* ---- independent batch (BASELINE config 3) -------------------------------------
  * P independent single-RHS problems that share the model structure, x and the
  * weights but have their own observations (column p of Y), nonlinear parameters

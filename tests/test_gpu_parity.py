@@ -411,3 +411,56 @@ def test_c3_independent_batch_weighted_double_exp_equals_single_problem_path():
         assert np.max(np.abs(res.nonlinear_parameters[p] - r1.nonlinear_parameters()) / r1.nonlinear_parameters()) <= 1e-7
         assert np.max(np.abs(res.linear_coefficients[:, p] - r1.linear_coefficients())) <= 1e-6
     batch.close()
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_statistics_lmfit_goldens(weighted):
+    """fit_with_statistics against the reference's lmfit goldens (tests/integration_tests/main.rs:600-612,
+    :670-687): chi2_red 1e-8, covariance 1e-6, 88% confidence band 1e-6 -- and against the oracle."""
+    import varpro_b200 as vb
+    wl = W.lmfit_case(weighted)
+    gp = W.make_gpu_problem(wl)
+    res, st = vb.LevMarSolver.default().fit_with_statistics(gp)
+    assert abs(st.reduced_chi2() - wl["gold"]["chi2"]) <= 1e-8
+    # lmfit orders (c1, c2, c3, tau1, tau2) == the reference's (c..., alpha...) ordering (main.rs:603)
+    assert np.max(np.abs(st.covariance_matrix() - wl["covmat"])) <= 1e-6
+    assert np.max(np.abs(st.confidence_band_radius(0.88) - wl["conf"])) <= 1e-6
+    op = W.make_oracle(wl)
+    op.fit()
+    so = op.statistics(0)
+    assert np.max(np.abs(st.covariance_matrix() - so["covariance"])) <= 1e-9 * np.abs(so["covariance"]).max() + 1e-12
+    assert abs(st.reduced_chi2() - so["reduced_chi2"]) <= 1e-10 * so["reduced_chi2"]
+
+
+def test_statistics_oleary_goldens():
+    import varpro_b200 as vb
+    wl = W.oleary()
+    gp = W.make_gpu_problem(wl)
+    res, st = vb.LevMarSolver.default().fit_with_statistics(gp)
+    assert abs(st.regression_standard_error() - wl["sigma"]) <= 1e-5                    # main.rs:780-784
+    cov = st.covariance_matrix()
+    assert np.allclose(cov, wl["cov"], rtol=0, atol=1e-5)                               # main.rs:786-802
+    assert np.allclose(st.calculate_correlation_matrix(), wl["corr"], rtol=0, atol=1e-4)  # main.rs:804-823
+
+
+def test_statistics_mrhs_every_column_matches_oracle():
+    """The reference supports SingleRhs statistics only; per column with the shared alpha the GPU result
+    must equal the oracle's try_calculate applied to that column (BASELINE config 4 semantics)."""
+    import varpro_b200 as vb
+    rng = np.random.default_rng(5)
+    m, S = 200, 7
+    x = np.linspace(0.0, 12.0, m)
+    w = rng.uniform(0.5, 1.5, size=m)
+    Cs = rng.uniform(1.0, 5.0, size=(3, S))
+    Phi = np.stack([np.exp(-x / 1.5), np.exp(-x / 4.0), np.ones_like(x)], axis=1)
+    Y = np.asfortranarray(Phi @ Cs + 1e-2 * rng.standard_normal((m, S)))
+    wl = dict(x=x, Y=Y, basis=W.DOUBLE_EXP, q=2, alpha0=[1.2, 5.0], weights=w)
+    gp, op = W.make_gpu_problem(wl), W.make_oracle(wl)
+    res, sts = vb.LevMarSolver.default().fit_with_statistics(gp)
+    op.fit()
+    assert len(sts) == S
+    for s in range(S):
+        so = op.statistics(s)
+        assert np.max(np.abs(sts[s].covariance_matrix() - so["covariance"])) <= 1e-6 * np.abs(so["covariance"]).max()
+        assert abs(sts[s].reduced_chi2() - so["reduced_chi2"]) <= 1e-8 * so["reduced_chi2"]
+        assert np.max(np.abs(sts[s]._sigma - so["unscaled_confidence_sigma"])) <= 1e-6 * np.abs(so["unscaled_confidence_sigma"]).max()

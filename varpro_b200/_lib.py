@@ -72,6 +72,7 @@ SYMBOLS = {
     "vp_problem_set_comm": (C.c_int, [_vp, _vp]),
     "vp_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),
     "vp_fit_many": (C.c_int, [_pp, C.c_int64, C.POINTER(LmOptions), C.POINTER(FitReport), C.c_int32]),
+    "vp_statistics": (C.c_int, [_vp, _dp, _dp, _dp]),
     "vp_batch_create": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),
     "vp_batch_create_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),
     "vp_batch_destroy": (C.c_int, [_vp]),

@@ -437,6 +437,20 @@ class SeparableProblem:
         return dict(rnorm2=r.rnorm2, g=np.array(r.g[:q]), H=np.array(r.H[:q * q]).reshape(q, q).T.copy(),
                     finite=bool(r.finite))
 
+    def statistics(self, confidence_sigma: bool = False):
+        """FitStatistics::try_calculate (src/statistics/mod.rs:352-441) for every right-hand side with the
+        shared nonlinear parameters (vp_statistics). Returns a list of FitStatistics (one per column)."""
+        t = self._n + self._q
+        cov = np.empty((self._S, t, t), dtype=np.float64)
+        chi2 = np.empty(self._S, dtype=np.float64)
+        conf = np.empty((self._S, self._m), dtype=np.float64) if confidence_sigma else None
+        dp = C.POINTER(C.c_double)
+        _check(_lib.load().vp_statistics(self._h, cov.ctypes.data_as(dp), chi2.ctypes.data_as(dp),
+                                         conf.ctypes.data_as(dp) if conf is not None else None), self._ctx.h)
+        dof = self._m - t
+        return [FitStatistics(cov[s].T.copy(), float(chi2[s]), dof, self._n, None if conf is None else conf[s])
+                for s in range(self._S)]
+
     def model(self) -> SeparableModel:
         return self.model_host
 
@@ -589,6 +603,44 @@ class FitResult:
         return self.minimization_report.termination.was_successful()
 
 
+class FitStatistics:
+    """src/statistics/mod.rs:24-345: covariance ordered (c..., alpha...), reduced chi^2, confidence band."""
+
+    def __init__(self, covariance, reduced_chi2, degrees_of_freedom, n_linear, conf_sigma):
+        self._cov = covariance
+        self._chi2 = reduced_chi2
+        self._dof = degrees_of_freedom
+        self._n = n_linear
+        self._sigma = conf_sigma
+
+    def covariance_matrix(self) -> np.ndarray:  # :66-76
+        return self._cov
+
+    def reduced_chi2(self) -> float:  # :244-246
+        return self._chi2
+
+    def regression_standard_error(self) -> float:  # :250-252
+        return float(np.sqrt(self._chi2))
+
+    def linear_coefficients_variance(self) -> np.ndarray:  # :134-139
+        return np.diag(self._cov)[: self._n].copy()
+
+    def nonlinear_parameters_variance(self) -> np.ndarray:  # :127-132
+        return np.diag(self._cov)[self._n:].copy()
+
+    def calculate_correlation_matrix(self) -> np.ndarray:  # :446-472
+        d = np.sqrt(np.diag(self._cov))
+        return self._cov / np.outer(d, d)
+
+    def confidence_band_radius(self, probability: float) -> np.ndarray:  # :275-291
+        if not (0.0 < probability < 1.0):
+            raise VarproError("probability must be in (0, 1)")
+        if self._sigma is None:
+            raise VarproError("statistics were computed without confidence_sigma=True")
+        from scipy import stats
+        return self._sigma * stats.t.ppf((probability + 1.0) / 2.0, self._dof)
+
+
 class FitError(VarproError):
     """Err(FitResult) of LevMarSolver::fit: carries the same FitResult in `.result`."""
 
@@ -621,6 +673,13 @@ class LevMarSolver:
         if not result.was_successful():
             raise FitError(result)
         return result
+
+    def fit_with_statistics(self, problem: SeparableProblem):
+        """src/solvers/levmar/mod.rs:275-304. The reference allows SingleRhs only; for an MRHS problem the
+        statistics of every column are returned as a list."""
+        result = self.fit(problem)
+        st = problem.statistics(confidence_sigma=True)
+        return result, (st[0] if problem.single_rhs else st)
 
     def fit_many(self, problems: Sequence[SeparableProblem], max_concurrent: int = 0) -> List[FitResult]:
         """Fit independent problems concurrently (vp_fit_many): the loop a caller of the reference

@@ -107,4 +107,170 @@ __global__ void best_fit_kernel(int m, int S, int n, const double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched fit statistics (reference: FitStatistics::try_calculate,
+// src/statistics/mod.rs:352-441, which supports a single right-hand side only -- here it is
+// applied to every column s with the shared alpha, which is what BASELINE config 4 asks for).
+//   J_s = [Phi, (dPhi/dalpha_k) c_s]  (m x (n+q), :486-511),  H_s = W J_s  (:373)
+//   chi2_s = ||r_w,s||^2 / (m - n - q)  (:383-388),  Cov_s = chi2_s (H_s^T H_s)^-1  (:397-400)
+//   conf_sigma_s[i] = sqrt(j_i^T Cov_s j_i), j_i = row i of the UNWEIGHTED J_s  (:415-430)
+// H_s^T H_s is assembled per column from the S-independent Gram matrix of W [Phi | D] and c_s.
+// ---------------------------------------------------------------------------------------------
+
+// unweighted [Phi | D]: m x (n+p), double (model.eval / eval_partial_deriv, src/model/mod.rs:441-512)
+template <typename T>
+__global__ void basis_kernel(ModelDesc md, const T *__restrict__ x, const double *__restrict__ alpha,
+                             double *__restrict__ out)
+{
+    const int m = md.m, n = md.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        int e = 0;
+        for (int j = 0; j < n; ++j) {
+            const int np = md.npar[j];
+            const double a0 = np > 0 ? alpha[md.pidx[j][0]] : 0.0;
+            const double a1 = np > 1 ? alpha[md.pidx[j][1]] : 0.0;
+            const BasisVals bv = basis_eval_all(md.kind[j], (double)x[i], a0, a1, md.scale[j]);
+            out[(size_t)j * m + i] = bv.v;
+            if (np > 0) out[(size_t)(n + e++) * m + i] = bv.d0;
+            if (np > 1) out[(size_t)(n + e++) * m + i] = bv.d1;
+        }
+    }
+}
+
+// Gm = (W B)^T (W B) for B = [Phi | D] (m x t0, t0 = n+p <= 20): one thread per entry
+template <typename T>
+__global__ void gram_kernel(int m, int t0, const double *__restrict__ B, const T *__restrict__ w, double *__restrict__ Gm)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= t0 * t0) return;
+    const int a = idx % t0, b = idx / t0;
+    if (a > b) return;
+    double acc = 0.0;
+    for (int i = 0; i < m; ++i) {
+        const double wi = w ? (double)w[i] : 1.0;
+        acc += (wi * B[(size_t)a * m + i]) * (wi * B[(size_t)b * m + i]);
+    }
+    Gm[b * t0 + a] = acc;
+    Gm[a * t0 + b] = acc;
+}
+
+constexpr int STATS_MAX_T = VP_MAX_N + VP_MAX_Q;
+
+// one warp per column
+template <typename T>
+__global__ void statistics_kernel(ModelDesc md, const T *__restrict__ Y, int ld, int ldp, int S, const T *__restrict__ Pq,
+                                  const T *__restrict__ C, const double *__restrict__ Gm, const double *__restrict__ B,
+                                  double *__restrict__ cov, double *__restrict__ chi2, double *__restrict__ conf,
+                                  int *__restrict__ fail_flag)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int m = md.m, n = md.n, p = md.p, q = md.q, t = n + q, t0 = n + p;
+    __shared__ double cov_s[8][STATS_MAX_T * STATS_MAX_T];
+    double *cv = cov_s[wib];
+    for (int s = blockIdx.x * wpb + wib; s < S; s += gridDim.x * wpb) {
+        // ||r_s||^2 with r_s = y_s - Q (Q^T y_s)
+        const T *y = Y + (size_t)s * ld;
+        double b[VP_MAX_N];
+#pragma unroll
+        for (int k = 0; k < VP_MAX_N; ++k) b[k] = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            const double yi = (double)y[i];
+#pragma unroll
+            for (int k = 0; k < VP_MAX_N; ++k)
+                if (k < n) b[k] += (double)Pq[(size_t)k * ldp + i] * yi;
+        }
+#pragma unroll
+        for (int k = 0; k < VP_MAX_N; ++k) b[k] = warp_sum(b[k]);
+        double rn2 = 0.0;
+        for (int i = lane; i < m; i += 32) {
+            double r = (double)y[i];
+#pragma unroll
+            for (int k = 0; k < VP_MAX_N; ++k)
+                if (k < n) r -= (double)Pq[(size_t)k * ldp + i] * b[k];
+            rn2 += r * r;
+        }
+        rn2 = warp_sum(rn2);
+        const double chi = rn2 / (double)(m - t);
+        double c[VP_MAX_N];
+#pragma unroll
+        for (int j = 0; j < VP_MAX_N; ++j) c[j] = j < n ? (double)C[(size_t)s * n + j] : 0.0;
+        int bad = 0;
+        if (lane == 0) {
+            // H^T H, ordering (c..., alpha...) (src/statistics/mod.rs:66-76)
+            double A[STATS_MAX_T * STATS_MAX_T];
+            for (int a = 0; a < t; ++a)
+                for (int bb = 0; bb < t; ++bb) {
+                    double v = 0.0;
+                    if (a < n && bb < n) v = Gm[bb * t0 + a];
+                    else if (a < n) {
+                        for (int e = 0; e < p; ++e)
+                            if (md.e_param[e] == bb - n) v += Gm[(n + e) * t0 + a] * c[md.e_basis[e]];
+                    } else if (bb < n) {
+                        for (int e = 0; e < p; ++e)
+                            if (md.e_param[e] == a - n) v += Gm[(n + e) * t0 + bb] * c[md.e_basis[e]];
+                    } else {
+                        for (int e = 0; e < p; ++e) {
+                            if (md.e_param[e] != a - n) continue;
+                            for (int f = 0; f < p; ++f)
+                                if (md.e_param[f] == bb - n) v += Gm[(n + f) * t0 + (n + e)] * c[md.e_basis[e]] * c[md.e_basis[f]];
+                        }
+                    }
+                    A[bb * t + a] = v;
+                }
+            // inverse by Gauss-Jordan with partial pivoting (nalgebra try_inverse: LU, :397-399)
+            double Inv[STATS_MAX_T * STATS_MAX_T];
+            for (int i = 0; i < t * t; ++i) Inv[i] = 0.0;
+            for (int i = 0; i < t; ++i) Inv[i * t + i] = 1.0;
+            for (int col = 0; col < t && !bad; ++col) {
+                int piv = col;
+                for (int r = col + 1; r < t; ++r)
+                    if (fabs(A[col * t + r]) > fabs(A[col * t + piv])) piv = r;
+                const double d = A[col * t + piv];
+                if (!(fabs(d) > 0.0) || !isfinite(d)) { bad = 1; break; }
+                if (piv != col)
+                    for (int k = 0; k < t; ++k) {
+                        double tmp = A[k * t + col]; A[k * t + col] = A[k * t + piv]; A[k * t + piv] = tmp;
+                        tmp = Inv[k * t + col]; Inv[k * t + col] = Inv[k * t + piv]; Inv[k * t + piv] = tmp;
+                    }
+                const double inv_d = 1.0 / d;
+                for (int k = 0; k < t; ++k) { A[k * t + col] *= inv_d; Inv[k * t + col] *= inv_d; }
+                for (int r = 0; r < t; ++r) {
+                    if (r == col) continue;
+                    const double f = A[col * t + r];
+                    if (f == 0.0) continue;
+                    for (int k = 0; k < t; ++k) { A[k * t + r] -= f * A[k * t + col]; Inv[k * t + r] -= f * Inv[k * t + col]; }
+                }
+            }
+            for (int i = 0; i < t * t; ++i) {
+                const double v = bad ? nan("") : chi * Inv[i];
+                cv[i] = v;
+                cov[(size_t)s * t * t + i] = v;
+            }
+            chi2[s] = chi;
+            if (bad) atomicExch(fail_flag, 1);
+        }
+        __syncwarp();
+        if (conf) {
+            for (int i = lane; i < m; i += 32) {
+                double jrow[STATS_MAX_T];
+                for (int a = 0; a < n; ++a) jrow[a] = B[(size_t)a * m + i];
+                for (int k = 0; k < q; ++k) {
+                    double v = 0.0;
+                    for (int e = 0; e < p; ++e)
+                        if (md.e_param[e] == k) v += B[(size_t)(n + e) * m + i] * c[md.e_basis[e]];
+                    jrow[n + k] = v;
+                }
+                double acc = 0.0;
+                for (int a = 0; a < t; ++a) {
+                    double inner = 0.0;
+                    for (int bb = 0; bb < t; ++bb) inner += cv[bb * t + a] * jrow[bb];
+                    acc += jrow[a] * inner;
+                }
+                conf[(size_t)s * m + i] = sqrt(acc);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 } // namespace vp

@@ -1311,6 +1311,65 @@ extern "C" int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options
 }
 
 // ----------------------------------------------------------------------------
+// vp_statistics: FitStatistics::try_calculate per right-hand side (src/statistics/mod.rs:352-441)
+// ----------------------------------------------------------------------------
+template <typename T>
+static int statistics_t(vp_problem *pr, double *cov_host, double *chi2_host, double *conf_host)
+{
+    vp_ctx *ctx = pr->ctx;
+    vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    const int m = md.m, t = md.n + md.q, t0 = md.n + md.p;
+    const size_t S = (size_t)pr->S;
+    double *B = nullptr, *Gm = nullptr, *cov = nullptr, *chi2 = nullptr, *conf = nullptr;
+    int *flag = nullptr;
+    cudaError_t e = DEV_ALLOC(ctx, &B, sizeof(double) * (size_t)m * t0);
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &Gm, sizeof(double) * (size_t)t0 * t0);
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &cov, sizeof(double) * (size_t)t * t * S);
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &chi2, sizeof(double) * S);
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &flag, sizeof(int));
+    if (e == cudaSuccess && conf_host) e = DEV_ALLOC(ctx, &conf, sizeof(double) * (size_t)m * S);
+    int host_flag = 0;
+    if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream);
+    if (e == cudaSuccess) {
+        basis_kernel<T><<<(m + 255) / 256, 256, 0, ctx->stream>>>(md, (const T *)mo->x_dev, pr->alpha_dev, B);
+        gram_kernel<T><<<(t0 * t0 + 127) / 128, 128, 0, ctx->stream>>>(m, t0, B, (const T *)pr->w_dev, Gm);
+        long long blocks = ((long long)S + 7) / 8;
+        if (blocks > (long long)ctx->sm_count * 8) blocks = (long long)ctx->sm_count * 8;
+        statistics_kernel<T><<<(unsigned)blocks, 256, 0, ctx->stream>>>(md, (const T *)pr->Yw, mo->ld, pr->ldp, (int)pr->S,
+                                                                        (const T *)pr->Pq, (const T *)pr->C[pr->cur], Gm, B, cov,
+                                                                        chi2, conf, flag);
+        ctx->launches += 3;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cov_host, cov, sizeof(double) * (size_t)t * t * S, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && chi2_host) e = cudaMemcpyAsync(chi2_host, chi2, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && conf_host) e = cudaMemcpyAsync(conf_host, conf, sizeof(double) * (size_t)m * S, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    DEV_FREE(ctx, B); DEV_FREE(ctx, Gm); DEV_FREE(ctx, cov); DEV_FREE(ctx, chi2); DEV_FREE(ctx, flag); DEV_FREE(ctx, conf);
+    if (e != cudaSuccess)
+        return fail(ctx, e == cudaErrorMemoryAllocation ? VP_ERR_OUT_OF_MEMORY : VP_ERR_CUDA, std::string("vp_statistics: ") + cudaGetErrorString(e));
+    if (host_flag) return fail(ctx, VP_ERR_MATRIX_INVERSION, vp_status_string(VP_ERR_MATRIX_INVERSION));
+    return VP_OK;
+}
+
+extern "C" int vp_statistics(vp_problem *pr, double *cov_out, double *reduced_chi2_out, double *conf_sigma_out)
+{
+    if (!pr || !cov_out) return VP_ERR_INVALID_ARGUMENT;
+    vp_ctx *ctx = pr->ctx;
+    if (pr->comm) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "vp_statistics: call it on each rank's own columns after detaching the communicator");
+    if (!pr->cached) return fail(ctx, VP_ERR_NO_CACHED_CALCULATION, vp_status_string(VP_ERR_NO_CACHED_CALCULATION));
+    const ModelDesc &md = pr->model->md;
+    if (md.m <= md.n + md.q) return fail(ctx, VP_ERR_UNDERDETERMINED, vp_status_string(VP_ERR_UNDERDETERMINED)); // :377-379
+    cudaSetDevice(ctx->device);
+    int rc = ensure_panel_current(pr); // Q at the accepted parameters, in HBM
+    if (rc != VP_OK) return rc;
+    return pr->model->dtype == VP_F32 ? statistics_t<float>(pr, cov_out, reduced_chi2_out, conf_sigma_out)
+                                      : statistics_t<double>(pr, cov_out, reduced_chi2_out, conf_sigma_out);
+}
+
+// ----------------------------------------------------------------------------
 // vp_batch: P independent problems (BASELINE config 3), one CTA per problem (batch_fit_kernel)
 // ----------------------------------------------------------------------------
 struct vp_batch {

@@ -9,15 +9,19 @@ convergence with the crate-default tolerances, starting from a built problem (th
 criterion bench builds the problem in its un-timed setup closure and times `fit`).
 
   value : whole-job fits/s with the observations already resident in HBM when the timed region
-          starts. K distinct problem instances (K x 33.5 MB, rotated, more than the 126 MB L2 for
-          K >= 4) are built un-timed; the timed region is exactly K fits, CUDA events on the
-          library's stream, barrier + synchronize on both sides, max over ranks.
+          starts. K distinct problem instances (K x 33.5 MB, more than the 126 MB L2 for K >= 4)
+          are built un-timed; the timed region is exactly K fits made by ONE vp_fit_many call (all
+          K fits share one persistent grid through a device-side work queue), CUDA events on the
+          library's stream, barrier + synchronize on both sides, max over ranks. `latency_mode`
+          reports the same K fits made one after the other (vp_fit, whole GPU per fit).
   e2e   : the same metric through the reference-facing API with HOST buffers: every step builds
           the problem from pinned host memory (H2D of Y inside the timed region), fits, and
-          reads parameters + linear coefficients back (D2H).
-  roofline : the Y-streaming reduce kernel (K2), algorithmic bytes = 8*m*S per launch, CUDA events
-          on the launching stream, L2 flushed before every timed launch (cold, HBM-bound figure);
-          the un-flushed back-to-back figure is reported as achieved_l2_warm.
+          reads parameters + linear coefficients back (D2H); a few host threads pipeline steps so
+          that one step's copy overlaps another step's fit (PCIe-bound: 33.6 MB per step).
+  roofline : the dominant kernel of the timed region (fit_queue_kernel): algorithmic bytes = 8*m*S per
+          evaluation x the evaluations made in the timed region, over the region's CUDA-event time.
+          `single_evaluation_full_grid` is one fused evaluation launch on the whole GPU with L2
+          flushed before every launch (and un-flushed).
   cpu_baseline : the CPU restatement of the reference algorithm (oracle/, "port"), 1 thread
           (the reference is single-threaded), on a bounded sample of the same workload.
 
@@ -175,7 +179,7 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- value: observations resident in HBM, K distinct built problems, fitted concurrently ----
-    # (throughput mode, vp_fit_many: each fit is one persistent kernel on #SMs/K SMs)
+    # (throughput mode, vp_fit_many: one persistent grid serves all K fits through a device-side work queue)
     def timed_fits(probs, many):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -290,7 +294,7 @@ def run_gpu(args, rank, world, local_rank):
         single_cold = BYTES_EVAL / (cold_us * 1e-6) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_fit_traffic.json")))["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_queue_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
         # CPU baseline: oracle port, 1 thread, bounded sample (rank 0, N = 1 only)
@@ -316,11 +320,12 @@ def run_gpu(args, rank, world, local_rank):
                     "host_threads": NTH, "steps_per_chunk": CH},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "fit_kernel_dmma<3,2,32,8> (persistent fit: panel + Y-streaming reduce + LM step)",
-                         "how": "K launches run concurrently (vp_fit_many), each on #SMs/K SMs: achieved = algorithmic bytes of "
-                                "all launches in the timed region (timed evaluations x 8*m*S) / CUDA-event time of the region",
-                         "bytes_per_launch": BYTES_EVAL * timed_evals / K, "timed_evaluations": timed_evals,
-                         "concurrent_launches": K, "region_us": ms * 1e3,
+                         "traffic": traffic, "kernel": "fit_queue_kernel<3,2,32,8> (all K fits on one persistent grid: work queue of "
+                                                      "(fit, chunk) items; panel + Y-streaming reduce + LM step in-kernel)",
+                         "how": "ONE launch fits all K problems (vp_fit_many): achieved = algorithmic bytes of the launch "
+                                "(timed evaluations x 8*m*S) / CUDA-event time of the timed region",
+                         "bytes_per_launch": BYTES_EVAL * timed_evals, "timed_evaluations": timed_evals,
+                         "fits_per_launch": K, "region_us": ms * 1e3,
                          "single_evaluation_full_grid": {"us_l2_flushed": cold_us, "GBps_l2_flushed": single_cold,
                                                          "frac_l2_flushed": single_cold / peak, "us_l2_warm": warm_us,
                                                          "GBps_l2_warm": BYTES_EVAL / (warm_us * 1e-6) / 1e9,

@@ -278,9 +278,12 @@ def test_sharded_fit_world1_exercises_the_mailbox_protocol():
     comm.close()
 
 
-def test_fit_many_equals_sequential_fits():
-    """vp_fit_many (concurrent persistent kernels on SM slices) against one vp_fit per problem."""
+@pytest.mark.parametrize("many_mode", ["queue", "streams"])
+def test_fit_many_equals_sequential_fits(monkeypatch, many_mode):
+    """vp_fit_many against one vp_fit per problem: the work-queue kernel (all SMs serve all fits, default)
+    and the per-fit persistent kernels on SM slices (VP_FIT_MANY=streams)."""
     import varpro_b200 as vb
+    monkeypatch.setenv("VP_FIT_MANY", many_mode)
     solver = vb.LevMarSolver.default()
     wls = [W.c2(S=64 + 8 * k, seed=100 + k) for k in range(6)] + [W.mrhs20(3), W.lmfit_case(True)]
     seq = [solver.fit(W.make_gpu_problem(wl)) for wl in wls]

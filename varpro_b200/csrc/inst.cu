@@ -3,6 +3,7 @@
 #include "kernel_tables.h"
 #include "batch_fit_kernel.cuh"
 #include "fit_kernel_dmma.cuh"
+#include "fit_queue_kernel.cuh"
 #include "panel_kernel_hh.cuh"
 #include "stream_kernel.cuh"
 #include "stream_kernel_dmma.cuh"
@@ -36,6 +37,16 @@ static const FitKernelEntry fit_tab[] = {VP_FK(32, 8, 0), VP_FK(32, 8, 1)};
 static const FitKernelEntry fit_tab[] = {VP_FK(32, 16, 0)};
 #endif
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, fit_tab, (int)(sizeof(fit_tab) / sizeof(fit_tab[0]))};
+#elif VP_INST_PART == 5
+#define VP_QK(KS, NW, EX) {N_, P_, KS, NW, EX, (const void *)&fit_queue_kernel<N_, P_, KS, NW, (EX) != 0>}
+#if VP_INST_VARIANT == 0
+static const QueueKernelEntry queue_tab[] = {VP_QK(8, 4, 0), VP_QK(16, 8, 0)};
+#elif VP_INST_VARIANT == 1
+static const QueueKernelEntry queue_tab[] = {VP_QK(32, 8, 0), VP_QK(32, 8, 1)};
+#else
+static const QueueKernelEntry queue_tab[] = {VP_QK(32, 16, 0)};
+#endif
+static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, queue_tab, (int)(sizeof(queue_tab) / sizeof(queue_tab[0]))};
 #elif VP_INST_PART == 4
 constexpr int BATCH_THREADS = 512;
 #define VP_BK(RPT) {N_, P_, RPT, BATCH_THREADS, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS>}

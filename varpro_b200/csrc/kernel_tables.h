@@ -22,6 +22,10 @@ struct FitKernelEntry { // fit_kernel_dmma: fused panel + streaming reduce (+ wh
     int n, p, ksteps, nwarps, exact;
     const void *fn;
 };
+struct QueueKernelEntry { // fit_queue_kernel: many fits on one persistent grid with a device-side work queue
+    int n, p, ksteps, nwarps, exact;
+    const void *fn;
+};
 struct BatchKernelEntry { // batch_fit_kernel: one CTA fits one independent problem at a time
     int n, p, rpt, threads;
     const void *fn;
@@ -32,11 +36,13 @@ struct KernelGroup {
     const PanelHHEntry *panel;     int npanel;
     const FitKernelEntry *fit;     int nfit;
     const BatchKernelEntry *batch; int nbatch;
+    const QueueKernelEntry *queue; int nqueue;
 };
 typedef const KernelGroup *(*KernelGroupFn)();
 
 // (tag, C type, vp_dtype, n, p, part): part 0 = SIMT streaming, 1 = DMMA streaming, 2 = Householder panel,
-// 3 = fused evaluation / persistent fit kernel, 4 = independent-batch fit kernel.
+// 3 = fused evaluation / persistent fit kernel, 4 = independent-batch fit kernel,
+// 5 = multi-fit work-queue kernel.
 // The model shapes with a compiled fast path; everything else runs the generic kernels.
 #define VP_KERNEL_GROUPS(X)                 \
     X(f64_3_2_simt, double, VP_F64, 3, 2, 0) /* double exponential + offset (benches, C1/C2/C5) */ \
@@ -45,6 +51,9 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_3_2_fit0, double, VP_F64, 3, 2, 3) \
     X(f64_3_2_fit1, double, VP_F64, 3, 2, 3) \
     X(f64_3_2_fit2, double, VP_F64, 3, 2, 3) \
+    X(f64_3_2_queue0, double, VP_F64, 3, 2, 5) \
+    X(f64_3_2_queue1, double, VP_F64, 3, 2, 5) \
+    X(f64_3_2_queue2, double, VP_F64, 3, 2, 5) \
     X(f32_3_2_simt, float, VP_F32, 3, 2, 0)  /* the same in fp32 (C4) */ \
     X(f32_3_2_panel, float, VP_F32, 3, 2, 2) \
     X(f64_3_3_simt, double, VP_F64, 3, 3, 0) /* triple exponential (C3 shape) */ \
@@ -53,12 +62,18 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_3_3_fit0, double, VP_F64, 3, 3, 3) \
     X(f64_3_3_fit1, double, VP_F64, 3, 3, 3) \
     X(f64_3_3_fit2, double, VP_F64, 3, 3, 3) \
+    X(f64_3_3_queue0, double, VP_F64, 3, 3, 5) \
+    X(f64_3_3_queue1, double, VP_F64, 3, 3, 5) \
+    X(f64_3_3_queue2, double, VP_F64, 3, 3, 5) \
     X(f64_2_4_simt, double, VP_F64, 2, 4, 0) /* O'Leary exp*cos example */ \
     X(f64_2_4_dmma, double, VP_F64, 2, 4, 1) \
     X(f64_2_4_panel, double, VP_F64, 2, 4, 2) \
     X(f64_2_4_fit0, double, VP_F64, 2, 4, 3) \
     X(f64_2_4_fit1, double, VP_F64, 2, 4, 3) \
     X(f64_2_4_fit2, double, VP_F64, 2, 4, 3) \
+    X(f64_2_4_queue0, double, VP_F64, 2, 4, 5) \
+    X(f64_2_4_queue1, double, VP_F64, 2, 4, 5) \
+    X(f64_2_4_queue2, double, VP_F64, 2, 4, 5) \
     X(f64_3_3_batch, double, VP_F64, 3, 3, 4) \
     X(f64_3_2_batch, double, VP_F64, 3, 2, 4) \
     X(f64_2_4_batch, double, VP_F64, 2, 4, 4)

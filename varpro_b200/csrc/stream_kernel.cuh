@@ -141,7 +141,7 @@ __device__ void stream_finalize(const StreamArgs<T> &a, int n, int p, int nparts
         Msh[tid] = SMEM_SMALL ? *msrc : __ldcg(msrc);
     }
     int nonfinite = 0;
-    if (tid == 0) nonfinite = a.small->nonfinite;
+    if (tid == 0) nonfinite = SMEM_SMALL ? a.small->nonfinite : __ldcg(&a.small->nonfinite);
     dbg_mark(a.dbg, 11);
 #pragma unroll 1
     for (int base = 0; base < nv; base += 16) {
@@ -263,7 +263,8 @@ __device__ __forceinline__ void stream_epilogue(const StreamArgs<T> &a, int n, i
 // live for a few microseconds.
 template <typename T, int N, int P, int CT, int NW>
 __device__ __forceinline__ void cta_publish_partial(const StreamArgs<T> &a, double rn2, const double *Gacc, const double *Vacc,
-                                                    double *wsum /* NW */, double *gv /* CT*(NG+P) */, int *is_last)
+                                                    double *wsum /* NW */, double *gv /* CT*(NG+P) */, int *is_last,
+                                                    const int row = blockIdx.x, const int nrows = gridDim.x)
 {
     constexpr int NG = N * (N + 1) / 2, NGP = NG + P, NVR = 1 + NGP;
     static_assert(NVR <= 32, "the partial row must be written by one warp");
@@ -287,7 +288,7 @@ __device__ __forceinline__ void cta_publish_partial(const StreamArgs<T> &a, doub
 #pragma unroll
             for (int c = 0; c < CT; ++c) s += gv[c * NGP + tid - 1];
         }
-        a.partials[(size_t)blockIdx.x * a.red_stride + tid] = s;
+        a.partials[(size_t)row * a.red_stride + tid] = s;
     }
     // publish: the partial row is written by warp 0; its lane 0 then takes a ticket with
     // release/acquire semantics at gpu scope (orders the row before the ticket and, in
@@ -298,7 +299,7 @@ __device__ __forceinline__ void cta_publish_partial(const StreamArgs<T> &a, doub
         if (lane == 0) {
             unsigned int prev;
             asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(a.ticket) : "memory");
-            *is_last = (prev == gridDim.x - 1);
+            *is_last = (prev == (unsigned int)nrows - 1u);
         }
     }
     __syncthreads();

@@ -23,6 +23,7 @@
 #include "stream_kernel.cuh"
 #include "fit_kernel_dmma.cuh"
 #include "batch_fit_kernel.cuh"
+#include "fit_queue_kernel.cuh"
 
 using namespace vp;
 
@@ -366,6 +367,7 @@ static std::vector<DmmaKernelEntry> g_dmma_kernels;
 static std::vector<PanelHHEntry> g_panel_kernels;
 static std::vector<FitKernelEntry> g_fit_kernels;
 static std::vector<BatchKernelEntry> g_batch_kernels;
+static std::vector<QueueKernelEntry> g_queue_kernels;
 static int g_num_stream_kernels = 0, g_num_dmma_kernels = 0;
 static void gather_kernel_tables()
 {
@@ -379,6 +381,7 @@ static void gather_kernel_tables()
         g_panel_kernels.insert(g_panel_kernels.end(), g->panel, g->panel + g->npanel);           \
         g_fit_kernels.insert(g_fit_kernels.end(), g->fit, g->fit + g->nfit);                     \
         g_batch_kernels.insert(g_batch_kernels.end(), g->batch, g->batch + g->nbatch);           \
+        g_queue_kernels.insert(g_queue_kernels.end(), g->queue, g->queue + g->nqueue);           \
     }
     VP_KERNEL_GROUPS(VP_GATHER)
 #undef VP_GATHER
@@ -1236,6 +1239,97 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
     return VP_OK;
 }
 
+// One launch of fit_queue_kernel for a group of problems that share the kernel instantiation and the
+// padded row count. states[i] has been advanced past the cached evaluation at the starting point.
+// Returns VP_OK after the fits completed and their final states were adopted.
+static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, std::vector<LmState> &states,
+                           const std::vector<LmConfig> &cfgs)
+{
+    const int K = (int)prs.size();
+    vp_problem *p0 = prs[0];
+    const FitKernelEntry &fk = g_fit_kernels[p0->plan_fit];
+    const QueueKernelEntry *qk = nullptr;
+    for (const QueueKernelEntry &k : g_queue_kernels)
+        if (k.n == fk.n && k.p == fk.p && k.ksteps == fk.ksteps && k.nwarps == fk.nwarps && k.exact == fk.exact) qk = &k;
+    if (!qk) return VP_ERR_UNSUPPORTED_BASIS; // caller falls back to the per-fit kernels
+    const int lds = p0->plan_lds;
+    const size_t stage_bytes = (size_t)DMMA_CT * lds * sizeof(double);
+    cudaFuncAttributes fa{};
+    VP_CUDA(ctx, cudaFuncGetAttributes(&fa, qk->fn));
+    if (fa.sharedSizeBytes + 1024 + 2 * stage_bytes > 227 * 1024) return VP_ERR_UNSUPPORTED_BASIS;
+    int nst = (int)((227 * 1024 - fa.sharedSizeBytes - 1024) / stage_bytes);
+    if (nst > STREAM_MAX_STAGES) nst = STREAM_MAX_STAGES;
+    const size_t smem = (size_t)nst * stage_bytes;
+    VP_CUDA(ctx, cudaFuncSetAttribute(qk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qk->fn, qk->nwarps * 32, smem));
+    if (occ < 1) return VP_ERR_UNSUPPORTED_BASIS;
+
+    const int min_chunk = env_int("VP_QUEUE_MIN_CHUNK", 4); // tiles; the kernel picks the chunk size per evaluation
+    std::vector<QueueFit> hq((size_t)K);
+    long long total_chunks = 0;
+    for (int i = 0; i < K; ++i) {
+        vp_problem *pr = prs[(size_t)i];
+        const ModelDesc &md = pr->model->md;
+        QueueFit &f = hq[(size_t)i];
+        memset(&f, 0, sizeof(f));
+        f.md = md;
+        f.Y = (const double *)pr->Yw; f.C0 = (double *)pr->C[0]; f.C1 = (double *)pr->C[1];
+        f.x = (const double *)pr->model->x_dev; f.w = (const double *)pr->w_dev;
+        f.Pq = (double *)pr->Pq; f.small = pr->small; f.partials = pr->partials; f.ticket = pr->ticket;
+        f.out = pr->out_dev; f.fit = pr->fit_dev; f.svd_eps = pr->svd_eps;
+        f.ld = pr->model->ld; f.S = (int)pr->S; f.ldp = pr->ldp; f.red_stride = pr->red_stride;
+        f.ntiles = (int)((pr->S + DMMA_CT - 1) / DMMA_CT);
+        f.min_chunk_tiles = min_chunk < 1 ? 1 : min_chunk;
+        f.max_chunks = pr->max_grid; // one partial row per chunk
+        f.chunk_tiles = f.ntiles;
+        f.nchunks = 1;
+        f.cdst = pr->cur ^ 1;
+        total_chunks += (f.ntiles + f.min_chunk_tiles - 1) / f.min_chunk_tiles < f.max_chunks ? (f.ntiles + f.min_chunk_tiles - 1) / f.min_chunk_tiles : f.max_chunks;
+        // device-resident LM state
+        FitDevice *fh = pr->fit_host;
+        memset(fh, 0, sizeof(FitDevice));
+        fh->st = states[(size_t)i]; fh->cfg = cfgs[(size_t)i]; fh->accepted = pr->eval; fh->cur = pr->cur; fh->evals = 0;
+        VP_CUDA(ctx, cudaMemcpyAsync(pr->fit_dev, fh, sizeof(FitDevice), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const unsigned int cap = (unsigned int)(total_chunks + 2048);
+    QueueFit *dq = nullptr;
+    QueueCtl *dctl = nullptr;
+    QueueItem *ditems = nullptr;
+    cudaError_t e = DEV_ALLOC(ctx, &dq, sizeof(QueueFit) * (size_t)K);
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &dctl, sizeof(QueueCtl));
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &ditems, sizeof(QueueItem) * (size_t)cap);
+    QueueCtl hctl{};
+    hctl.head = 0; hctl.tail = 0; hctl.fits_left = K; hctl.error = 0; hctl.items = ditems; hctl.cap = cap;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dq, hq.data(), sizeof(QueueFit) * (size_t)K, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dctl, &hctl, sizeof(QueueCtl), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ditems, 0, sizeof(QueueItem) * (size_t)cap, ctx->stream);
+    int rc = VP_OK;
+    if (e == cudaSuccess) {
+        long long grid = (long long)ctx->sm_count * occ;
+        int nf = K, lds_arg = lds, nst_arg = nst;
+        void *args[] = {(void *)&dctl, (void *)&dq, (void *)&nf, (void *)&lds_arg, (void *)&nst_arg};
+        e = cudaLaunchKernel(qk->fn, dim3((unsigned)grid), dim3(qk->nwarps * 32), args, smem, ctx->stream);
+        ctx->launches++;
+    }
+    for (int i = 0; i < K && e == cudaSuccess; ++i)
+        e = cudaMemcpyAsync(prs[(size_t)i]->fit_host, prs[(size_t)i]->fit_dev, sizeof(FitDevice), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hctl, dctl, sizeof(QueueCtl), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    DEV_FREE(ctx, dq); DEV_FREE(ctx, dctl); DEV_FREE(ctx, ditems);
+    if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, std::string("vp_fit_many (queue): ") + cudaGetErrorString(e));
+    if (hctl.error) return fail(ctx, VP_ERR_CUDA, "vp_fit_many: a wait inside the work-queue kernel timed out");
+    for (int i = 0; i < K; ++i) {
+        vp_problem *pr = prs[(size_t)i];
+        FitDevice *fh = pr->fit_host;
+        states[(size_t)i] = fh->st;
+        pr->cur = fh->cur;
+        pr->eval = fh->accepted;
+        for (int k = 0; k < pr->model->md.q; ++k) pr->alpha[k] = fh->st.x[k];
+    }
+    return rc;
+}
+
 // Many independent fits at once (throughput mode). A single fit on the whole GPU is latency
 // bound: per evaluation the panel, the grid-wide reduction and the serial LM step cost more than
 // streaming 33.5 MB does. Independent problems are therefore run CONCURRENTLY, each as its own
@@ -1254,6 +1348,63 @@ extern "C" int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options
     cudaSetDevice(ctx->device);
     const char *mode = getenv("VP_FIT_MODE");
     const bool persistent_ok = !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph")));
+    // ---- default: ONE persistent grid with a device-side work queue per group of like-shaped problems
+    const char *many = getenv("VP_FIT_MANY"); // "queue" (default) or "streams"
+    if (persistent_ok && n > 1 && !(many && !strcmp(many, "streams"))) {
+        std::vector<char> done((size_t)n, 0);
+        std::vector<LmState> all_states((size_t)n);
+        std::vector<LmConfig> all_cfgs((size_t)n);
+        bool any_left = false;
+        for (int64_t i = 0; i < n; ++i) {
+            vp_problem *pr = problems[i];
+            memset(&reports[i], 0, sizeof(vp_fit_report));
+            lm_config_from_options(pr, opt, all_cfgs[(size_t)i]);
+            lm_init(all_states[(size_t)i], pr->model->md.q, pr->alpha);
+            if (!pr->cached || pr->plan_fit < 0 || pr->comm) { any_left = true; continue; }
+            if (!lm_advance(all_states[(size_t)i], all_cfgs[(size_t)i], pr->eval)) { // terminated at the starting point
+                fill_report(all_states[(size_t)i], &reports[i]);
+                done[(size_t)i] = 1;
+                continue;
+            }
+            done[(size_t)i] = 2; // to be fitted by a queue launch
+        }
+        int first_error = VP_OK;
+        for (int64_t i = 0; i < n; ++i) {
+            if (done[(size_t)i] != 2) continue;
+            // group: same kernel instantiation, same padded rows
+            std::vector<int64_t> idx;
+            for (int64_t j = i; j < n; ++j)
+                if (done[(size_t)j] == 2 && problems[j]->plan_fit == problems[i]->plan_fit &&
+                    problems[j]->plan_lds == problems[i]->plan_lds && problems[j]->model->ld == problems[i]->model->ld)
+                    idx.push_back(j);
+            std::vector<vp_problem *> prs;
+            std::vector<LmState> sts;
+            std::vector<LmConfig> cfs;
+            for (int64_t j : idx) { prs.push_back(problems[j]); sts.push_back(all_states[(size_t)j]); cfs.push_back(all_cfgs[(size_t)j]); }
+            int rc = idx.size() > 1 ? fit_queue_group(ctx, prs, sts, cfs) : VP_ERR_UNSUPPORTED_BASIS;
+            for (size_t t = 0; t < idx.size(); ++t) {
+                const int64_t j = idx[t];
+                if (rc == VP_OK) {
+                    fill_report(sts[t], &reports[j]);
+                    done[(size_t)j] = 1;
+                } else if (rc == VP_ERR_UNSUPPORTED_BASIS) {
+                    done[(size_t)j] = 0; // no queue kernel for this shape (or a group of one): per-fit kernel below
+                    any_left = true;
+                } else {
+                    done[(size_t)j] = 3;
+                    if (first_error == VP_OK) first_error = rc;
+                }
+            }
+        }
+        if (any_left)
+            for (int64_t i = 0; i < n; ++i)
+                if (done[(size_t)i] == 0) {
+                    int rc = vp_fit(problems[i], opt, &reports[i]);
+                    if (rc != VP_OK && first_error == VP_OK) first_error = rc;
+                }
+        return first_error;
+    }
+    // ---- VP_FIT_MANY=streams: one persistent kernel per fit on a slice of the SMs, on separate streams
     int64_t width = max_concurrent > 0 ? max_concurrent : ctx->sm_count;
     if (width > n) width = n;
     if (width > ctx->sm_count) width = ctx->sm_count;

@@ -4,7 +4,7 @@ TAG=${1:-q}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
 tail -30 gpurun_out/${TAG}_pytest_gpu.log
-for MC in 2 4 8; do for K in 20 60; do
-VP_QUEUE_MIN_CHUNK=$MC timeout 600 python bench.py --steps $K --warmup 3 --no-cpu > gpurun_out/${TAG}_bench${K}_mc$MC.json 2> gpurun_out/${TAG}_bench.err; tail -3 gpurun_out/${TAG}_bench.err
-python -c "import sys,json; d=json.loads(open('gpurun_out/${TAG}_bench${K}_mc$MC.json').read()); print('minchunk=$MC K=$K value', round(d['value']), 'e2e', round(d['e2e']['value']), 'frac', round(d['roofline']['frac'],3), 'lat', round(d['latency_mode']['value']), 'evals', d['config']['evals_per_fit_mean'])"
-done; done
+for K in 20 60; do
+timeout 600 python bench.py --steps $K --warmup 3 > gpurun_out/${TAG}_bench$K.json 2> gpurun_out/${TAG}_bench.err; tail -3 gpurun_out/${TAG}_bench.err
+python -c "import sys,json; d=json.loads(open('gpurun_out/${TAG}_bench$K.json').read()); print('K=$K value', round(d['value']), 'e2e', round(d['e2e']['value']), 'frac', round(d['roofline']['frac'],3), 'lat', round(d['latency_mode']['value']), 'evals', d['config']['evals_per_fit_mean'])"
+done

@@ -1286,23 +1286,35 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         f.nchunks = 1;
         f.cdst = pr->cur ^ 1;
         total_chunks += (f.ntiles + f.min_chunk_tiles - 1) / f.min_chunk_tiles < f.max_chunks ? (f.ntiles + f.min_chunk_tiles - 1) / f.min_chunk_tiles : f.max_chunks;
-        // device-resident LM state
-        FitDevice *fh = pr->fit_host;
-        memset(fh, 0, sizeof(FitDevice));
-        fh->st = states[(size_t)i]; fh->cfg = cfgs[(size_t)i]; fh->accepted = pr->eval; fh->cur = pr->cur; fh->evals = 0;
-        VP_CUDA(ctx, cudaMemcpyAsync(pr->fit_dev, fh, sizeof(FitDevice), cudaMemcpyHostToDevice, ctx->stream));
     }
+    // One pinned host block and one device block: [FitDevice x K | QueueCtl | QueueFit x K]. One copy
+    // in; one copy out (states + control word).
+    const size_t off_ctl = sizeof(FitDevice) * (size_t)K;
+    const size_t off_q = (off_ctl + sizeof(QueueCtl) + 255) / 256 * 256;
+    const size_t total_bytes = off_q + sizeof(QueueFit) * (size_t)K;
     const unsigned int cap = (unsigned int)(total_chunks + 2048);
-    QueueFit *dq = nullptr;
-    QueueCtl *dctl = nullptr;
+    unsigned char *hb = nullptr, *db = nullptr;
     QueueItem *ditems = nullptr;
-    cudaError_t e = DEV_ALLOC(ctx, &dq, sizeof(QueueFit) * (size_t)K);
-    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &dctl, sizeof(QueueCtl));
+    cudaError_t e = HOST_ALLOC(ctx, &hb, total_bytes);
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &db, total_bytes);
     if (e == cudaSuccess) e = DEV_ALLOC(ctx, &ditems, sizeof(QueueItem) * (size_t)cap);
-    QueueCtl hctl{};
-    hctl.head = 0; hctl.tail = 0; hctl.fits_left = K; hctl.error = 0; hctl.items = ditems; hctl.cap = cap;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dq, hq.data(), sizeof(QueueFit) * (size_t)K, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dctl, &hctl, sizeof(QueueCtl), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        HOST_FREE(ctx, hb); DEV_FREE(ctx, db); DEV_FREE(ctx, ditems);
+        return fail(ctx, VP_ERR_OUT_OF_MEMORY, std::string("vp_fit_many (queue): ") + cudaGetErrorString(e));
+    }
+    FitDevice *hstate = reinterpret_cast<FitDevice *>(hb), *dstate = reinterpret_cast<FitDevice *>(db);
+    QueueCtl *hctl = reinterpret_cast<QueueCtl *>(hb + off_ctl), *dctl = reinterpret_cast<QueueCtl *>(db + off_ctl);
+    QueueFit *hqp = reinterpret_cast<QueueFit *>(hb + off_q), *dq = reinterpret_cast<QueueFit *>(db + off_q);
+    memset(hb, 0, off_q);
+    for (int i = 0; i < K; ++i) {
+        vp_problem *pr = prs[(size_t)i];
+        FitDevice *fh = &hstate[i];
+        fh->st = states[(size_t)i]; fh->cfg = cfgs[(size_t)i]; fh->accepted = pr->eval; fh->cur = pr->cur; fh->evals = 0;
+        hq[(size_t)i].fit = dstate + i;
+        hqp[i] = hq[(size_t)i];
+    }
+    hctl->head = 0; hctl->tail = 0; hctl->fits_left = K; hctl->error = 0; hctl->items = ditems; hctl->cap = cap;
+    e = cudaMemcpyAsync(db, hb, total_bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ditems, 0, sizeof(QueueItem) * (size_t)cap, ctx->stream);
     int rc = VP_OK;
     if (e == cudaSuccess) {
@@ -1312,21 +1324,21 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         e = cudaLaunchKernel(qk->fn, dim3((unsigned)grid), dim3(qk->nwarps * 32), args, smem, ctx->stream);
         ctx->launches++;
     }
-    for (int i = 0; i < K && e == cudaSuccess; ++i)
-        e = cudaMemcpyAsync(prs[(size_t)i]->fit_host, prs[(size_t)i]->fit_dev, sizeof(FitDevice), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&hctl, dctl, sizeof(QueueCtl), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb, db, off_ctl + sizeof(QueueCtl), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    DEV_FREE(ctx, dq); DEV_FREE(ctx, dctl); DEV_FREE(ctx, ditems);
-    if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, std::string("vp_fit_many (queue): ") + cudaGetErrorString(e));
-    if (hctl.error) return fail(ctx, VP_ERR_CUDA, "vp_fit_many: a wait inside the work-queue kernel timed out");
+    const int qerr = hctl->error;
+    DEV_FREE(ctx, db); DEV_FREE(ctx, ditems);
+    if (e != cudaSuccess) { HOST_FREE(ctx, hb); return fail(ctx, VP_ERR_CUDA, std::string("vp_fit_many (queue): ") + cudaGetErrorString(e)); }
+    if (qerr) { HOST_FREE(ctx, hb); return fail(ctx, VP_ERR_CUDA, "vp_fit_many: a wait inside the work-queue kernel timed out"); }
     for (int i = 0; i < K; ++i) {
         vp_problem *pr = prs[(size_t)i];
-        FitDevice *fh = pr->fit_host;
+        FitDevice *fh = &hstate[i];
         states[(size_t)i] = fh->st;
         pr->cur = fh->cur;
         pr->eval = fh->accepted;
         for (int k = 0; k < pr->model->md.q; ++k) pr->alpha[k] = fh->st.x[k];
     }
+    HOST_FREE(ctx, hb);
     return rc;
 }
 

@@ -226,11 +226,13 @@ int vp_problem_set_comm(vp_problem *problem, vp_comm *comm);
 int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *report);
 /* Fit n independent problems of one context (throughput mode): what a caller of the reference
  * does in a loop over LevMarSolver::fit (e.g. benches/multiple_right_hand_sides.rs:97-101 per
- * criterion iteration). The fits run concurrently, each as one persistent kernel on
- * #SMs / min(n, max_concurrent) SMs (max_concurrent <= 0: as many as there are SMs), so the
- * latency-bound phases of one fit overlap the HBM streaming of the others. Results are
- * identical to n calls of vp_fit up to the summation order of the per-CTA partial sums.
- * reports: n entries. Returns the first error, VP_OK otherwise. */
+ * criterion iteration). Like-shaped problems are fitted by ONE persistent kernel whose CTAs take
+ * (fit, chunk-of-columns) work items from a device-side queue, so the latency-bound phases of
+ * one fit (panel, reduction, LM step) overlap the HBM streaming of the others and the load is
+ * balanced dynamically. Results are identical to n calls of vp_fit up to the summation order of
+ * the partial sums. max_concurrent is only used by the alternative VP_FIT_MANY=streams mode
+ * (one persistent kernel per fit on #SMs / min(n, max_concurrent) SMs). reports: n entries.
+ * Returns the first error, VP_OK otherwise. */
 int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *options, vp_fit_report *reports,
                 int32_t max_concurrent);
 

@@ -1344,11 +1344,12 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
 
 // Many independent fits at once (throughput mode). A single fit on the whole GPU is latency
 // bound: per evaluation the panel, the grid-wide reduction and the serial LM step cost more than
-// streaming 33.5 MB does. Independent problems are therefore run CONCURRENTLY, each as its own
-// persistent fit kernel on a slice of the SMs (grid = #SMs / n, at least 1 CTA), on separate
-// streams: while one fit sits in its LM step the others keep HBM busy, and the panel is
-// recomputed by few CTAs instead of 148. Problems that cannot use the persistent kernel are
-// fitted one after the other with vp_fit.
+// streaming 33.5 MB does. Independent problems are therefore fitted TOGETHER. Default
+// (VP_FIT_MANY=queue): like-shaped problems share ONE persistent grid through a device-side work
+// queue (fit_queue_kernel.cuh): every CTA streams chunks of whichever fit has work, the panel of
+// an evaluation is computed once, and the serial phases of one fit hide behind the streaming of
+// the others. VP_FIT_MANY=streams: each fit is its own persistent kernel (fit_kernel_dmma) on
+// #SMs / n SMs on its own stream. Problems that can use neither are fitted one after the other.
 extern "C" int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *opt, vp_fit_report *reports,
                            int32_t max_concurrent)
 {

@@ -28,6 +28,34 @@
 
 namespace vp {
 
+// Sum K per-thread values over the CTA; every thread gets the totals. Two-level: per-warp shuffle
+// fold -> shared, warp 0 folds the NW per-warp partials (one lane per value), everybody reads the K
+// totals back (with 16 warps and K ~ 10 the one-level version makes every thread read NW*K values).
+// buf: NW*K + K doubles; two __syncthreads; buf must not be reused by the next call.
+template <int K, int NW>
+__device__ __forceinline__ void block_sum_two_level(double (&v)[K], double *buf)
+{
+    static_assert(K <= 32, "one lane of warp 0 per value");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) buf[warp * K + k] = t;
+    }
+    __syncthreads();
+    if (warp == 0 && lane < K) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += buf[w * K + lane];
+        buf[NW * K + lane] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = buf[NW * K + k];
+}
+
 struct BatchArgs {
     ModelDesc md;
     const double *x;      // m
@@ -47,7 +75,22 @@ struct BatchArgs {
     int mpad;             // rows of the shared-memory working matrix (>= m, multiple of 2)
 };
 
-template <int N, int P, int RPT, int THREADS>
+// What one evaluation leaves behind for the LM phase (per problem slot, shared memory).
+template <int N, int P, int KMAX>
+struct BatchTail {
+    double tv[KMAX];          // ||r||^2, u_e, M_ef (upper triangle)
+    double top[N][N + P + 1]; // rows 0..n-1 of the rotated system: R, Q^T D, Q^T y
+    double rdiag[N];
+    int dropped, bad;
+};
+
+// G problems are in flight per CTA ("slots"). The serial LM step of a problem costs about as much as
+// its evaluation (ncu: 47 % of all samples were the other 511 threads waiting for thread 0), so the
+// CTA evaluates its G problems one after the other with all threads and then runs the G LM steps
+// CONCURRENTLY, each on lane 0 of a different warp: the LM latency is paid once per G evaluations.
+// y_p is re-read from global memory for every evaluation (first touch from HBM, then L2): keeping
+// G columns in registers is not possible at 128 registers per thread.
+template <int N, int P, int RPT, int THREADS, int G = 4>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_fit_kernel(const BatchArgs a)
 {
@@ -55,15 +98,15 @@ batch_fit_kernel(const BatchArgs a)
     constexpr int NW = THREADS / 32;
     constexpr int NTAIL = 1 + P + P * (P + 1) / 2; // ||r||^2, u_e, M_ef (upper)
     constexpr int KMAX = (NTAIL > NPV + 1) ? NTAIL : NPV + 1;
+    static_assert(G <= NW, "one warp per slot in the LM phase");
     extern __shared__ __align__(16) double colm[]; // NPV columns of mpad doubles
-    __shared__ double red[2][NW * KMAX];
-    __shared__ double top[N][NPV + 1]; // rows 0..n-1 of the rotated system (R, Q^T D, Q^T y)
+    __shared__ double red[2][NW * KMAX + KMAX];
     __shared__ double alpha_s[VP_MAX_Q];
-    __shared__ LmState st_s;
-    __shared__ LmEval ev_s;
-    __shared__ double coef_s[N], coef_acc[N];
-    __shared__ long long prob_s;
-    __shared__ int more_s;
+    __shared__ LmState st_s[G];
+    __shared__ BatchTail<N, P, KMAX> tail_s[G];
+    __shared__ double coef_acc[G][N];
+    __shared__ long long prob_s[G]; // problem in the slot, -1 = empty
+    __shared__ int exhausted_s, nactive_s;
 
     const int tid = threadIdx.x;
     const int m = a.md.m, mpad = a.mpad, q = a.md.q;
@@ -77,34 +120,50 @@ batch_fit_kernel(const BatchArgs a)
         xi[r] = in ? a.x[i] : 0.0;
         wi[r] = in ? (a.w ? a.w[i] : 1.0) : 0.0;
     }
+    if (tid < G) prob_s[tid] = -1;
+    if (tid == 0) exhausted_s = 0;
+    __syncthreads();
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) prob_s = (long long)atomicAdd(a.next, 1ull);
-        __syncthreads();
-        const long long prob = prob_s;
-        if (prob >= a.P) break;
-
-        // y_p: HBM -> registers, once per fit; weighted like builder.rs:307
-        double y[RPT];
-#pragma unroll
-        for (int r = 0; r < RPT; ++r) {
-            const int i = tid + r * THREADS;
-            y[r] = (i < m) ? wi[r] * __ldcs(&a.Y[(size_t)prob * a.ld + i]) : 0.0;
-        }
+        // ---- refill empty slots from the global work counter -------------------------------------
         if (tid == 0) {
-            double x0[VP_MAX_Q];
-            for (int k = 0; k < VP_MAX_Q; ++k) x0[k] = k < q ? a.alpha0[(size_t)prob * q + k] : 0.0;
-            lm_init(st_s, q, x0);
-            more_s = 1;
+            int nact = 0;
+            for (int g = 0; g < G; ++g) {
+                if (prob_s[g] < 0 && !exhausted_s) {
+                    const long long pnew = (long long)atomicAdd(a.next, 1ull);
+                    if (pnew < a.P) {
+                        double x0[VP_MAX_Q];
+                        for (int k = 0; k < VP_MAX_Q; ++k) x0[k] = k < q ? a.alpha0[(size_t)pnew * q + k] : 0.0;
+                        lm_init(st_s[g], q, x0);
+                        prob_s[g] = pnew;
+                    } else {
+                        exhausted_s = 1;
+                    }
+                }
+                nact += prob_s[g] >= 0;
+            }
+            nactive_s = nact;
         }
         __syncthreads();
+        if (nactive_s == 0) break;
 
-        while (more_s) {
-            if (tid < VP_MAX_Q) alpha_s[tid] = tid < q ? st_s.x_trial[tid] : 0.0;
+        // ---- evaluation phase: the active slots one after the other, all threads -----------------
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            const long long prob = prob_s[g];
+            if (prob < 0) continue; // uniform
+            BatchTail<N, P, KMAX> &tl = tail_s[g];
+            if (tid < VP_MAX_Q) alpha_s[tid] = tid < q ? st_s[g].x_trial[tid] : 0.0;
+            // y_p (weighted like builder.rs:307): issued first, consumed after the basis evaluation
+            double yt[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int i = tid + r * THREADS;
+                yt[r] = (i < m) ? wi[r] * __ldg(&a.Y[(size_t)prob * a.ld + i]) : 0.0;
+            }
             __syncthreads();
 
-            // ---- 1. Phi_w, D into the working matrix (rolled over basis functions, rows unrolled) ----
+            // 1. Phi_w, D into the working matrix (rolled over basis functions, rows unrolled)
             int bad = 0;
             {
                 int e = 0;
@@ -146,18 +205,14 @@ batch_fit_kernel(const BatchArgs a)
             }
             bad = __syncthreads_or(bad);
 
-            // ---- 2. Householder steps on [Phi_w | D | y] (y in registers) ----------------------------
-            double yt[RPT];
-#pragma unroll
-            for (int r = 0; r < RPT; ++r) yt[r] = y[r];
-            double rdiag[N];
+            // 2. Householder steps on [Phi_w | D | y] (y in registers)
             int dropped = 0;
 #pragma unroll
             for (int J = 0; J < N; ++J) {
                 const int K = NPV - J + 1; // sigma, dots with the columns to the right, dot with y
-                double s[NPV + 1];
+                double s[KMAX];
 #pragma unroll
-                for (int k = 0; k < NPV + 1; ++k) s[k] = 0.0;
+                for (int k = 0; k < KMAX; ++k) s[k] = 0.0;
 #pragma unroll
                 for (int r = 0; r < RPT; ++r) {
                     const int i = tid + r * THREADS;
@@ -170,31 +225,25 @@ batch_fit_kernel(const BatchArgs a)
                 }
                 if (tid == J) { // row J is owned by thread J (r = 0): publish it
 #pragma unroll
-                    for (int k = 0; k < NPV; ++k) top[J][k] = colm[(size_t)k * mpad + J];
-                    top[J][NPV] = yt[0];
+                    for (int k = 0; k < NPV; ++k) tl.top[J][k] = colm[(size_t)k * mpad + J];
+                    tl.top[J][NPV] = yt[0];
                 }
-                {
-                    double sv[KMAX];
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) sv[k] = (k < K) ? s[k] : 0.0;
-                    block_sum_once<KMAX, NW>(sv, red[J & 1]);
-#pragma unroll
-                    for (int k = 0; k < NPV + 1; ++k) s[k] = sv[k < KMAX ? k : 0];
-                }
+                (void)K;
+                block_sum_two_level<KMAX, NW>(s, red[J & 1]);
                 const double sigma = s[0];
-                const double ajj = top[J][J];
+                const double ajj = tl.top[J][J];
                 const double nrm = sqrt(sigma);
                 const bool keep = isfinite(nrm) && nrm > a.svd_eps;
                 const double al = (ajj >= 0.0) ? -nrm : nrm;
                 const double vnorm2 = 2.0 * (sigma - ajj * al);
                 const double bt = (keep && vnorm2 > 0.0) ? 2.0 / vnorm2 : 0.0;
-                rdiag[J] = keep ? al : 0.0;
+                if (tid == 0) tl.rdiag[J] = keep ? al : 0.0;
                 if (!keep) dropped |= 1 << J;
                 const double vjj = ajj - al;
                 double tau[NPV + 1];
 #pragma unroll
-                for (int k = 1; k < NPV - J; ++k) tau[k] = bt * (s[k] - al * top[J][J + k]);
-                const double tau_y = bt * (s[NPV - J] - al * top[J][NPV]);
+                for (int k = 1; k < NPV - J; ++k) tau[k] = bt * (s[k] - al * tl.top[J][J + k]);
+                const double tau_y = bt * (s[NPV - J] - al * tl.top[J][NPV]);
 #pragma unroll
                 for (int r = 0; r < RPT; ++r) {
                     const int i = tid + r * THREADS;
@@ -209,12 +258,12 @@ batch_fit_kernel(const BatchArgs a)
                 __syncthreads(); // everyone has read top[J]; its owner rewrites it with the final row
                 if (tid == J) {
 #pragma unroll
-                    for (int k = J + 1; k < NPV; ++k) top[J][k] = colm[(size_t)k * mpad + J]; // R[J][k], (Q^T D)[J][:]
-                    top[J][NPV] = yt[0];                                                        // (Q^T y)[J]
+                    for (int k = J + 1; k < NPV; ++k) tl.top[J][k] = colm[(size_t)k * mpad + J]; // R[J][k], (Q^T D)[J][:]
+                    tl.top[J][NPV] = yt[0];                                                        // (Q^T y)[J]
                 }
             }
 
-            // ---- 3. tail reduction: rows >= n (plus the rows of dropped columns) --------------------
+            // 3. tail reduction: rows >= n (plus the rows of dropped columns)
             {
                 double tv[KMAX];
 #pragma unroll
@@ -239,69 +288,78 @@ batch_fit_kernel(const BatchArgs a)
                             for (int f2 = e; f2 < P; ++f2) { tv[t] = fma(de[e], de[f2], tv[t]); ++t; }
                     }
                 }
-                block_sum_once<KMAX, NW>(tv, red[N & 1]);
-                // ---- 4. thread 0: coefficients, (||r||^2, g, H), LM step -------------------------------
+                block_sum_two_level<KMAX, NW>(tv, red[N & 1]);
                 if (tid == 0) {
-                    double coef[N];
 #pragma unroll
-                    for (int i = N - 1; i >= 0; --i) {
-                        double sacc = top[i][NPV];
-#pragma unroll
-                        for (int k = i + 1; k < N; ++k) sacc -= top[i][k] * coef[k];
-                        coef[i] = ((dropped >> i) & 1) ? 0.0 : sacc / rdiag[i];
-                    }
-                    LmEval &ev = ev_s;
-                    ev.rnorm2 = tv[0];
-                    int finite = !bad && isfinite(tv[0]);
-                    for (int k = 0; k < VP_LM_MAXQ; ++k) ev.g[k] = 0.0;
-                    for (int k = 0; k < VP_LM_MAXQ * VP_LM_MAXQ; ++k) ev.H[k] = 0.0;
-                    double Mm[P > 0 ? P : 1][P > 0 ? P : 1];
-                    {
-                        int t = 1 + P;
-#pragma unroll
-                        for (int e = 0; e < P; ++e)
-#pragma unroll
-                            for (int f2 = e; f2 < P; ++f2) { Mm[e][f2] = tv[t]; Mm[f2][e] = tv[t]; ++t; }
-                    }
-#pragma unroll
-                    for (int e = 0; e < P; ++e) {
-                        double ce = 0.0;
-#pragma unroll
-                        for (int r = 0; r < N; ++r) ce = (a.md.e_basis[e] == r) ? coef[r] : ce;
-                        const int ke = a.md.e_param[e];
-                        ev.g[ke] -= ce * tv[1 + e];
-#pragma unroll
-                        for (int f2 = 0; f2 < P; ++f2) {
-                            double cf = 0.0;
-#pragma unroll
-                            for (int r = 0; r < N; ++r) cf = (a.md.e_basis[f2] == r) ? coef[r] : cf;
-                            ev.H[a.md.e_param[f2] * q + ke] += Mm[e][f2] * ce * cf;
-                        }
-                    }
-                    for (int k = 0; k < q; ++k) finite = finite && isfinite(ev.g[k]);
-                    for (int k = 0; k < q * q; ++k) finite = finite && isfinite(ev.H[k]);
-                    ev.finite = finite;
-#pragma unroll
-                    for (int r = 0; r < N; ++r) coef_s[r] = coef[r];
-                    const bool more = lm_advance(st_s, a.cfg, ev);
-                    if (st_s.last_accepted) {
-#pragma unroll
-                        for (int r = 0; r < N; ++r) coef_acc[r] = coef_s[r];
-                    }
-                    more_s = more ? 1 : 0;
+                    for (int k = 0; k < KMAX; ++k) tl.tv[k] = tv[k];
+                    tl.dropped = dropped;
+                    tl.bad = bad;
                 }
             }
-            __syncthreads();
+            __syncthreads(); // the working matrix and the reduction buffers are free for the next slot
         }
 
-        // ---- results of this problem ---------------------------------------------------------------
-        if (tid == 0) {
-            for (int k = 0; k < q; ++k) a.alpha_out[(size_t)prob * q + k] = st_s.x[k];
-            for (int r = 0; r < N; ++r) a.C_out[(size_t)prob * N + r] = coef_acc[r];
-            a.obj_out[prob] = 0.5 * st_s.fnorm * st_s.fnorm;
-            a.term_out[prob] = st_s.termination;
-            a.nfev_out[prob] = st_s.nfev;
+        // ---- LM phase: lane 0 of warp g advances slot g; the G steps run concurrently ----------------
+        if ((tid & 31) == 0 && (tid >> 5) < G && prob_s[tid >> 5] >= 0) {
+            const int g = tid >> 5;
+            const BatchTail<N, P, KMAX> &tl = tail_s[g];
+            const int dropped = tl.dropped;
+            double coef[N];
+#pragma unroll
+            for (int i = N - 1; i >= 0; --i) {
+                double sacc = tl.top[i][NPV];
+#pragma unroll
+                for (int k = i + 1; k < N; ++k) sacc -= tl.top[i][k] * coef[k];
+                coef[i] = ((dropped >> i) & 1) ? 0.0 : sacc / tl.rdiag[i];
+            }
+            LmEval ev;
+            ev.rnorm2 = tl.tv[0];
+            int finite = !tl.bad && isfinite(tl.tv[0]);
+            for (int k = 0; k < VP_LM_MAXQ; ++k) ev.g[k] = 0.0;
+            for (int k = 0; k < VP_LM_MAXQ * VP_LM_MAXQ; ++k) ev.H[k] = 0.0;
+            double Mm[P > 0 ? P : 1][P > 0 ? P : 1];
+            {
+                int t = 1 + P;
+#pragma unroll
+                for (int e = 0; e < P; ++e)
+#pragma unroll
+                    for (int f2 = e; f2 < P; ++f2) { Mm[e][f2] = tl.tv[t]; Mm[f2][e] = tl.tv[t]; ++t; }
+            }
+#pragma unroll
+            for (int e = 0; e < P; ++e) {
+                double ce = 0.0;
+#pragma unroll
+                for (int r = 0; r < N; ++r) ce = (a.md.e_basis[e] == r) ? coef[r] : ce;
+                const int ke = a.md.e_param[e];
+                ev.g[ke] -= ce * tl.tv[1 + e];
+#pragma unroll
+                for (int f2 = 0; f2 < P; ++f2) {
+                    double cf = 0.0;
+#pragma unroll
+                    for (int r = 0; r < N; ++r) cf = (a.md.e_basis[f2] == r) ? coef[r] : cf;
+                    ev.H[a.md.e_param[f2] * q + ke] += Mm[e][f2] * ce * cf;
+                }
+            }
+            for (int k = 0; k < q; ++k) finite = finite && isfinite(ev.g[k]);
+            for (int k = 0; k < q * q; ++k) finite = finite && isfinite(ev.H[k]);
+            ev.finite = finite;
+            LmState &st = st_s[g];
+            const bool more = lm_advance(st, a.cfg, ev);
+            if (st.last_accepted) {
+#pragma unroll
+                for (int r = 0; r < N; ++r) coef_acc[g][r] = coef[r];
+            }
+            if (!more) { // results of this problem; the slot is refilled in the next round
+                const long long prob = prob_s[g];
+                for (int k = 0; k < q; ++k) a.alpha_out[(size_t)prob * q + k] = st.x[k];
+                for (int r = 0; r < N; ++r) a.C_out[(size_t)prob * N + r] = coef_acc[g][r];
+                a.obj_out[prob] = 0.5 * st.fnorm * st.fnorm;
+                a.term_out[prob] = st.termination;
+                a.nfev_out[prob] = st.nfev;
+                prob_s[g] = -1;
+            }
         }
+        __syncthreads();
     }
 }
 

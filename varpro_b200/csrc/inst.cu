@@ -49,8 +49,8 @@ static const QueueKernelEntry queue_tab[] = {VP_QK(32, 16, 0)};
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, queue_tab, (int)(sizeof(queue_tab) / sizeof(queue_tab[0]))};
 #elif VP_INST_PART == 4
 constexpr int BATCH_THREADS = 512;
-#define VP_BK(RPT) {N_, P_, RPT, BATCH_THREADS, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS>}
-static const BatchKernelEntry batch_tab[] = {VP_BK(1), VP_BK(2), VP_BK(4), VP_BK(8)};
+#define VP_BK(RPT, G) {N_, P_, RPT, BATCH_THREADS, G, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS, G>}
+static const BatchKernelEntry batch_tab[] = {VP_BK(1, 4), VP_BK(2, 4), VP_BK(4, 4), VP_BK(8, 4), VP_BK(8, 8), VP_BK(8, 2)};
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, batch_tab, (int)(sizeof(batch_tab) / sizeof(batch_tab[0]))};
 #else
 constexpr int PANEL_HH_THREADS = 512;

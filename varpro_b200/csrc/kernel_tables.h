@@ -26,8 +26,8 @@ struct QueueKernelEntry { // fit_queue_kernel: many fits on one persistent grid 
     int n, p, ksteps, nwarps, exact;
     const void *fn;
 };
-struct BatchKernelEntry { // batch_fit_kernel: one CTA fits one independent problem at a time
-    int n, p, rpt, threads;
+struct BatchKernelEntry { // batch_fit_kernel: one CTA fits `slots` independent problems at a time
+    int n, p, rpt, threads, slots;
     const void *fn;
 };
 struct KernelGroup {

@@ -1572,7 +1572,11 @@ static int batch_create_common(vp_ctx *ctx, vp_model *model, int64_t P, const vo
     for (size_t i = 0; i < g_batch_kernels.size(); ++i) {
         const BatchKernelEntry &k = g_batch_kernels[i];
         if (k.n != md.n || k.p != md.p || (long long)k.rpt * k.threads < md.m) continue;
-        if (pick < 0 || k.rpt < g_batch_kernels[pick].rpt) pick = (int)i;
+        // smallest row tiling that covers m; among those the requested number of problem slots (default 8)
+        const int want = env_int("VP_BATCH_SLOTS", 8);
+        if (pick < 0 || k.rpt < g_batch_kernels[pick].rpt ||
+            (k.rpt == g_batch_kernels[pick].rpt && std::abs(k.slots - want) < std::abs(g_batch_kernels[pick].slots - want)))
+            pick = (int)i;
     }
     if (pick < 0)
         return fail(ctx, VP_ERR_MODEL_TOO_LARGE, "vp_batch: no independent-batch kernel instantiated for this model shape / m > 4096");

@@ -84,7 +84,8 @@ typedef enum {
                                   shared_test_code/src/models.rs:321-322,362-385 */
     VP_BASIS_SIN_PHASE = 3,    /* sin(omega x + phi), params (omega,phi)
                                   src/test_helpers/mod.rs:27-51                  */
-    VP_BASIS_LINEAR_X = 4      /* scale*x (invariant) src/model/builder/test.rs:97,101 */
+    VP_BASIS_LINEAR_X = 4,     /* scale*x (invariant) src/model/builder/test.rs:97,101 */
+    VP_BASIS_HOST = 100        /* column supplied by the host callback (vp_model_create_hosteval) */
 } vp_basis_kind;
 
 typedef struct {
@@ -164,6 +165,19 @@ void *vp_ctx_stream(const vp_ctx *ctx);
  * (src/model/builder/mod.rs:547-557) and n >= 1 (:538). */
 int vp_model_create(vp_ctx *ctx, int dtype, int64_t m, const void *x_host, int32_t q, int32_t n,
                     const vp_basis_desc *basis, vp_model **out);
+/* Host-evaluated model: keeps ARBITRARY SeparableNonlinearModel implementations (user closures,
+ * hand-rolled models: src/model/mod.rs:239-363, src/model/detail.rs:96-127) working while the
+ * O(m*S) work stays on the GPU. The library calls `eval` on the host once per evaluation with the
+ * q parameters; it must fill phi_out (m x n, column-major, f64: model.eval(), :441-471) and
+ * dphi_out (m x p, column-major, f64): the p NON-ZERO columns of the derivative matrices
+ * (eval_partial_deriv, :473-512), column e being d(basis ind[2e]) / d(param ind[2e+1]) -- the
+ * `Ind` table of the original MATLAB code (matlab/varpro.m:147-189). Return 0, or non-zero to
+ * signal a model error (the cache becomes None, src/solvers/levmar/mod.rs:43-45).
+ * Such problems are fitted with the host-driven LM loop (one callback + one streaming pass per
+ * evaluation); the fused / persistent kernels need the built-in device basis functions. */
+typedef int (*vp_host_eval_fn)(void *user, const double *alpha, double *phi_out, double *dphi_out);
+int vp_model_create_hosteval(vp_ctx *ctx, int dtype, int64_t m, int32_t q, int32_t n, int32_t p, const int32_t *ind,
+                             vp_host_eval_fn eval, void *user, vp_model **out);
 int vp_model_destroy(vp_model *model);
 
 /* ---- problem: replaces SeparableProblemBuilder::build + SeparableProblem ---

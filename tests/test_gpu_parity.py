@@ -467,3 +467,76 @@ def test_statistics_mrhs_every_column_matches_oracle():
         assert np.max(np.abs(sts[s].covariance_matrix() - so["covariance"])) <= 1e-6 * np.abs(so["covariance"]).max()
         assert abs(sts[s].reduced_chi2() - so["reduced_chi2"]) <= 1e-8 * so["reduced_chi2"]
         assert np.max(np.abs(sts[s]._sigma - so["unscaled_confidence_sigma"])) <= 1e-6 * np.abs(so["unscaled_confidence_sigma"]).max()
+
+
+def _closure_double_exp_model(x, alpha0):
+    """The reference's own way of building the model: closures + partial derivatives
+    (shared_test_code/src/lib.rs:101-135)."""
+    import varpro_b200 as vb
+
+    def exp_decay(x, tau):
+        return np.exp(-x / tau)
+
+    def exp_decay_dtau(x, tau):
+        return np.exp(-x / tau) * x / (tau * tau)
+
+    return (vb.SeparableModelBuilder(["tau1", "tau2"])
+            .function(["tau1"], exp_decay).partial_deriv("tau1", exp_decay_dtau)
+            .function(["tau2"], exp_decay).partial_deriv("tau2", exp_decay_dtau)
+            .invariant_function(lambda x: np.ones_like(x))
+            .independent_variable(x).initial_parameters(alpha0).build())
+
+
+def test_host_evaluated_closure_model_matches_builtin_and_oracle():
+    """Arbitrary SeparableNonlinearModel implementations (host closures) through vp_model_create_hosteval:
+    Phi / dPhi come from the host once per evaluation, the O(m*S) pass and the LM step stay in the library."""
+    import varpro_b200 as vb
+    wl = W.c2(S=48)
+    model = _closure_double_exp_model(wl["x"], wl["alpha0"])
+    assert model.is_host_evaluated()
+    gp = vb.SeparableProblemBuilder.mrhs(model).observations(wl["Y"]).build()
+    op = W.make_oracle(wl)
+    _compare_state(gp, op, np.linalg.norm(wl["Y"]), "closure model @alpha0")
+    builtin = W.make_gpu_problem(wl)
+    rb, rh = builtin.reduce(), gp.reduce()
+    assert abs(rb["rnorm2"] - rh["rnorm2"]) <= 1e-10 * rb["rnorm2"]
+    assert np.max(np.abs(rb["H"] - rh["H"])) <= 1e-9 * np.abs(rb["H"]).max()
+    res = vb.LevMarSolver.default().fit(gp)
+    assert res.was_successful()
+    assert np.allclose(np.sort(res.nonlinear_parameters()), [1.0, 3.0], rtol=0, atol=1e-8)
+    assert np.max(np.abs(res.best_fit() - wl["Y"])) <= 1e-5 * np.abs(wl["Y"]).max()
+    rep = op.fit()
+    a_g, a_o = np.sort(res.nonlinear_parameters()), np.sort(op.params())
+    assert np.max(np.abs(a_g - a_o) / a_o) <= REL_PARAM
+
+
+def test_host_evaluated_model_statistics_and_errors():
+    import varpro_b200 as vb
+    wl = W.lmfit_case(True)
+    model = _closure_double_exp_model(wl["x"], wl["alpha0"])
+    gp = vb.SeparableProblemBuilder.new(model).observations(wl["Y"][:, 0]).weights(wl["weights"]).build()
+    res, st = vb.LevMarSolver.default().fit_with_statistics(gp)
+    assert np.allclose(res.nonlinear_parameters(), wl["gold"]["tau"], rtol=0, atol=1e-5)
+    assert np.max(np.abs(st.covariance_matrix() - wl["covmat"])) <= 1e-6
+    # a closure that raises: the cache becomes None, fit stops with a User termination (levmar/mod.rs:43-45)
+    calls = {"n": 0}
+
+    def flaky(x, tau):
+        calls["n"] += 1
+        if calls["n"] > 3:
+            raise RuntimeError("model error")
+        return np.exp(-x / tau)
+
+    bad = (vb.SeparableModelBuilder(["tau"]).function(["tau"], flaky)
+           .partial_deriv("tau", lambda x, tau: np.exp(-x / tau) * x / tau ** 2)
+           .invariant_function(lambda x: np.ones_like(x))
+           .independent_variable(wl["x"]).initial_parameters([1.0]).build())
+    gp2 = vb.SeparableProblemBuilder.new(bad).observations(wl["Y"][:, 0]).build()
+    with pytest.raises(vb.FitError) as ei:
+        vb.LevMarSolver.default().fit(gp2)
+    assert repr(ei.value.result.minimization_report.termination).lower().find("user") >= 0
+    assert gp2.residuals() is None
+    # missing derivative -> build error like the reference
+    with pytest.raises(vb.ModelBuildError):
+        (vb.SeparableModelBuilder(["tau"]).function(["tau"], lambda x, tau: np.exp(-x / tau))
+         .independent_variable(wl["x"]).initial_parameters([1.0]).build())

@@ -3,7 +3,7 @@ surface of geo-ant/varpro. Importing the package does not load
 the CUDA library; the first use of a problem/solver does, and fails loudly if
 the extension is missing."""
 from .api import (  # noqa: F401
-    BatchFitResult, Constant, ExpDecay, ExpRateCos, FitError, FitResult, FitStatistics, IndependentBatch, LevenbergMarquardt, LevMarSolver, LinearX,
+    BatchFitResult, Constant, ExpDecay, ExpRateCos, FitError, FitResult, FitStatistics, HostFunction, IndependentBatch, LevenbergMarquardt, LevMarSolver, LinearX,
     MinimizationReport, ModelBuildError, ModelError, SeparableModel, SeparableModelBuilder,
     SeparableProblem, SeparableProblemBuilder, SeparableProblemBuilderError, SinPhase,
     TerminationReason, VarproError, kernel_launches,

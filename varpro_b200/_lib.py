@@ -41,6 +41,8 @@ class Reduced(C.Structure):
                 ("H", C.c_double * (VP_MAX_Q * VP_MAX_Q)), ("finite", C.c_int32), ("q", C.c_int32)]
 
 
+HOST_EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+
 # every symbol include/varpro_b200.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 _pp = C.POINTER(C.c_void_p)
@@ -55,6 +57,8 @@ SYMBOLS = {
     "vp_ctx_stream": (C.c_void_p, [_vp]),
     "vp_model_create": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, C.c_int32, C.c_int32,
                                   C.POINTER(BasisDesc), _pp]),
+    "vp_model_create_hosteval": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_int32), C.c_void_p, _vp, _pp]),
     "vp_model_destroy": (C.c_int, [_vp]),
     "vp_problem_create": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),
     "vp_problem_create_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),

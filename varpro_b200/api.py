@@ -161,6 +161,38 @@ def LinearX(scale=1.0):
     return BasisFunction(4, 0, float(scale))
 
 
+class HostFunction:
+    """A basis function given as a host closure f(x, *params) -> array of len(x), with its partial
+    derivatives (the reference's `.function(params, f).partial_deriv(name, df)`,
+    src/model/builder/mod.rs:338-440). A model that contains one is evaluated on the host once per
+    evaluation (vp_model_create_hosteval); the O(m*S) work stays on the GPU."""
+
+    def __init__(self, f, param_names):
+        self.f = f
+        self.param_names = list(param_names)
+        self.arity = len(self.param_names)
+        self.derivs = {}
+        self.kind, self.scale = 100, 1.0
+
+
+def _builtin_numpy(fn: "BasisFunction", x, p):
+    """numpy restatement of the built-in device kinds (used when a model mixes them with host closures)."""
+    k = fn.kind
+    if k == 0:
+        e = np.exp(-x / p[0])
+        return e, [e * x / (p[0] * p[0])]
+    if k == 1:
+        return np.ones_like(x), []
+    if k == 2:
+        e, c, sn = np.exp(-p[0] * x), np.cos(p[1] * x), np.sin(p[1] * x)
+        return e * c, [-x * (e * c), -x * e * sn]
+    if k == 3:
+        return np.sin(p[0] * x + p[1]), [x * np.cos(p[0] * x + p[1]), np.cos(p[0] * x + p[1])]
+    if k == 4:
+        return fn.scale * x, []
+    raise ModelError(f"unsupported basis kind {k}")
+
+
 # ---------------------------------------------------------------------------
 # device context (one per device ordinal, created lazily)
 # ---------------------------------------------------------------------------
@@ -232,6 +264,30 @@ class SeparableModel:
             raise ModelError(f"Model expects {self.parameter_count()} parameters, but got {p.shape[0]}")
         self._params = p.copy()
 
+    def is_host_evaluated(self) -> bool:
+        return any(isinstance(f, HostFunction) for f, _ in self._functions)
+
+    def derivative_index(self):
+        """(basis j, parameter k) of every non-zero derivative column, ordered by (function, slot)."""
+        return [(j, k) for j, (_, idx) in enumerate(self._functions) for k in idx]
+
+    def eval_host(self, alpha):
+        """model.eval() and the non-zero columns of eval_partial_deriv(k) on the host (f64)."""
+        x = np.asarray(self.x, dtype=np.float64)
+        cols, dcols = [], []
+        for f, idx in self._functions:
+            p = [alpha[i] for i in idx]
+            if isinstance(f, HostFunction):
+                v = np.asarray(f.f(x, *p), dtype=np.float64)
+                ds = [np.asarray(f.derivs[nm](x, *p), dtype=np.float64) for nm in f.param_names]
+            else:
+                v, ds = _builtin_numpy(f, x, p)
+            if v.shape != x.shape or any(d.shape != x.shape for d in ds):
+                raise ModelError(f"Basis function gave vector of length {v.shape}, but expected output length {x.shape}")
+            cols.append(v)
+            dcols.extend(ds)
+        return cols, dcols
+
     def _descs(self):
         arr = (_lib.BasisDesc * len(self._functions))()
         for d, (f, idx) in zip(arr, self._functions):
@@ -273,11 +329,18 @@ class SeparableModelBuilder:
         if len(set(names)) != len(names):
             return self._fail(DuplicateParameterNames(f"Parameter list {list(names)} contains duplicates!"))
 
-    def function(self, function_params: Sequence[str], function: BasisFunction):
+    def function(self, function_params: Sequence[str], function):
+        """`function`: a built-in device basis function (ExpDecay(), ...) or any host callable
+        f(x, *params) -> array, whose derivatives are then added with .partial_deriv(name, df)."""
         fp = list(function_params)
         self._check_names(fp)
         if self._error:
             return self
+        if not isinstance(function, BasisFunction):
+            if not callable(function):
+                self._fail(ModelBuildError("function must be a BasisFunction or a callable"))
+                return self
+            function = HostFunction(function, fp)
         if len(fp) != function.arity:
             self._fail(IncorrectParameterCount(
                 f"Incorrect number of parameters for function: expected {function.arity}, got {len(fp)}"))
@@ -292,7 +355,9 @@ class SeparableModelBuilder:
         self._functions.append((function, idx))
         return self
 
-    def invariant_function(self, function: BasisFunction):
+    def invariant_function(self, function):
+        if not isinstance(function, BasisFunction) and callable(function):
+            function = HostFunction(function, [])
         if function.arity != 0:
             self._fail(IncorrectParameterCount(
                 f"Incorrect number of parameters for function: expected {function.arity}, got 0"))
@@ -301,7 +366,21 @@ class SeparableModelBuilder:
         return self
 
     def partial_deriv(self, parameter: str, derivative=None):
-        """Accepted for source compatibility: derivatives of the built-in kinds are built in."""
+        """src/model/builder/mod.rs:387-440. For the built-in device kinds the derivatives are built in
+        (accepted and ignored); for a host closure the derivative callable df(x, *params) is required."""
+        if self._error or not self._functions:
+            return self
+        f, _ = self._functions[-1]
+        if isinstance(f, HostFunction):
+            if parameter not in f.param_names:
+                self._fail(FunctionParameterNotInModel(
+                    f"Function parameter '{parameter}' is not part of the function's parameters."))
+            elif parameter in f.derivs:
+                self._fail(ModelBuildError(f"Derivative for parameter '{parameter}' was already provided!"))
+            elif not callable(derivative):
+                self._fail(ModelBuildError("partial_deriv of a host function needs a callable"))
+            else:
+                f.derivs[parameter] = derivative
         return self
 
     def independent_variable(self, x):
@@ -321,6 +400,11 @@ class SeparableModelBuilder:
         for k, nm in enumerate(self._names):  # src/model/builder/mod.rs:547-557
             if k not in used:
                 raise UnusedParameter(f"Model depends on parameter '{nm}', but none of its functions use it.")
+        for f, _ in self._functions:  # MissingDerivative (src/model/builder/error.rs)
+            if isinstance(f, HostFunction):
+                for nm in f.param_names:
+                    if nm not in f.derivs:
+                        raise ModelBuildError(f"Missing partial derivative for parameter '{nm}'.")
         if self._x is None:
             raise MissingX("Missing vector for independent variable x")
         if self._p0 is None:
@@ -350,9 +434,35 @@ class SeparableProblem:
         self._model_h = C.c_void_p()
         self._h = C.c_void_p()
         dt = VP_F32 if self.dtype == np.float32 else VP_F64
-        descs = model._descs()
-        _check(lib.vp_model_create(self._ctx.h, dt, self._m, model.x.ctypes.data_as(C.c_void_p), self._q,
-                                   self._n, descs, C.byref(self._model_h)), self._ctx.h)
+        if model.is_host_evaluated():
+            ind = model.derivative_index()
+            p = len(ind)
+            ind_arr = (C.c_int32 * max(2 * p, 1))(*[v for jk in ind for v in jk])
+            m_, n_ = self._m, self._n
+
+            def _cb(_user, alpha_p, phi_p, dphi_p):
+                try:
+                    alpha = np.array([alpha_p[i] for i in range(self._q)], dtype=np.float64)
+                    cols, dcols = model.eval_host(alpha)
+                    phi = np.ctypeslib.as_array(phi_p, shape=(n_, m_))      # column-major m x n == row-major n x m
+                    for j, c in enumerate(cols):
+                        phi[j, :] = c
+                    if p:
+                        dphi = np.ctypeslib.as_array(dphi_p, shape=(p, m_))
+                        for e, c in enumerate(dcols):
+                            dphi[e, :] = c
+                    return 0
+                except Exception:  # a model error: the cache becomes None (src/solvers/levmar/mod.rs:43-45)
+                    return 1
+
+            self._host_cb = _lib.HOST_EVAL_FN(_cb)  # must outlive the model handle
+            _check(lib.vp_model_create_hosteval(self._ctx.h, dt, self._m, self._q, self._n, p, ind_arr,
+                                                C.cast(self._host_cb, C.c_void_p), None, C.byref(self._model_h)),
+                   self._ctx.h)
+        else:
+            descs = model._descs()
+            _check(lib.vp_model_create(self._ctx.h, dt, self._m, model.x.ctypes.data_as(C.c_void_p), self._q,
+                                       self._n, descs, C.byref(self._model_h)), self._ctx.h)
         a0 = np.ascontiguousarray(model.params(), dtype=np.float64)
         w = None if weights is None else np.ascontiguousarray(weights, dtype=self.dtype)
         wp = None if w is None else w.ctypes.data_as(C.c_void_p)

@@ -118,8 +118,9 @@ template <typename T>
 __global__ void __launch_bounds__(PANEL_THREADS)
 panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
              const double *__restrict__ alpha_dev, double svd_eps, int ldp, T *__restrict__ Pq,
-             PanelSmall *__restrict__ small, unsigned long long *dbg)
+             PanelSmall *__restrict__ small, unsigned long long *dbg, const double *__restrict__ pre)
 {
+    // pre != nullptr: host-evaluated model -- the unweighted [Phi | D] (m x (n+p), f64) was uploaded
     extern __shared__ __align__(16) double psm[];
     const int m = md.m, n = md.n, p = md.p;
     double *col = psm;                           // (n+p) columns of m doubles
@@ -171,7 +172,15 @@ panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
 
     // 1. evaluate the weighted basis functions and derivative columns
     int bad = 0;
-    for (int i = tid; i < m; i += nt) {
+    if (pre) {
+        for (int idx = tid; idx < m * (n + p); idx += nt) {
+            const int i = idx % m;
+            const double v = (w ? (double)w[i] : 1.0) * pre[idx];
+            bad |= !isfinite(v);
+            col[idx] = v;
+        }
+    }
+    for (int i = tid; i < m && !pre; i += nt) {
         const double xi = (double)x[i];
         const double wi = w ? (double)w[i] : 1.0;
         int e = 0; // derivative columns are ordered by (basis function, slot)

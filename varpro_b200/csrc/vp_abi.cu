@@ -109,6 +109,12 @@ struct vp_model {
     ModelDesc md{};
     void *x_dev = nullptr;
     int ld = 0; // padded row count (multiple of 16/sizeof(T))
+    // host-evaluated model (vp_model_create_hosteval)
+    bool hosteval = false;
+    vp_host_eval_fn eval_fn = nullptr;
+    void *eval_user = nullptr;
+    double *pre_host = nullptr; // pinned m x (n+p)
+    double *pre_dev = nullptr;  // the unweighted [Phi | D] of the last callback
 };
 
 // Column-sharded global fit across the GPUs of one box (one process per GPU): this rank's
@@ -348,10 +354,58 @@ extern "C" int vp_model_create(vp_ctx *ctx, int dtype, int64_t m, const void *x_
     return VP_OK;
 }
 
+extern "C" int vp_model_create_hosteval(vp_ctx *ctx, int dtype, int64_t m, int32_t q, int32_t n, int32_t p, const int32_t *ind,
+                                        vp_host_eval_fn eval, void *user, vp_model **out)
+{
+    if (!ctx || !out) return VP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (dtype != VP_F64 && dtype != VP_F32) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "dtype must be VP_F64 or VP_F32");
+    if (!eval) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "vp_model_create_hosteval: eval callback is NULL");
+    if (n <= 0) return fail(ctx, VP_ERR_EMPTY_MODEL, vp_status_string(VP_ERR_EMPTY_MODEL));
+    if (m <= 0) return fail(ctx, VP_ERR_ZERO_LENGTH_VECTOR, vp_status_string(VP_ERR_ZERO_LENGTH_VECTOR));
+    if (n > VP_MAX_N || q > VP_MAX_Q || q < 0 || p < 0 || p > VP_MAX_P || m > (1 << 24) || (p > 0 && !ind))
+        return fail(ctx, VP_ERR_MODEL_TOO_LARGE, vp_status_string(VP_ERR_MODEL_TOO_LARGE));
+    ModelDesc md{};
+    md.m = (int)m; md.n = n; md.q = q; md.p = p;
+    for (int j = 0; j < n; ++j) { md.kind[j] = VP_BASIS_HOST; md.npar[j] = 0; }
+    std::vector<int> used(q > 0 ? q : 1, 0);
+    for (int e = 0; e < p; ++e) {
+        const int j = ind[2 * e], k = ind[2 * e + 1];
+        if (j < 0 || j >= n) return fail(ctx, VP_ERR_DERIVATIVE_INDEX_OUT_OF_BOUNDS, vp_status_string(VP_ERR_DERIVATIVE_INDEX_OUT_OF_BOUNDS));
+        if (k < 0 || k >= q) return fail(ctx, VP_ERR_PARAMETER_NOT_IN_MODEL, vp_status_string(VP_ERR_PARAMETER_NOT_IN_MODEL));
+        md.e_basis[e] = j; md.e_param[e] = k; md.e_slot[e] = 0;
+        used[k] = 1;
+    }
+    for (int k = 0; k < q; ++k)
+        if (!used[k]) return fail(ctx, VP_ERR_UNUSED_PARAMETER, vp_status_string(VP_ERR_UNUSED_PARAMETER));
+    vp_model *mo = new (std::nothrow) vp_model();
+    if (!mo) return VP_ERR_OUT_OF_MEMORY;
+    mo->ctx = ctx; mo->dtype = dtype; mo->md = md;
+    mo->hosteval = true; mo->eval_fn = eval; mo->eval_user = user;
+    const int v = vec_of(dtype);
+    mo->ld = (int)((m + v - 1) / v * v);
+    cudaSetDevice(ctx->device);
+    const size_t bytes = sizeof(double) * (size_t)m * (n + p);
+    cudaError_t e = DEV_ALLOC(ctx, &mo->pre_dev, bytes);
+    if (e == cudaSuccess) e = HOST_ALLOC(ctx, &mo->pre_host, bytes);
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &mo->x_dev, esize(dtype) * (size_t)m); // unused by the kernels; keeps the layout uniform
+    if (e == cudaSuccess) e = cudaMemsetAsync(mo->x_dev, 0, esize(dtype) * (size_t)m, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        DEV_FREE(ctx, mo->pre_dev); HOST_FREE(ctx, mo->pre_host); DEV_FREE(ctx, mo->x_dev);
+        delete mo;
+        return fail(ctx, VP_ERR_CUDA, std::string("vp_model_create_hosteval: ") + cudaGetErrorString(e));
+    }
+    *out = mo;
+    return VP_OK;
+}
+
 extern "C" int vp_model_destroy(vp_model *model)
 {
     if (!model) return VP_OK;
     cudaSetDevice(model->ctx->device);
+    DEV_FREE(model->ctx, model->pre_dev);
+    HOST_FREE(model->ctx, model->pre_host);
     DEV_FREE(model->ctx, model->x_dev);
     delete model;
     return VP_OK;
@@ -397,6 +451,7 @@ static int plan_fit_kernel(vp_problem *pr, const DmmaKernelEntry &dk, int lds)
     pr->plan_fit = -1;
     const char *which = getenv("VP_EVAL_KERNEL"); // "fused" (default) or "split" (K1 + K2)
     if (which && !strcmp(which, "split")) return VP_OK;
+    if (pr->model->hosteval) return VP_OK; // the fused kernels evaluate the built-in device basis functions
     for (size_t i = 0; i < g_fit_kernels.size(); ++i) {
         const FitKernelEntry &k = g_fit_kernels[i];
         if (k.n != dk.n || k.p != dk.p || k.ksteps != dk.ksteps || k.nwarps != dk.nwarps || k.exact != dk.exact) continue;
@@ -563,7 +618,7 @@ static int launch_panel_t(vp_problem *pr)
     const ModelDesc &md = mo->md;
     unsigned long long *dbg = pr->dbg ? pr->dbg + (size_t)pr->max_grid * VP_DBG_SLOTS : nullptr;
     // fast path: register-resident Householder panel
-    if (!env_int("VP_PANEL_GENERIC", 0)) {
+    if (!env_int("VP_PANEL_GENERIC", 0) && !mo->hosteval) {
         for (const PanelHHEntry &k : g_panel_kernels) {
             if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p || (long long)k.rpt * k.threads < md.m) continue;
             ModelDesc mdc = md;
@@ -591,7 +646,8 @@ static int launch_panel_t(vp_problem *pr)
         configured = smem;
     }
     panel_kernel<T><<<1, threads, smem, ctx->stream>>>(md, (const T *)mo->x_dev, (const T *)pr->w_dev, pr->alpha_dev,
-                                                       pr->svd_eps, pr->ldp, (T *)pr->Pq, pr->small, dbg);
+                                                       pr->svd_eps, pr->ldp, (T *)pr->Pq, pr->small, dbg,
+                                                       mo->hosteval ? mo->pre_dev : nullptr);
     ctx->launches++;
     VP_CUDA(ctx, cudaGetLastError());
     return VP_OK;
@@ -706,12 +762,30 @@ static int comm_check(vp_problem *pr)
     return VP_OK;
 }
 
+// host-evaluated model: run the user's callback at `alpha` and upload the unweighted [Phi | D]
+static int host_eval_push(vp_problem *pr, const double *alpha)
+{
+    vp_ctx *ctx = pr->ctx;
+    vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    const size_t nphi = (size_t)md.m * md.n, nd = (size_t)md.m * md.p;
+    VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the previous upload has been consumed
+    const int rc = mo->eval_fn(mo->eval_user, alpha, mo->pre_host, mo->pre_host + nphi);
+    if (rc != 0) return fail(ctx, VP_ERR_NO_CACHED_CALCULATION, "the model's evaluation callback reported an error");
+    VP_CUDA(ctx, cudaMemcpyAsync(mo->pre_dev, mo->pre_host, sizeof(double) * (nphi + nd), cudaMemcpyHostToDevice, ctx->stream));
+    return VP_OK;
+}
+
 // Evaluate at `alpha` into coefficient buffer `cdst`; result in pr->out_host.
 static int evaluate_sync(vp_problem *pr, const double *alpha, int cdst)
 {
     vp_ctx *ctx = pr->ctx;
     const int q = pr->model->md.q;
     cudaSetDevice(ctx->device);
+    if (pr->model->hosteval) {
+        int rce = host_eval_push(pr, alpha);
+        if (rce != VP_OK) return rce;
+    }
     for (int k = 0; k < q; ++k) pr->alpha_stage[k] = alpha[k];
     if (q > 0)
         VP_CUDA(ctx, cudaMemcpyAsync(pr->alpha_dev, pr->alpha_stage, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
@@ -821,6 +895,11 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     // first evaluation at the initial guess (src/problem/builder.rs:321)
     for (int k = 0; k < md.q; ++k) pr->alpha[k] = alpha0[k];
     rc = evaluate_sync(pr, pr->alpha, pr->cur);
+    if (rc == VP_ERR_NO_CACHED_CALCULATION) { // model error: the problem is built with cache = None (levmar/mod.rs:43-45)
+        pr->cached = false;
+        *out = pr;
+        return VP_OK;
+    }
     if (rc != VP_OK) { vp_problem_destroy(pr); return rc; }
     evalout_to_lm(*pr->out_host, md.q, pr->eval);
     pr->cached = pr->eval.finite != 0;
@@ -867,6 +946,7 @@ extern "C" int vp_set_params(vp_problem *pr, const double *alpha)
     for (int k = 0; k < q; ++k) pr->alpha[k] = alpha[k];
     const int dst = pr->cur ^ 1;
     int rc = evaluate_sync(pr, pr->alpha, dst);
+    if (rc == VP_ERR_NO_CACHED_CALCULATION) { pr->cached = false; return VP_OK; } // model error -> cache = None
     if (rc != VP_OK) { pr->cached = false; return rc; }
     pr->cur = dst;
     evalout_to_lm(*pr->out_host, q, pr->eval);
@@ -901,6 +981,10 @@ static int ensure_panel_current(vp_problem *pr)
 {
     vp_ctx *ctx = pr->ctx;
     const int q = pr->model->md.q;
+    if (pr->model->hosteval) {
+        int rce = host_eval_push(pr, pr->alpha);
+        if (rce != VP_OK) return rce;
+    }
     for (int k = 0; k < q; ++k) pr->alpha_stage[k] = pr->alpha[k];
     if (q > 0)
         VP_CUDA(ctx, cudaMemcpyAsync(pr->alpha_dev, pr->alpha_stage, sizeof(double) * q, cudaMemcpyHostToDevice, ctx->stream));
@@ -926,8 +1010,12 @@ static int materialise_t(vp_problem *pr, int what, void *out_host)
         jacobian_kernel<T><<<blocks, 256, 0, ctx->stream>>>(pr->ldp, md.m, (int)pr->S, md.n, md.p, md.q,
                                                             (const T *)pr->Pq + (size_t)md.n * pr->ldp, (const T *)pr->C[pr->cur], md, buf);
     } else {
-        phi_kernel<T><<<32, 256, 0, ctx->stream>>>(md, (const T *)mo->x_dev, pr->alpha_dev, pr->phi_scratch);
-        ctx->launches++;
+        if (mo->hosteval) {
+            cudaMemcpyAsync(pr->phi_scratch, mo->pre_dev, sizeof(double) * (size_t)md.m * md.n, cudaMemcpyDeviceToDevice, ctx->stream);
+        } else {
+            phi_kernel<T><<<32, 256, 0, ctx->stream>>>(md, (const T *)mo->x_dev, pr->alpha_dev, pr->phi_scratch);
+            ctx->launches++;
+        }
         best_fit_kernel<T><<<blocks, 256, 0, ctx->stream>>>(md.m, (int)pr->S, md.n, pr->phi_scratch,
                                                             (const T *)pr->C[pr->cur], buf);
     }
@@ -1194,7 +1282,7 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
         more = false;
     }
     if (more && pr->comm) return fail(pr->ctx, VP_ERR_COMM, "column-sharded fits run on the persistent fit kernel only");
-    if (more && !(mode && !strcmp(mode, "host"))) {
+    if (more && !(mode && !strcmp(mode, "host")) && !pr->model->hosteval) {
         // ---- device-driven loop: one CUDA graph launch per fit ------------------------
         vp_ctx *ctx = pr->ctx;
         cudaSetDevice(ctx->device);
@@ -1222,6 +1310,11 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
         // ---- host-driven loop (VP_FIT_MODE=host): one synchronisation per evaluation ---
         const int dst = pr->cur ^ 1;
         int rc = evaluate_sync(pr, st.x_trial, dst);
+        if (rc == VP_ERR_NO_CACHED_CALCULATION) { // residuals() is None -> the LM loop stops with a User termination
+            st.termination = TERM_USER;
+            pr->cached = false;
+            break;
+        }
         if (rc != VP_OK) return rc;
         LmEval ev;
         evalout_to_lm(*pr->out_host, q, ev);
@@ -1496,7 +1589,10 @@ static int statistics_t(vp_problem *pr, double *cov_host, double *chi2_host, dou
     int host_flag = 0;
     if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream);
     if (e == cudaSuccess) {
-        basis_kernel<T><<<(m + 255) / 256, 256, 0, ctx->stream>>>(md, (const T *)mo->x_dev, pr->alpha_dev, B);
+        if (mo->hosteval)
+            cudaMemcpyAsync(B, mo->pre_dev, sizeof(double) * (size_t)m * t0, cudaMemcpyDeviceToDevice, ctx->stream);
+        else
+            basis_kernel<T><<<(m + 255) / 256, 256, 0, ctx->stream>>>(md, (const T *)mo->x_dev, pr->alpha_dev, B);
         gram_kernel<T><<<(t0 * t0 + 127) / 128, 128, 0, ctx->stream>>>(m, t0, B, (const T *)pr->w_dev, Gm);
         long long blocks = ((long long)S + 7) / 8;
         if (blocks > (long long)ctx->sm_count * 8) blocks = (long long)ctx->sm_count * 8;
@@ -1559,6 +1655,7 @@ static int batch_create_common(vp_ctx *ctx, vp_model *model, int64_t P, const vo
     *out = nullptr;
     if (model->ctx != ctx) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "model belongs to a different context");
     if (model->dtype != VP_F64) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "vp_batch: fp64 models only");
+    if (model->hosteval) return fail(ctx, VP_ERR_UNSUPPORTED_BASIS, "vp_batch: needs the built-in device basis functions");
     if (!Y) return fail(ctx, VP_ERR_Y_DATA_MISSING, vp_status_string(VP_ERR_Y_DATA_MISSING));
     const ModelDesc &md = model->md;
     if (P <= 0) return fail(ctx, VP_ERR_ZERO_LENGTH_VECTOR, vp_status_string(VP_ERR_ZERO_LENGTH_VECTOR));
@@ -1770,6 +1867,7 @@ extern "C" int vp_profile_evaluation(vp_problem *pr, int iters, int64_t flush_by
     // warm-up: keep the device busy long enough for the clocks to ramp up
     const bool fused = pr->plan_fit >= 0;
     if (pr->comm) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "vp_profile_evaluation: not for column-sharded problems");
+    if (pr->model->hosteval) return fail(ctx, VP_ERR_INVALID_ARGUMENT, "vp_profile_evaluation: not for host-evaluated models");
     for (int it = 0; it < 64 && rc == VP_OK; ++it) {
         if (fused) { rc = launch_fused(pr, pr->cur ^ 1, false); continue; }
         rc = launch_panel(pr);

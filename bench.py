@@ -65,8 +65,9 @@ class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
         self.index = index
+        self.enabled = enabled
         self.samples = []
         self.reasons = set()
         self._stop = threading.Event()
@@ -88,13 +89,15 @@ class ClockSampler:
             self._stop.wait(0.05)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.enabled:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         if not self.samples:
@@ -205,14 +208,18 @@ def run_gpu(args, rank, world, local_rank):
             p.close()
     probs = fresh(K)
     launches0 = ctx.kernel_launches()
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank, enabled=(rank == 0))  # one sampler per job: nvidia-smi polling costs host CPU
     clocks.__enter__()  # samples until the end of the e2e region: all three timed regions run under it
     ms, nfev = timed_fits(probs, many=True)
     launches = ctx.kernel_launches() - launches0
     alpha = np.sort(probs[-1].params())
     assert np.allclose(alpha, [1.0, 3.0], atol=1e-8), alpha
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    rank_ms = [ms]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(v.item()) for v in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     timed_evals = int(sum(nfev) - len(nfev))  # the evaluation at the starting point belongs to the (un-timed) build
@@ -313,7 +320,7 @@ def run_gpu(args, rank, world, local_rank):
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C2", "m": M, "S": S_C2, "n": N_BASIS, "q": Q, "alpha0": [2.0, 6.5],
-                       "problems_per_rank": K, "concurrent_fits": K,
+                       "problems_per_rank": K, "concurrent_fits": K, "rank_ms": rank_ms,
                        "l2_policy": "K distinct 33.5 MB problems are fitted concurrently: K*33.5 MB of inputs are streamed "
                                     "per evaluation round (larger than the 126 MB L2 for K >= 4)",
                        "evals_per_fit_mean": float(np.mean(nfev)), "fit_mode": os.environ.get("VP_FIT_MODE", "persistent")},

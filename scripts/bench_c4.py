@@ -1,0 +1,39 @@
+"""BASELINE config 4 on the GPU: weighted multi-exponential (the reference's lmfit asset shape), m = 1000,
+S = 16 384 right-hand sides, fp32 with fp64 accumulation, global fit + per-column statistics
+(fit_with_statistics). Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import workloads as W  # noqa: E402
+import varpro_b200 as vb  # noqa: E402
+
+dtype = np.float32 if (len(sys.argv) < 2 or sys.argv[1] == "f32") else np.float64
+wl = W.c4(dtype=dtype)
+solver = vb.LevMarSolver.default()
+gp = W.make_gpu_problem(wl, dtype=dtype)
+res = solver.fit(gp)
+t_fit, t_stat = [], []
+for _ in range(5):
+    gp.set_params(wl["alpha0"])
+    t0 = time.perf_counter()
+    res = solver.fit(gp)
+    t_fit.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    st = gp.statistics(confidence_sigma=False)
+    t_stat.append(time.perf_counter() - t0)
+nfev = res.minimization_report.number_of_evaluations
+es = np.dtype(dtype).itemsize
+print(json.dumps({"workload": "C4: weighted multiexp, global fit + statistics", "dtype": np.dtype(dtype).name, "m": 1000, "S": 16384,
+                  "ms_per_fit": 1e3 * min(t_fit), "fits_per_s": 1.0 / min(t_fit), "evaluations": nfev,
+                  "us_per_evaluation": 1e6 * min(t_fit) / max(nfev - 1, 1),
+                  "GBps_in_fit": es * 1000 * 16384 * max(nfev - 1, 1) / min(t_fit) / 1e9,
+                  "ms_statistics_all_columns": 1e3 * min(t_stat),
+                  "alpha": res.nonlinear_parameters().tolist(),
+                  "chi2_red_col0": st[0].reduced_chi2(), "cov_diag_col0": np.diag(st[0].covariance_matrix()).tolist()}))

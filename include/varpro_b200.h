@@ -209,6 +209,11 @@ int vp_jacobian(vp_problem *problem, void *out_host);
 int vp_linear_coefficients(vp_problem *problem, void *out_host);
 /* FitResult::best_fit (src/fit.rs:55-59): Phi(alpha)*C with the unweighted Phi, m x S */
 int vp_best_fit(vp_problem *problem, void *out_host);
+/* The same three outputs written into a caller-owned DEVICE buffer of the same layout (SURVEY.md
+ * 8f row 3): one write-bound streaming kernel, no device-to-host copy. */
+int vp_residuals_device(vp_problem *problem, void *out_device);
+int vp_jacobian_device(vp_problem *problem, void *out_device);
+int vp_best_fit_device(vp_problem *problem, void *out_device);
 /* ||r||^2, J^T r and J^T J of the current parameters without materialising r or J */
 int vp_reduce(vp_problem *problem, vp_reduced *out);
 

@@ -540,3 +540,22 @@ def test_host_evaluated_model_statistics_and_errors():
     with pytest.raises(vb.ModelBuildError):
         (vb.SeparableModelBuilder(["tau"]).function(["tau"], lambda x, tau: np.exp(-x / tau))
          .independent_variable(wl["x"]).initial_parameters([1.0]).build())
+
+
+def test_device_resident_materialisers_match_host_copies():
+    """vp_residuals_device / vp_jacobian_device / vp_best_fit_device write into a caller-owned device buffer."""
+    import ctypes as C
+    import torch
+    from varpro_b200 import _lib
+    wl = W.c2(S=72)
+    gp = W.make_gpu_problem(wl)
+    gp.set_params([1.4, 3.3])
+    m, S, q = 1024, 72, 2
+    lib = _lib.load()
+    for fn, host, count in ((lib.vp_residuals_device, gp.residuals(), m * S),
+                            (lib.vp_jacobian_device, gp.jacobian().ravel(order="F"), m * S * q),
+                            (lib.vp_best_fit_device, gp.best_fit().ravel(order="F"), m * S)):
+        buf = torch.empty(count, dtype=torch.float64, device="cuda")
+        assert fn(gp._h, C.c_void_p(buf.data_ptr())) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(buf.cpu().numpy(), np.asarray(host).ravel(order="F"))

@@ -166,6 +166,7 @@ __global__ void statistics_kernel(ModelDesc md, const T *__restrict__ Y, int ld,
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int m = md.m, n = md.n, p = md.p, q = md.q, t = n + q, t0 = n + p;
     __shared__ double cov_s[8][STATS_MAX_T * STATS_MAX_T];
+    __shared__ double a_s[8][STATS_MAX_T * STATS_MAX_T];
     double *cv = cov_s[wib];
     for (int s = blockIdx.x * wpb + wib; s < S; s += gridDim.x * wpb) {
         // ||r_s||^2 with r_s = y_s - Q (Q^T y_s)
@@ -194,58 +195,69 @@ __global__ void statistics_kernel(ModelDesc md, const T *__restrict__ Y, int ld,
         double c[VP_MAX_N];
 #pragma unroll
         for (int j = 0; j < VP_MAX_N; ++j) c[j] = j < n ? (double)C[(size_t)s * n + j] : 0.0;
-        int bad = 0;
-        if (lane == 0) {
-            // H^T H, ordering (c..., alpha...) (src/statistics/mod.rs:66-76)
-            double A[STATS_MAX_T * STATS_MAX_T];
-            for (int a = 0; a < t; ++a)
-                for (int bb = 0; bb < t; ++bb) {
-                    double v = 0.0;
-                    if (a < n && bb < n) v = Gm[bb * t0 + a];
-                    else if (a < n) {
-                        for (int e = 0; e < p; ++e)
-                            if (md.e_param[e] == bb - n) v += Gm[(n + e) * t0 + a] * c[md.e_basis[e]];
-                    } else if (bb < n) {
-                        for (int e = 0; e < p; ++e)
-                            if (md.e_param[e] == a - n) v += Gm[(n + e) * t0 + bb] * c[md.e_basis[e]];
-                    } else {
-                        for (int e = 0; e < p; ++e) {
-                            if (md.e_param[e] != a - n) continue;
-                            for (int f = 0; f < p; ++f)
-                                if (md.e_param[f] == bb - n) v += Gm[(n + f) * t0 + (n + e)] * c[md.e_basis[e]] * c[md.e_basis[f]];
-                        }
-                    }
-                    A[bb * t + a] = v;
+        // H^T H, ordering (c..., alpha...) (src/statistics/mod.rs:66-76): assembled and inverted by the
+        // warp in shared memory (Gauss-Jordan with partial pivoting; nalgebra try_inverse is LU, :397-399)
+        double *A = a_s[wib], *Inv = cv;
+        for (int idx = lane; idx < t * t; idx += 32) {
+            const int a = idx % t, bb = idx / t;
+            double v = 0.0;
+            if (a < n && bb < n) v = Gm[bb * t0 + a];
+            else if (a < n) {
+                for (int e = 0; e < p; ++e)
+                    if (md.e_param[e] == bb - n) v += Gm[(n + e) * t0 + a] * c[md.e_basis[e]];
+            } else if (bb < n) {
+                for (int e = 0; e < p; ++e)
+                    if (md.e_param[e] == a - n) v += Gm[(n + e) * t0 + bb] * c[md.e_basis[e]];
+            } else {
+                for (int e = 0; e < p; ++e) {
+                    if (md.e_param[e] != a - n) continue;
+                    for (int f = 0; f < p; ++f)
+                        if (md.e_param[f] == bb - n) v += Gm[(n + f) * t0 + (n + e)] * c[md.e_basis[e]] * c[md.e_basis[f]];
                 }
-            // inverse by Gauss-Jordan with partial pivoting (nalgebra try_inverse: LU, :397-399)
-            double Inv[STATS_MAX_T * STATS_MAX_T];
-            for (int i = 0; i < t * t; ++i) Inv[i] = 0.0;
-            for (int i = 0; i < t; ++i) Inv[i * t + i] = 1.0;
-            for (int col = 0; col < t && !bad; ++col) {
-                int piv = col;
-                for (int r = col + 1; r < t; ++r)
-                    if (fabs(A[col * t + r]) > fabs(A[col * t + piv])) piv = r;
-                const double d = A[col * t + piv];
-                if (!(fabs(d) > 0.0) || !isfinite(d)) { bad = 1; break; }
-                if (piv != col)
-                    for (int k = 0; k < t; ++k) {
-                        double tmp = A[k * t + col]; A[k * t + col] = A[k * t + piv]; A[k * t + piv] = tmp;
-                        tmp = Inv[k * t + col]; Inv[k * t + col] = Inv[k * t + piv]; Inv[k * t + piv] = tmp;
-                    }
+            }
+            A[bb * t + a] = v;
+            Inv[idx] = (a == bb) ? 1.0 : 0.0;
+        }
+        __syncwarp();
+        int bad = 0;
+        for (int col = 0; col < t; ++col) {
+            int piv = col;
+            for (int r = col + 1; r < t; ++r)
+                if (fabs(A[col * t + r]) > fabs(A[col * t + piv])) piv = r;
+            const double d = A[col * t + piv];
+            if (!(fabs(d) > 0.0) || !isfinite(d)) { bad = 1; break; } // uniform across the warp
+            __syncwarp();
+            if (lane < t) { // lane = matrix column k
+                const int k = lane;
+                if (piv != col) {
+                    double tmp = A[k * t + col]; A[k * t + col] = A[k * t + piv]; A[k * t + piv] = tmp;
+                    tmp = Inv[k * t + col]; Inv[k * t + col] = Inv[k * t + piv]; Inv[k * t + piv] = tmp;
+                }
                 const double inv_d = 1.0 / d;
-                for (int k = 0; k < t; ++k) { A[k * t + col] *= inv_d; Inv[k * t + col] *= inv_d; }
+                const double ak = A[k * t + col] * inv_d, ik = Inv[k * t + col] * inv_d;
+                A[k * t + col] = ak; Inv[k * t + col] = ik;
+            }
+            __syncwarp();
+            double fr[STATS_MAX_T];
+            for (int r = 0; r < t; ++r) fr[r] = A[col * t + r]; // multipliers, read before they are cleared
+            __syncwarp();
+            if (lane < t) {
+                const int k = lane;
+                const double ak = A[k * t + col], ik = Inv[k * t + col];
                 for (int r = 0; r < t; ++r) {
                     if (r == col) continue;
-                    const double f = A[col * t + r];
-                    if (f == 0.0) continue;
-                    for (int k = 0; k < t; ++k) { A[k * t + r] -= f * A[k * t + col]; Inv[k * t + r] -= f * Inv[k * t + col]; }
+                    A[k * t + r] -= fr[r] * ak;
+                    Inv[k * t + r] -= fr[r] * ik;
                 }
             }
-            for (int i = 0; i < t * t; ++i) {
-                const double v = bad ? nan("") : chi * Inv[i];
-                cv[i] = v;
-                cov[(size_t)s * t * t + i] = v;
-            }
+            __syncwarp();
+        }
+        for (int idx = lane; idx < t * t; idx += 32) {
+            const double v = bad ? nan("") : chi * Inv[idx];
+            Inv[idx] = v;
+            cov[(size_t)s * t * t + idx] = v;
+        }
+        if (lane == 0) {
             chi2[s] = chi;
             if (bad) atomicExch(fail_flag, 1);
         }

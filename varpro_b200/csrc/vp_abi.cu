@@ -992,7 +992,7 @@ static int ensure_panel_current(vp_problem *pr)
 }
 
 template <typename T>
-static int materialise_t(vp_problem *pr, int what, void *out_host)
+static int materialise_t(vp_problem *pr, int what, void *out_host, void *out_device = nullptr)
 {
     vp_ctx *ctx = pr->ctx;
     vp_model *mo = pr->model;
@@ -1000,8 +1000,8 @@ static int materialise_t(vp_problem *pr, int what, void *out_host)
     const size_t mS = (size_t)md.m * pr->S;
     const size_t count = what == 1 ? mS * md.q : mS;
     if (count == 0) return VP_OK;
-    T *buf = nullptr;
-    VP_CUDA(ctx, DEV_ALLOC(ctx, &buf, sizeof(T) * count));
+    T *buf = static_cast<T *>(out_device); // device-resident output requested: write it in place, no copy
+    if (!buf) VP_CUDA(ctx, DEV_ALLOC(ctx, &buf, sizeof(T) * count));
     const int blocks = ctx->sm_count * 8;
     if (what == 0) {
         residuals_kernel<T><<<blocks, 256, 0, ctx->stream>>>((const T *)pr->Yw, mo->ld, pr->ldp, md.m, (int)pr->S, md.n,
@@ -1021,26 +1021,31 @@ static int materialise_t(vp_problem *pr, int what, void *out_host)
     }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, buf, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && !out_device) e = cudaMemcpyAsync(out_host, buf, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    DEV_FREE(ctx, buf);
+    if (!out_device) DEV_FREE(ctx, buf);
     if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, std::string("materialise: ") + cudaGetErrorString(e));
     return VP_OK;
 }
 
-static int materialise(vp_problem *pr, int what, void *out_host)
+static int materialise(vp_problem *pr, int what, void *out_host, void *out_device = nullptr)
 {
-    if (!pr || !out_host) return VP_ERR_INVALID_ARGUMENT;
+    if (!pr || (!out_host && !out_device)) return VP_ERR_INVALID_ARGUMENT;
     if (!pr->cached) return fail(pr->ctx, VP_ERR_NO_CACHED_CALCULATION, vp_status_string(VP_ERR_NO_CACHED_CALCULATION));
     cudaSetDevice(pr->ctx->device);
     int rc = ensure_panel_current(pr);
     if (rc != VP_OK) return rc;
-    return pr->model->dtype == VP_F32 ? materialise_t<float>(pr, what, out_host) : materialise_t<double>(pr, what, out_host);
+    return pr->model->dtype == VP_F32 ? materialise_t<float>(pr, what, out_host, out_device)
+                                      : materialise_t<double>(pr, what, out_host, out_device);
 }
 
 extern "C" int vp_residuals(vp_problem *pr, void *out_host) { return materialise(pr, 0, out_host); }
 extern "C" int vp_jacobian(vp_problem *pr, void *out_host) { return materialise(pr, 1, out_host); }
 extern "C" int vp_best_fit(vp_problem *pr, void *out_host) { return materialise(pr, 2, out_host); }
+// the same three, written straight into a caller-owned DEVICE buffer (no host copy)
+extern "C" int vp_residuals_device(vp_problem *pr, void *out_device) { return materialise(pr, 0, nullptr, out_device); }
+extern "C" int vp_jacobian_device(vp_problem *pr, void *out_device) { return materialise(pr, 1, nullptr, out_device); }
+extern "C" int vp_best_fit_device(vp_problem *pr, void *out_device) { return materialise(pr, 2, nullptr, out_device); }
 
 extern "C" int vp_linear_coefficients(vp_problem *pr, void *out_host)
 {

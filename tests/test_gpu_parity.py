@@ -559,3 +559,18 @@ def test_device_resident_materialisers_match_host_copies():
         assert fn(gp._h, C.c_void_p(buf.data_ptr())) == 0
         torch.cuda.synchronize()
         assert np.array_equal(buf.cpu().numpy(), np.asarray(host).ravel(order="F"))
+
+
+def test_fp32_problems_share_the_work_queue_kernel():
+    """fp32 problems in vp_fit_many: streamed as fp32, all arithmetic in fp64 (work-queue kernel)."""
+    import varpro_b200 as vb
+    solver = vb.LevMarSolver.default()
+    wls = [W.c4(S=40 + 8 * k, seed=50 + k) for k in range(4)]
+    many = solver.fit_many([W.make_gpu_problem(wl, dtype=np.float32) for wl in wls])
+    for wl, r in zip(wls, many):
+        assert r.was_successful()
+        wl64 = dict(wl, x=wl["x"].astype(np.float64), Y=np.asfortranarray(wl["Y"].astype(np.float64)),
+                    weights=wl["weights"].astype(np.float64))
+        op = W.make_oracle(wl64)
+        assert op.fit()["successful"]
+        assert np.max(np.abs(r.nonlinear_parameters() - op.params()) / np.abs(op.params())) <= F32_PARAM_REL

@@ -32,10 +32,10 @@ namespace vp {
 
 struct QueueFit {
     ModelDesc md;
-    const double *Y;  // ld x S weighted observations
-    double *C0, *C1;  // coefficient buffers
-    const double *x, *w;
-    double *Pq;       // panel [Q | E | 0] in HBM: (n+p+1) columns of ldp rows (ldp >= the kernel's row tiling)
+    const void *Y;    // ld x S weighted observations in the problem dtype TY
+    void *C0, *C1;    // coefficient buffers (TY)
+    const void *x, *w; // TY
+    double *Pq;       // panel [Q | E | 0] in HBM, ALWAYS f64: (n+p+1) columns of ldp rows (ldp >= the kernel's row tiling)
     PanelSmall *small;
     double *partials; // nchunks rows of red_stride doubles
     unsigned int *ticket;
@@ -80,7 +80,12 @@ __device__ __forceinline__ int ld_acquire_gpu_s32(const int *p)
     return v;
 }
 
-template <int N, int P, int KSTEPS, int NWARPS, bool EXACT>
+// TY: element type of the observations / coefficients in HBM (double or float). All arithmetic is
+// fp64 either way: fp32 problems (BASELINE config 4) stream half the bytes and are converted when
+// the tile fragments are loaded, so they are MORE accurate than an fp32 reference and share every
+// other piece of the machinery. lds (column stride of a tile slot, in elements) = 4 (mod 16) for
+// double, 8 (mod 32) for float: both fragment access patterns are then bank-conflict free.
+template <typename TY, int N, int P, int KSTEPS, int NWARPS, bool EXACT>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, const int nst)
 {
@@ -107,12 +112,14 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     __shared__ double red[2][NWARPS * KMAX];
     __shared__ double top[N][NPV];
     __shared__ double alpha_s[VP_MAX_Q];
-    __shared__ int is_last, item_fit, item_chunk, more_s;
+    __shared__ int is_last, item_fit, item_chunk, more_s, push_n;
+    __shared__ unsigned long long push_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = lane >> 2, tig = lane & 3;
     const size_t stage_elems = (size_t)CT * lds;
-    double *tiles = reinterpret_cast<double *>(smem_raw);
+    TY *tiles = reinterpret_cast<TY *>(smem_raw);
+    double *staging = reinterpret_cast<double *>(smem_raw); // panel staging (f64, stride lds): fits in the ring for nst >= 2
 
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) mbar_init(&full_bar[s], 1);
@@ -134,43 +141,61 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         for (int r = 0; r < RPT; ++r) {
             const int i = tid + r * THREADS;
             const bool in = i < md.m;
-            xi[r] = in ? qf->x[i] : 0.0;
-            wi[r] = in ? (qf->w ? qf->w[i] : 1.0) : 0.0;
+            xi[r] = in ? (double)static_cast<const TY *>(qf->x)[i] : 0.0;
+            wi[r] = in ? (qf->w ? (double)static_cast<const TY *>(qf->w)[i] : 1.0) : 0.0;
         }
         // the staging rows [ld, lds) of stage 0 may hold zeros only by construction of the evaluator
         __syncthreads();
         {
             double pa[RPT][NPV], pd0[RPT][P > 0 ? P : 1];
-            const int bad = panel_eval_staged<N, P, RPT, THREADS>(md, xi, wi, alpha_s, tiles, lds, pa, pd0);
+            const int bad = panel_eval_staged<N, P, RPT, THREADS>(md, xi, wi, alpha_s, staging, lds, pa, pd0);
             panel_hh_factor<double, N, P, RPT, THREADS>(md, pa, pd0, bad, alpha_s, qf->svd_eps, qf->ldp, qf->Pq, qf->small, red, top,
                                                         nullptr);
         }
-        fence_proxy_async_smem(); // generic writes to stage 0 before later bulk copies into it
+        if (sizeof(TY) != sizeof(double)) {
+            // the f64 staging overlaid the float slots: restore the zero pad rows [ld, lds) of every slot
+            __syncthreads();
+            const int ld0 = qf->ld;
+            for (int slot = tid; slot < nst * CT; slot += THREADS)
+                for (int r = ld0; r < lds; ++r) tiles[(size_t)slot * lds + r] = (TY)0;
+        }
+        fence_proxy_async_smem(); // generic writes to the staging area before later bulk copies into it
         __threadfence();
         __syncthreads();
         if (tid == 0) {
             const int cdst = __ldcg(&qf->fit->cur) ^ 1;
             qf->cdst = cdst;
-            __threadfence();
             // chunk size of this evaluation: about four items per CTA over the fits still running, so
             // that the last few fits are spread over the whole grid too
             int active = ld_acquire_gpu_s32(&ctl->fits_left);
             if (active < 1) active = 1;
-            const int target = (4 * (int)gridDim.x + active - 1) / active;
+            // many fits: ~4 items per CTA per round (balance); few fits: larger items (less per-item overhead)
+            const int per_cta = active >= 8 ? 4 : (active >= 3 ? 2 : 1);
+            const int target = (per_cta * (int)gridDim.x + active - 1) / active;
             int ct = (qf->ntiles + target - 1) / target;
             if (ct < qf->min_chunk_tiles) ct = qf->min_chunk_tiles;
             while ((qf->ntiles + ct - 1) / ct > qf->max_chunks) ct *= 2;
             const int nch = (qf->ntiles + ct - 1) / ct;
             qf->chunk_tiles = ct;
             qf->nchunks = nch;
-            __threadfence();
-            const unsigned long long base = atomicAdd(&ctl->tail, (unsigned long long)nch);
-            for (int j = 0; j < nch; ++j) {
+            push_n = nch;
+            push_base = atomicAdd(&ctl->tail, (unsigned long long)nch);
+        }
+        __syncthreads();
+        // publish the items: all threads fill slots, one fence, then the sequence flags (a slot is
+        // valid once its flag holds item index + 1; consumers read it with ld.acquire)
+        {
+            const int nch = push_n;
+            const unsigned long long base = push_base;
+            for (int j = tid; j < nch; j += THREADS) {
                 QueueItem *it = &ctl->items[(base + j) % ctl->cap];
                 it->fit = k;
                 it->chunk = j;
-                st_release_gpu_u64(&it->seq, base + j + 1ull);
             }
+            __threadfence();
+            __syncthreads();
+            for (int j = tid; j < nch; j += THREADS)
+                st_release_gpu_u64(&ctl->items[(base + j) % ctl->cap].seq, base + j + 1ull);
         }
         __syncthreads();
     };
@@ -181,7 +206,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         const int ld0 = fits[0].ld;
         if (lds > ld0)
             for (int slot = tid; slot < nst * CT; slot += THREADS)
-                for (int r = ld0; r < lds; ++r) tiles[(size_t)slot * lds + r] = 0.0;
+                for (int r = ld0; r < lds; ++r) tiles[(size_t)slot * lds + r] = (TY)0;
         __syncthreads();
     }
 
@@ -208,26 +233,26 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         if (k < 0) break;
         QueueFit *qf = &fits[k];
         const int ld = qf->ld, S = qf->S, ldp = qf->ldp;
-        const double *Yk = qf->Y;
+        const TY *Yk = static_cast<const TY *>(qf->Y);
         const int chunk_tiles = __ldcg(&qf->chunk_tiles), nchunks = __ldcg(&qf->nchunks);
         const int t_begin = chunk * chunk_tiles;
         const int t_end = min(qf->ntiles, t_begin + chunk_tiles);
         const int my = t_end - t_begin;
-        double *Cout = __ldcg(&qf->cdst) ? qf->C1 : qf->C0;
+        TY *Cout = static_cast<TY *>(__ldcg(&qf->cdst) ? qf->C1 : qf->C0);
         int ebasis[P > 0 ? P : 1];
 #pragma unroll
         for (int e2 = 0; e2 < P; ++e2) ebasis[e2] = qf->md.e_basis[e2];
 
         // ---- TMA producer for this chunk ------------------------------------------------------------
         int next_i = 0, next_st = 0;
-        const uint32_t col_bytes = (uint32_t)(ld * sizeof(double));
+        const uint32_t col_bytes = (uint32_t)(ld * sizeof(TY));
         auto issue = [&]() {
             const int col0 = (t_begin + next_i) * CT;
             const int nc = min(CT, S - col0);
             if (lane == 0) {
                 if (warp == 0) mbar_arrive_expect_tx(&full_bar[next_st], col_bytes * nc);
-                double *dst = tiles + (size_t)next_st * stage_elems;
-                const double *src = Yk + (size_t)col0 * ld;
+                TY *dst = tiles + (size_t)next_st * stage_elems;
+                const TY *src = Yk + (size_t)col0 * ld;
 #pragma unroll 1
                 for (int c = warp; c < nc; c += NWARPS)
                     bulk_copy_g2s(dst + (size_t)c * lds, src + (size_t)c * ld, col_bytes, &full_bar[next_st]);
@@ -271,7 +296,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         for (int i = 0; i < my; ++i) {
             const int col0 = (t_begin + i) * CT;
             const int nc = min(CT, S - col0);
-            const double *tp = tiles + (size_t)st * stage_elems;
+            const TY *tp = tiles + (size_t)st * stage_elems;
             mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
             phase_bits ^= 1u << st;
             if (++st == nst) st = 0;
@@ -279,12 +304,12 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
                 double c[4][2];
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) c[ch][0] = c[ch][1] = 0.0;
-                const double *bp = tp + (size_t)grp * lds + 4 * (warp * KSTEPS) + tig;
+                const TY *bp = tp + (size_t)grp * lds + 4 * (warp * KSTEPS) + tig;
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                     double b;
-                    if (EXACT) b = bp[4 * ks];
-                    else b = (4 * (warp * KSTEPS + ks) + tig < lds) ? bp[4 * ks] : 0.0;
+                    if (EXACT) b = (double)bp[4 * ks];
+                    else b = (4 * (warp * KSTEPS + ks) + tig < lds) ? (double)bp[4 * ks] : 0.0;
                     dmma_8x8x4(c[ks & 3][0], c[ks & 3][1], a1[ks], b);
                 }
                 const double s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
@@ -308,7 +333,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
 #pragma unroll
                     for (int c2 = r; c2 < N; ++c2) s += rinv_s[c2 * N + r] * bu[c2 * 8 + tid];
                     coef[r] = s;
-                    Cout[(size_t)(col0 + tid) * N + r] = s;
+                    Cout[(size_t)(col0 + tid) * N + r] = (TY)s;
                 }
                 int gi = 0;
 #pragma unroll
@@ -325,17 +350,17 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             }
             {
                 const double b2 = (tig < N) ? -bu[tig * 8 + pcol_b] : 0.0;
-                const double *cp0 = tp + (size_t)pcol_c0 * lds + 8 * (warp * RSTEPS) + grp;
-                const double *cp1 = tp + (size_t)pcol_c1 * lds + 8 * (warp * RSTEPS) + grp;
+                const TY *cp0 = tp + (size_t)pcol_c0 * lds + 8 * (warp * RSTEPS) + grp;
+                const TY *cp1 = tp + (size_t)pcol_c1 * lds + 8 * (warp * RSTEPS) + grp;
                 double q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int rs = 0; rs < RSTEPS; ++rs) {
                     double d0, d1;
-                    if (EXACT) { d0 = cp0[8 * rs]; d1 = cp1[8 * rs]; }
+                    if (EXACT) { d0 = (double)cp0[8 * rs]; d1 = (double)cp1[8 * rs]; }
                     else {
                         const bool ok = 8 * (warp * RSTEPS + rs) + grp < lds;
-                        d0 = ok ? cp0[8 * rs] : 0.0;
-                        d1 = ok ? cp1[8 * rs] : 0.0;
+                        d0 = ok ? (double)cp0[8 * rs] : 0.0;
+                        d1 = ok ? (double)cp1[8 * rs] : 0.0;
                     }
                     dmma_8x8x4(d0, d1, a2[rs], b2);
                     q0 = fma(d0, d0, q0);

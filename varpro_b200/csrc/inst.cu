@@ -38,7 +38,7 @@ static const FitKernelEntry fit_tab[] = {VP_FK(32, 16, 0)};
 #endif
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, fit_tab, (int)(sizeof(fit_tab) / sizeof(fit_tab[0]))};
 #elif VP_INST_PART == 5
-#define VP_QK(KS, NW, EX) {N_, P_, KS, NW, EX, (const void *)&fit_queue_kernel<N_, P_, KS, NW, (EX) != 0>}
+#define VP_QK(KS, NW, EX) {VP_INST_DT, N_, P_, KS, NW, EX, (const void *)&fit_queue_kernel<T_, N_, P_, KS, NW, (EX) != 0>}
 #if VP_INST_VARIANT == 0
 static const QueueKernelEntry queue_tab[] = {VP_QK(8, 4, 0), VP_QK(16, 8, 0)};
 #elif VP_INST_VARIANT == 1

@@ -23,7 +23,7 @@ struct FitKernelEntry { // fit_kernel_dmma: fused panel + streaming reduce (+ wh
     const void *fn;
 };
 struct QueueKernelEntry { // fit_queue_kernel: many fits on one persistent grid with a device-side work queue
-    int n, p, ksteps, nwarps, exact;
+    int dtype, n, p, ksteps, nwarps, exact;
     const void *fn;
 };
 struct BatchKernelEntry { // batch_fit_kernel: one CTA fits `slots` independent problems at a time
@@ -56,6 +56,9 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_3_2_queue2, double, VP_F64, 3, 2, 5) \
     X(f32_3_2_simt, float, VP_F32, 3, 2, 0)  /* the same in fp32 (C4) */ \
     X(f32_3_2_panel, float, VP_F32, 3, 2, 2) \
+    X(f32_3_2_queue0, float, VP_F32, 3, 2, 5) \
+    X(f32_3_2_queue1, float, VP_F32, 3, 2, 5) \
+    X(f32_3_2_queue2, float, VP_F32, 3, 2, 5) \
     X(f64_3_3_simt, double, VP_F64, 3, 3, 0) /* triple exponential (C3 shape) */ \
     X(f64_3_3_dmma, double, VP_F64, 3, 3, 1) \
     X(f64_3_3_panel, double, VP_F64, 3, 3, 2) \

@@ -174,6 +174,8 @@ struct vp_problem {
     int fit_grid = 0, fit_nst = 0;
     size_t fit_smem = 0;
     FitBcast *bcast = nullptr;
+    double *Pq64 = nullptr; // f64 panel buffer used by the work-queue kernel for fp32 problems (lazily allocated)
+    int ldp64 = 0;
 };
 
 static int env_int(const char *name, int dflt)
@@ -928,6 +930,7 @@ extern "C" int vp_problem_destroy(vp_problem *pr)
     DEV_FREE(ctx, pr->Yw); DEV_FREE(ctx, pr->w_dev); DEV_FREE(ctx, pr->Pq); DEV_FREE(ctx, pr->small);
     DEV_FREE(ctx, pr->C[0]); DEV_FREE(ctx, pr->C[1]); DEV_FREE(ctx, pr->partials); DEV_FREE(ctx, pr->ticket);
     DEV_FREE(ctx, pr->out_dev); DEV_FREE(ctx, pr->fit_dev); DEV_FREE(ctx, pr->phi_scratch); DEV_FREE(ctx, pr->bcast);
+    DEV_FREE(ctx, pr->Pq64);
     cudaFree(pr->dbg);
     if (pr->fit_exec) cudaGraphExecDestroy(pr->fit_exec);
     if (pr->fit_graph) cudaGraphDestroy(pr->fit_graph);
@@ -1189,6 +1192,10 @@ static int ensure_fit_graph(vp_problem *pr)
 // ----------------------------------------------------------------------------
 // LevMarSolver::fit  (src/solvers/levmar/mod.rs:238-254)
 // ----------------------------------------------------------------------------
+static int queue_kernel_for(const vp_problem *pr, int *lds_out);
+static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, std::vector<LmState> &states,
+                           const std::vector<LmConfig> &cfgs);
+
 static void lm_config_from_options(const vp_problem *pr, const vp_lm_options *opt, LmConfig &cfg)
 {
     const int q = pr->model->md.q;
@@ -1287,6 +1294,21 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
         more = false;
     }
     if (more && pr->comm) return fail(pr->ctx, VP_ERR_COMM, "column-sharded fits run on the persistent fit kernel only");
+    if (more && pr->plan_fit < 0 && !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph"))) &&
+        queue_kernel_for(pr, nullptr) >= 0) {
+        // ---- fp32 problems: the work-queue kernel with a single fit (panel once per evaluation, fp64 math) ---
+        cudaSetDevice(pr->ctx->device);
+        std::vector<vp_problem *> prs{pr};
+        std::vector<LmState> sts{st};
+        std::vector<LmConfig> cfs{cfg};
+        int rc = fit_queue_group(pr->ctx, prs, sts, cfs);
+        if (rc == VP_OK) {
+            st = sts[0];
+            more = false;
+        } else if (rc != VP_ERR_UNSUPPORTED_BASIS) {
+            return rc;
+        }
+    }
     if (more && !(mode && !strcmp(mode, "host")) && !pr->model->hosteval) {
         // ---- device-driven loop: one CUDA graph launch per fit ------------------------
         vp_ctx *ctx = pr->ctx;
@@ -1337,6 +1359,30 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
     return VP_OK;
 }
 
+// The work-queue kernel instantiation a problem can use (index into g_queue_kernels, -1 = none) and the
+// padded tile-column stride (elements) that goes with it.
+static int queue_kernel_for(const vp_problem *pr, int *lds_out)
+{
+    const vp_model *mo = pr->model;
+    if (mo->hosteval || pr->comm || !pr->cached) return -1;
+    const ModelDesc &md = mo->md;
+    int lds = mo->ld;
+    if (mo->dtype == VP_F64) { while (lds % 16 != 4) lds += 2; }
+    else { while (lds % 32 != 8) lds += 4; }
+    int pick = -1;
+    for (size_t i = 0; i < g_queue_kernels.size(); ++i) {
+        const QueueKernelEntry &k = g_queue_kernels[i];
+        if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p) continue;
+        const int rows = 4 * k.ksteps * k.nwarps;
+        if (rows < mo->ld) continue;
+        if (k.exact && rows > lds) continue;
+        const int prow = pick < 0 ? 0 : 4 * g_queue_kernels[pick].ksteps * g_queue_kernels[pick].nwarps;
+        if (pick < 0 || rows < prow || (rows == prow && k.exact && !g_queue_kernels[pick].exact)) pick = (int)i;
+    }
+    if (lds_out) *lds_out = lds;
+    return pick;
+}
+
 // One launch of fit_queue_kernel for a group of problems that share the kernel instantiation and the
 // padded row count. states[i] has been advanced past the cached evaluation at the starting point.
 // Returns VP_OK after the fits completed and their final states were adopted.
@@ -1345,13 +1391,13 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
 {
     const int K = (int)prs.size();
     vp_problem *p0 = prs[0];
-    const FitKernelEntry &fk = g_fit_kernels[p0->plan_fit];
-    const QueueKernelEntry *qk = nullptr;
-    for (const QueueKernelEntry &k : g_queue_kernels)
-        if (k.n == fk.n && k.p == fk.p && k.ksteps == fk.ksteps && k.nwarps == fk.nwarps && k.exact == fk.exact) qk = &k;
-    if (!qk) return VP_ERR_UNSUPPORTED_BASIS; // caller falls back to the per-fit kernels
-    const int lds = p0->plan_lds;
-    const size_t stage_bytes = (size_t)DMMA_CT * lds * sizeof(double);
+    int lds = 0;
+    const int qidx = queue_kernel_for(p0, &lds);
+    if (qidx < 0) return VP_ERR_UNSUPPORTED_BASIS; // caller falls back to the per-fit kernels
+    const QueueKernelEntry *qk = &g_queue_kernels[(size_t)qidx];
+    const size_t es = esize(p0->model->dtype);
+    const int prow = 4 * qk->ksteps * qk->nwarps;
+    const size_t stage_bytes = (size_t)DMMA_CT * lds * es;
     cudaFuncAttributes fa{};
     VP_CUDA(ctx, cudaFuncGetAttributes(&fa, qk->fn));
     if (fa.sharedSizeBytes + 1024 + 2 * stage_bytes > 227 * 1024) return VP_ERR_UNSUPPORTED_BASIS;
@@ -1372,11 +1418,24 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         QueueFit &f = hq[(size_t)i];
         memset(&f, 0, sizeof(f));
         f.md = md;
-        f.Y = (const double *)pr->Yw; f.C0 = (double *)pr->C[0]; f.C1 = (double *)pr->C[1];
-        f.x = (const double *)pr->model->x_dev; f.w = (const double *)pr->w_dev;
-        f.Pq = (double *)pr->Pq; f.small = pr->small; f.partials = pr->partials; f.ticket = pr->ticket;
+        f.Y = pr->Yw; f.C0 = pr->C[0]; f.C1 = pr->C[1];
+        f.x = pr->model->x_dev; f.w = pr->w_dev;
+        // the kernel's panel buffer is f64 with at least `prow` zero-padded rows per column
+        if (pr->model->dtype == VP_F64 && pr->ldp >= prow) {
+            f.Pq = (double *)pr->Pq; f.ldp = pr->ldp;
+        } else {
+            const int ldp64 = ((prow > lds ? prow : lds) + 3) / 4 * 4;
+            if (!pr->Pq64 || pr->ldp64 < ldp64) {
+                DEV_FREE(ctx, pr->Pq64);
+                pr->Pq64 = nullptr;
+                VP_CUDA(ctx, DEV_ALLOC(ctx, &pr->Pq64, sizeof(double) * (size_t)ldp64 * (md.n + md.p + 1)));
+                pr->ldp64 = ldp64;
+            }
+            f.Pq = pr->Pq64; f.ldp = pr->ldp64;
+        }
+        f.small = pr->small; f.partials = pr->partials; f.ticket = pr->ticket;
         f.out = pr->out_dev; f.fit = pr->fit_dev; f.svd_eps = pr->svd_eps;
-        f.ld = pr->model->ld; f.S = (int)pr->S; f.ldp = pr->ldp; f.red_stride = pr->red_stride;
+        f.ld = pr->model->ld; f.S = (int)pr->S; f.red_stride = pr->red_stride;
         f.ntiles = (int)((pr->S + DMMA_CT - 1) / DMMA_CT);
         f.min_chunk_tiles = min_chunk < 1 ? 1 : min_chunk;
         f.max_chunks = pr->max_grid; // one partial row per chunk
@@ -1471,7 +1530,7 @@ extern "C" int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options
             memset(&reports[i], 0, sizeof(vp_fit_report));
             lm_config_from_options(pr, opt, all_cfgs[(size_t)i]);
             lm_init(all_states[(size_t)i], pr->model->md.q, pr->alpha);
-            if (!pr->cached || pr->plan_fit < 0 || pr->comm) { any_left = true; continue; }
+            if (queue_kernel_for(pr, nullptr) < 0) { any_left = true; continue; }
             if (!lm_advance(all_states[(size_t)i], all_cfgs[(size_t)i], pr->eval)) { // terminated at the starting point
                 fill_report(all_states[(size_t)i], &reports[i]);
                 done[(size_t)i] = 1;
@@ -1485,14 +1544,16 @@ extern "C" int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options
             // group: same kernel instantiation, same padded rows
             std::vector<int64_t> idx;
             for (int64_t j = i; j < n; ++j)
-                if (done[(size_t)j] == 2 && problems[j]->plan_fit == problems[i]->plan_fit &&
-                    problems[j]->plan_lds == problems[i]->plan_lds && problems[j]->model->ld == problems[i]->model->ld)
+                if (done[(size_t)j] == 2 && queue_kernel_for(problems[j], nullptr) == queue_kernel_for(problems[i], nullptr) &&
+                    problems[j]->model->ld == problems[i]->model->ld)
                     idx.push_back(j);
             std::vector<vp_problem *> prs;
             std::vector<LmState> sts;
             std::vector<LmConfig> cfs;
             for (int64_t j : idx) { prs.push_back(problems[j]); sts.push_back(all_states[(size_t)j]); cfs.push_back(all_cfgs[(size_t)j]); }
-            int rc = idx.size() > 1 ? fit_queue_group(ctx, prs, sts, cfs) : VP_ERR_UNSUPPORTED_BASIS;
+            // a group of one f64 fit is better served by the whole-GPU persistent kernel (vp_fit)
+            const bool use_queue = idx.size() > 1 || problems[i]->plan_fit < 0;
+            int rc = use_queue ? fit_queue_group(ctx, prs, sts, cfs) : VP_ERR_UNSUPPORTED_BASIS;
             for (size_t t = 0; t < idx.size(); ++t) {
                 const int64_t j = idx[t];
                 if (rc == VP_OK) {

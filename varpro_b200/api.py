@@ -562,6 +562,7 @@ class SeparableProblem:
                 for s in range(self._S)]
 
     def model(self) -> SeparableModel:
+        self.model_host._params = self.params()  # the fitted parameters live in the library
         return self.model_host
 
     def weights(self):
@@ -804,12 +805,9 @@ class LevMarSolver:
         reps = (_lib.FitReport * n)()
         _check(_lib.load().vp_fit_many(handles, n, C.byref(self._solver._o), reps, int(max_concurrent)),
                problems[0]._ctx.h)
-        out = []
-        for p, rep in zip(problems, reps):
-            p.model_host._params = p.params()
-            out.append(FitResult(p, MinimizationReport(TerminationReason(rep.termination),
-                                                       rep.number_of_evaluations, rep.objective_function)))
-        return out
+        # (no per-problem calls here: the host-side model parameters are refreshed lazily by model())
+        return [FitResult(p, MinimizationReport(TerminationReason(rep.termination), rep.number_of_evaluations,
+                                                rep.objective_function)) for p, rep in zip(problems, reps)]
 
 
 # ---------------------------------------------------------------------------

@@ -1398,16 +1398,30 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
     const size_t es = esize(p0->model->dtype);
     const int prow = 4 * qk->ksteps * qk->nwarps;
     const size_t stage_bytes = (size_t)DMMA_CT * lds * es;
-    cudaFuncAttributes fa{};
-    VP_CUDA(ctx, cudaFuncGetAttributes(&fa, qk->fn));
-    if (fa.sharedSizeBytes + 1024 + 2 * stage_bytes > 227 * 1024) return VP_ERR_UNSUPPORTED_BASIS;
-    int nst = (int)((227 * 1024 - fa.sharedSizeBytes - 1024) / stage_bytes);
-    if (nst > STREAM_MAX_STAGES) nst = STREAM_MAX_STAGES;
-    const size_t smem = (size_t)nst * stage_bytes;
-    VP_CUDA(ctx, cudaFuncSetAttribute(qk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qk->fn, qk->nwarps * 32, smem));
-    if (occ < 1) return VP_ERR_UNSUPPORTED_BASIS;
+    // launch configuration of (kernel, stage size), cached: the attribute / occupancy queries cost tens of
+    // microseconds each and this function sits inside callers' timed regions
+    struct QueuePlan { const void *fn; size_t stage_bytes; int device; int nst; size_t smem; int occ; };
+    static thread_local std::vector<QueuePlan> plans;
+    const QueuePlan *plan = nullptr;
+    for (const QueuePlan &qp : plans)
+        if (qp.fn == qk->fn && qp.stage_bytes == stage_bytes && qp.device == ctx->device) plan = &qp;
+    if (!plan) {
+        cudaFuncAttributes fa{};
+        VP_CUDA(ctx, cudaFuncGetAttributes(&fa, qk->fn));
+        QueuePlan qp{qk->fn, stage_bytes, ctx->device, 0, 0, 0};
+        if (fa.sharedSizeBytes + 1024 + 2 * stage_bytes <= 227 * 1024) {
+            qp.nst = (int)((227 * 1024 - fa.sharedSizeBytes - 1024) / stage_bytes);
+            if (qp.nst > STREAM_MAX_STAGES) qp.nst = STREAM_MAX_STAGES;
+            qp.smem = (size_t)qp.nst * stage_bytes;
+            VP_CUDA(ctx, cudaFuncSetAttribute(qk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp.smem));
+            VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qp.occ, qk->fn, qk->nwarps * 32, qp.smem));
+        }
+        plans.push_back(qp);
+        plan = &plans.back();
+    }
+    if (plan->occ < 1) return VP_ERR_UNSUPPORTED_BASIS;
+    const int nst = plan->nst, occ = plan->occ;
+    const size_t smem = plan->smem;
 
     const int min_chunk = env_int("VP_QUEUE_MIN_CHUNK", 4); // tiles; the kernel picks the chunk size per evaluation
     std::vector<QueueFit> hq((size_t)K);

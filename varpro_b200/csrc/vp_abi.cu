@@ -1294,8 +1294,9 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
         more = false;
     }
     if (more && pr->comm) return fail(pr->ctx, VP_ERR_COMM, "column-sharded fits run on the persistent fit kernel only");
-    if (more && pr->plan_fit < 0 && !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph"))) &&
-        queue_kernel_for(pr, nullptr) >= 0) {
+    const char *single = getenv("VP_FIT_SINGLE"); // "queue": run single f64 fits on the work-queue kernel too
+    if (more && (pr->plan_fit < 0 || (single && !strcmp(single, "queue"))) &&
+        !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph"))) && queue_kernel_for(pr, nullptr) >= 0) {
         // ---- fp32 problems: the work-queue kernel with a single fit (panel once per evaluation, fp64 math) ---
         cudaSetDevice(pr->ctx->device);
         std::vector<vp_problem *> prs{pr};

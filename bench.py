@@ -62,42 +62,50 @@ def c2_workload(S=S_C2, seed=2314093240213841123 % (2 ** 63)):
 # clocks sampling (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """One long-running `nvidia-smi -lms` child started before the timed regions and stopped after them
+    (the recipe in B200_PROFILING.md): no per-sample fork from this process, whose host thread is
+    inside the timed region."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, enabled=True):
+    def __init__(self, index, enabled=True, period_ms=100):
         self.index = index
         self.enabled = enabled
+        self.period_ms = period_ms
         self.samples = []
         self.reasons = set()
-        self._stop = threading.Event()
-        self._t = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                p = [x.strip() for x in out.strip().split(",")]
-                if len(p) >= 6:
-                    self.samples.append((float(p[0]), float(p[1])))
-                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
-                        if val.lower().startswith("active"):
-                            self.reasons.add(name)
-            except Exception:
-                pass
-            self._stop.wait(0.05)
+        self._p = None
 
     def __enter__(self):
         if self.enabled:
-            self._t = threading.Thread(target=self._run, daemon=True)
-            self._t.start()
+            try:
+                self._p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                            "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self._p = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        if self._t is not None:
-            self._t.join(timeout=6)
+        if self._p is None:
+            return
+        try:
+            self._p.terminate()
+            out, _ = self._p.communicate(timeout=5)
+        except Exception:
+            out = ""
+        for line in out.splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                self.samples.append((float(p[0]), float(p[1])))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if val.lower().startswith("active"):
+                    self.reasons.add(name)
+        self._p = None
 
     def summary(self):
         if not self.samples:

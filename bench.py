@@ -68,7 +68,7 @@ class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, enabled=True, period_ms=100):
+    def __init__(self, index, enabled=True, period_ms=25):
         self.index = index
         self.enabled = enabled
         self.period_ms = period_ms

@@ -574,3 +574,28 @@ def test_fp32_problems_share_the_work_queue_kernel():
         op = W.make_oracle(wl64)
         assert op.fit()["successful"]
         assert np.max(np.abs(r.nonlinear_parameters() - op.params()) / np.abs(op.params())) <= F32_PARAM_REL
+
+
+def test_problems_of_different_sizes_share_kernel_instantiations():
+    """Regression (found by scripts/stress_fit_many.py): the dynamic shared-memory limit of a kernel is a
+    process-wide attribute. A problem that needs less shared memory, created later, must not lower the
+    limit under a problem planned with more (m = 500 and m = 200 use the same instantiation)."""
+    import varpro_b200 as vb
+    rng = np.random.default_rng(3)
+    solver = vb.LevMarSolver.default()
+
+    def make(m, S):
+        x = np.linspace(0.0, 10.0, m)
+        Phi = np.stack([np.exp(-x / 1.0), np.exp(-x / 3.0), np.ones_like(x)], axis=1)
+        Y = np.asfortranarray(Phi @ rng.uniform(1.0, 5.0, size=(3, S)) + 1e-3 * rng.standard_normal((m, S)))
+        return W.make_gpu_problem(dict(x=x, Y=Y, basis=W.DOUBLE_EXP, q=2, alpha0=[1.3, 2.4], weights=None))
+
+    big = [make(500, 50) for _ in range(3)]
+    small = [make(200, 50) for _ in range(3)]       # planned later, smaller shared-memory footprint
+    for p in big + small:
+        r = solver.fit(p)
+        assert r.was_successful() and np.allclose(np.sort(r.nonlinear_parameters()), [1.0, 3.0], atol=1e-3)
+    big2 = [make(500, 60) for _ in range(3)]
+    small2 = [make(200, 60) for _ in range(3)]
+    res = solver.fit_many(big2) + solver.fit_many(small2) + solver.fit_many([make(500, 40), make(500, 44)])
+    assert all(r.was_successful() for r in res)

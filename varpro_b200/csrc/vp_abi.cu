@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <type_traits>
@@ -177,6 +178,21 @@ struct vp_problem {
     double *Pq64 = nullptr; // f64 panel buffer used by the work-queue kernel for fp32 problems (lazily allocated)
     int ldp64 = 0;
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PROCESS-WIDE property of a kernel: problems of different
+// sizes (and host threads) share one instantiation, so the limit may only ever be raised -- a later,
+// smaller request must not lower it under a launch that was planned with the larger value.
+static cudaError_t ensure_dynamic_smem(const void *fn, size_t bytes)
+{
+    static std::mutex mu;
+    static std::unordered_map<const void *, size_t> current;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = current[fn];
+    if (bytes <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 static int env_int(const char *name, int dflt)
 {
@@ -468,7 +484,7 @@ static int plan_fit_kernel(vp_problem *pr, const DmmaKernelEntry &dk, int lds)
         if (max_st >= 2 && nst > max_st) nst = max_st;
         if (nst < 2) return VP_OK;
         const size_t smem = (size_t)nst * stage_bytes;
-        VP_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VP_CUDA(ctx, ensure_dynamic_smem(k.fn, smem));
         int occ = 0;
         VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.nwarps * 32, smem));
         if (occ < 1) return VP_OK;
@@ -526,7 +542,7 @@ static int plan_stream(vp_problem *pr)
             if (max_st >= 2 && nst > max_st) nst = max_st;
             if (nst >= 2) {
                 const size_t smem = (size_t)nst * stage_bytes;
-                VP_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                VP_CUDA(ctx, ensure_dynamic_smem(k.fn, smem));
                 int occ_real = 0;
                 VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k.fn, k.nwarps * 32, smem));
                 if (occ_real >= 1) {
@@ -581,7 +597,7 @@ static int plan_stream(vp_problem *pr)
             if (max_st >= 2 && nst > max_st) nst = max_st;
             const size_t smem = (size_t)nst * stage_bytes;
             if (smem + fa.sharedSizeBytes <= ctx->smem_optin) {
-                VP_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                VP_CUDA(ctx, ensure_dynamic_smem(k.fn, smem));
                 int occ_real = 0;
                 VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, k.fn, k.threads, smem));
                 if (occ_real >= 1) {
@@ -644,7 +660,7 @@ static int launch_panel_t(vp_problem *pr)
         return fail(ctx, VP_ERR_MODEL_TOO_LARGE, "m*(n+p) panel does not fit in shared memory");
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        VP_CUDA(ctx, cudaFuncSetAttribute(panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VP_CUDA(ctx, ensure_dynamic_smem((const void *)panel_kernel<T>, smem));
         configured = smem;
     }
     panel_kernel<T><<<1, threads, smem, ctx->stream>>>(md, (const T *)mo->x_dev, (const T *)pr->w_dev, pr->alpha_dev,
@@ -1414,7 +1430,7 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
             qp.nst = (int)((227 * 1024 - fa.sharedSizeBytes - 1024) / stage_bytes);
             if (qp.nst > STREAM_MAX_STAGES) qp.nst = STREAM_MAX_STAGES;
             qp.smem = (size_t)qp.nst * stage_bytes;
-            VP_CUDA(ctx, cudaFuncSetAttribute(qk->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp.smem));
+            VP_CUDA(ctx, ensure_dynamic_smem(qk->fn, qp.smem));
             VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&qp.occ, qk->fn, qk->nwarps * 32, qp.smem));
         }
         plans.push_back(qp);
@@ -1764,7 +1780,7 @@ static int batch_create_common(vp_ctx *ctx, vp_model *model, int64_t P, const vo
     VP_CUDA(ctx, cudaFuncGetAttributes(&fa, g_batch_kernels[pick].fn));
     if (smem + fa.sharedSizeBytes > ctx->smem_optin)
         return fail(ctx, VP_ERR_MODEL_TOO_LARGE, "vp_batch: m*(n+p) working matrix does not fit in shared memory");
-    VP_CUDA(ctx, cudaFuncSetAttribute(g_batch_kernels[pick].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VP_CUDA(ctx, ensure_dynamic_smem(g_batch_kernels[pick].fn, smem));
     vp_batch *b = new (std::nothrow) vp_batch();
     if (!b) return VP_ERR_OUT_OF_MEMORY;
     b->ctx = ctx; b->model = model; b->P = P; b->ld = md.m; b->kernel = pick; b->mpad = mpad; b->smem = smem;

@@ -214,6 +214,14 @@ int vp_best_fit(vp_problem *problem, void *out_host);
 int vp_residuals_device(vp_problem *problem, void *out_device);
 int vp_jacobian_device(vp_problem *problem, void *out_device);
 int vp_best_fit_device(vp_problem *problem, void *out_device);
+/* Jacobian used by residual-derivative consumers (vp_jacobian, vp_reduce's J^T J, vp_fit):
+ * VP_JACOBIAN_KAUFMAN (default) = what the reference implements (src/solvers/levmar/mod.rs:101-201);
+ * VP_JACOBIAN_FULL adds the second Golub-Pereyra term the reference leaves as a TODO (:188-190;
+ * matlab/varpro.m:696-731): exact derivative of the projected residual, faster convergence on
+ * large-residual problems. Costs one more pass over Y per evaluation and uses the host-driven LM
+ * loop. Re-evaluates at the current parameters. */
+enum { VP_JACOBIAN_KAUFMAN = 0, VP_JACOBIAN_FULL = 1 };
+int vp_problem_set_jacobian(vp_problem *problem, int mode);
 /* ||r||^2, J^T r and J^T J of the current parameters without materialising r or J */
 int vp_reduce(vp_problem *problem, vp_reduced *out);
 

@@ -599,3 +599,63 @@ def test_problems_of_different_sizes_share_kernel_instantiations():
     small2 = [make(200, 60) for _ in range(3)]
     res = solver.fit_many(big2) + solver.fit_many(small2) + solver.fit_many([make(500, 40), make(500, 44)])
     assert all(r.was_successful() for r in res)
+
+
+def _noisy_weighted_problem(m=160, S=5, noise=0.3, seed=21):
+    rng = np.random.default_rng(seed)
+    x = np.linspace(0.0, 10.0, m)
+    Phi = np.stack([np.exp(-x / 1.2), np.exp(-x / 3.7), np.ones_like(x)], axis=1)
+    Y = np.asfortranarray(Phi @ rng.uniform(1.0, 5.0, size=(3, S)) + noise * rng.standard_normal((m, S)))
+    w = rng.uniform(0.5, 1.5, size=m)
+    return dict(x=x, Y=Y, basis=W.DOUBLE_EXP, q=2, alpha0=[0.9, 4.5], weights=w)
+
+
+def test_full_golub_pereyra_jacobian_is_the_exact_derivative_of_the_residual():
+    """VP_JACOBIAN_FULL (the term the reference leaves as a TODO, src/solvers/levmar/mod.rs:188-190): the
+    explicit Jacobian must equal central finite differences of residuals() AWAY from the optimum on a
+    large-residual problem -- which Kaufman's approximation (the default, = the reference) does not --
+    and (||r||^2, J^T r, J^T J) must be those of that Jacobian."""
+    wl = _noisy_weighted_problem()
+    gp = W.make_gpu_problem(wl)
+    alpha = np.array([1.0, 4.2])
+
+    def resid(a):
+        gp.set_params(a)
+        return gp.residuals().copy()
+
+    J_fd = np.empty((160 * 5, 2))
+    for k in range(2):
+        h = 1e-6 * alpha[k]
+        ap, am = alpha.copy(), alpha.copy()
+        ap[k] += h
+        am[k] -= h
+        J_fd[:, k] = (resid(ap) - resid(am)) / (2 * h)
+    gp.set_params(alpha)
+    J_kaufman = gp.jacobian()
+    gp.set_jacobian("full")
+    J_full = gp.jacobian()
+    scale = np.abs(J_fd).max()
+    assert np.max(np.abs(J_full - J_fd)) <= 1e-6 * scale
+    assert np.max(np.abs(J_kaufman - J_fd)) >= 1e-3 * scale      # the approximation really differs here
+    r = gp.residuals()
+    red = gp.reduce()
+    assert np.max(np.abs(red["H"] - J_full.T @ J_full)) <= 1e-9 * np.abs(J_full.T @ J_full).max()
+    assert np.max(np.abs(red["g"] - J_full.T @ r)) <= 1e-8 * np.abs(J_kaufman.T @ r).max() + 1e-9
+    gp.set_jacobian("kaufman")
+    red_k = gp.reduce()
+    assert np.max(np.abs(red_k["H"] - J_kaufman.T @ J_kaufman)) <= 1e-9 * np.abs(red_k["H"]).max()
+
+
+def test_full_jacobian_fit_reaches_the_same_minimum():
+    import varpro_b200 as vb
+    wl = _noisy_weighted_problem(m=300, S=8, noise=0.5, seed=4)
+    a = vb.LevMarSolver.default().fit(W.make_gpu_problem(wl))
+    gp = W.make_gpu_problem(wl).set_jacobian("full")
+    b = vb.LevMarSolver.default().fit(gp)
+    assert a.was_successful() and b.was_successful()
+    pa, pb = a.nonlinear_parameters(), b.nonlinear_parameters()
+    assert np.max(np.abs(pa - pb) / np.abs(pa)) <= 1e-6
+    assert abs(a.minimization_report.objective_function - b.minimization_report.objective_function) \
+        <= 1e-10 * a.minimization_report.objective_function
+    # the exact Jacobian converges quadratically near the solution: no more evaluations than Kaufman's
+    assert b.minimization_report.number_of_evaluations <= a.minimization_report.number_of_evaluations + 1

@@ -72,6 +72,7 @@ SYMBOLS = {
     "vp_residuals_device": (C.c_int, [_vp, _vp]),
     "vp_jacobian_device": (C.c_int, [_vp, _vp]),
     "vp_best_fit_device": (C.c_int, [_vp, _vp]),
+    "vp_problem_set_jacobian": (C.c_int, [_vp, C.c_int]),
     "vp_reduce": (C.c_int, [_vp, C.POINTER(Reduced)]),
     "vp_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _pp, _vp]),
     "vp_comm_connect": (C.c_int, [_vp, _vp]),

@@ -547,6 +547,13 @@ class SeparableProblem:
         return dict(rnorm2=r.rnorm2, g=np.array(r.g[:q]), H=np.array(r.H[:q * q]).reshape(q, q).T.copy(),
                     finite=bool(r.finite))
 
+    def set_jacobian(self, mode: str):
+        """"kaufman" (default; what the reference implements) or "full" (adds the second Golub-Pereyra term
+        the reference leaves as a TODO, src/solvers/levmar/mod.rs:188-190)."""
+        code = {"kaufman": 0, "full": 1}[mode]
+        _check(_lib.load().vp_problem_set_jacobian(self._h, code), self._ctx.h)
+        return self
+
     def statistics(self, confidence_sigma: bool = False):
         """FitStatistics::try_calculate (src/statistics/mod.rs:352-441) for every right-hand side with the
         shared nonlinear parameters (vp_statistics). Returns a list of FitStatistics (one per column)."""

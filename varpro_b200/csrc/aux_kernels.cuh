@@ -285,4 +285,78 @@ __global__ void statistics_kernel(ModelDesc md, const T *__restrict__ Y, int ld,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Full Golub-Pereyra Jacobian. The reference implements Kaufman's
+// approximation only and leaves the second term as a TODO (src/solvers/levmar/mod.rs:188-190); the
+// MATLAB original has it (matlab/varpro.m:696-731, Jac1 + Jac2). With r_s = P_perp y_s:
+//   dr_s/dalpha_k = -(P_perp D_k c_s  +  Q R1^-T (D_k^T r_s)),   (D_k^T r_s)_j = sum_{e in k, j(e)=j} u_{s,e},
+//   u_{s,e} = E_e^T y_s  (= d_e^T r_s because r_s is orthogonal to range(Q)).
+// The two terms are orthogonal, J^T r is unchanged, and
+//   (J^T J)_kl += sum_{e in k, f in l} (R1^-1 R1^-T)_{j(e) j(f)} U_ef,   U_ef = sum_s u_{s,e} u_{s,f}.
+// Optional mode (vp_problem_set_jacobian): one extra pass over Y per evaluation, host-driven LM loop.
+// ---------------------------------------------------------------------------------------------
+
+// U_ef partial sums: one row of p*(p+1)/2 doubles per warp (folded on the host in a fixed order)
+template <typename T>
+__global__ void ugram_kernel(const T *__restrict__ Y, int ld, int ldp, int m, int S, int p, const T *__restrict__ Pe,
+                             double *__restrict__ rows)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+    double U[VP_MAX_P * (VP_MAX_P + 1) / 2];
+    const int nu = p * (p + 1) / 2;
+    for (int t = 0; t < nu; ++t) U[t] = 0.0;
+    for (int s = gw; s < S; s += nw) {
+        const T *y = Y + (size_t)s * ld;
+        double u[VP_MAX_P];
+        for (int e = 0; e < p; ++e) {
+            double acc = 0.0;
+            for (int i = lane; i < m; i += 32) acc += (double)Pe[(size_t)e * ldp + i] * (double)y[i];
+            u[e] = warp_sum(acc);
+        }
+        int t = 0;
+        for (int e = 0; e < p; ++e)
+            for (int f = e; f < p; ++f) U[t++] += u[e] * u[f];
+    }
+    if (lane == 0)
+        for (int t = 0; t < nu; ++t) rows[(size_t)gw * nu + t] = U[t];
+}
+
+// explicit second term: J[s*m + i, k] -= sum_c Q[i][c] z_{s,k}[c],  z_{s,k} = R1^-T v_{s,k}
+template <typename T>
+__global__ void jacobian_full_term_kernel(ModelDesc md, const T *__restrict__ Y, int ld, int ldp, int S, const T *__restrict__ Pq,
+                                          const PanelSmall *__restrict__ small, T *__restrict__ J)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int m = md.m, n = md.n, p = md.p, q = md.q;
+    const T *Pe = Pq + (size_t)n * ldp;
+    const size_t total = (size_t)m * S;
+    for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
+        const T *y = Y + (size_t)s * ld;
+        double u[VP_MAX_P];
+        for (int e = 0; e < p; ++e) {
+            double acc = 0.0;
+            for (int i = lane; i < m; i += 32) acc += (double)Pe[(size_t)e * ldp + i] * (double)y[i];
+            u[e] = warp_sum(acc);
+        }
+        for (int k = 0; k < q; ++k) {
+            double v[VP_MAX_N], z[VP_MAX_N];
+            for (int j = 0; j < n; ++j) v[j] = 0.0;
+            for (int e = 0; e < p; ++e)
+                if (md.e_param[e] == k) v[md.e_basis[e]] += u[e];
+            for (int c = 0; c < n; ++c) { // (R^-T v)_c = sum_j (R^-1)[j][c] v_j ; Rinv[c*VP_MAX_N + j] = (R^-1)[j][c]
+                double acc = 0.0;
+                for (int j = 0; j < n; ++j) acc += small->Rinv[c * VP_MAX_N + j] * v[j];
+                z[c] = acc;
+            }
+            for (int i = lane; i < m; i += 32) {
+                double acc = 0.0;
+                for (int c = 0; c < n; ++c) acc += (double)Pq[(size_t)c * ldp + i] * z[c];
+                const size_t idx = (size_t)k * total + (size_t)s * m + i;
+                J[idx] = (T)((double)J[idx] - acc);
+            }
+        }
+    }
+}
+
 } // namespace vp

@@ -175,6 +175,7 @@ struct vp_problem {
     int fit_grid = 0, fit_nst = 0;
     size_t fit_smem = 0;
     FitBcast *bcast = nullptr;
+    int jac_full = 0;       // 1: full Golub-Pereyra Jacobian (vp_problem_set_jacobian); 0: Kaufman (the reference)
     double *Pq64 = nullptr; // f64 panel buffer used by the work-queue kernel for fp32 problems (lazily allocated)
     int ldp64 = 0;
 };
@@ -794,6 +795,65 @@ static int host_eval_push(vp_problem *pr, const double *alpha)
     return VP_OK;
 }
 
+// Full Golub-Pereyra mode: H += sum (R^-1 R^-T)_{j(e) j(f)} U_ef on top of the Kaufman H in pr->out_host
+// (one extra pass over Y; see aux_kernels.cuh). The panel [Q | E] must be in HBM at the evaluation point.
+template <typename T>
+static int add_full_jacobian_term_t(vp_problem *pr)
+{
+    vp_ctx *ctx = pr->ctx;
+    vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
+    const int p = md.p, n = md.n, q = md.q, nu = p * (p + 1) / 2;
+    if (p == 0) return VP_OK;
+    if (pr->plan_fit >= 0) { // the fused kernel keeps the panel on chip: build it in HBM with K1
+        int rc = launch_panel(pr);
+        if (rc != VP_OK) return rc;
+    }
+    long long blocks = (pr->S + 7) / 8;
+    if (blocks > (long long)ctx->sm_count * 4) blocks = (long long)ctx->sm_count * 4;
+    const size_t nrows = (size_t)blocks * 8;
+    double *rows = nullptr;
+    VP_CUDA(ctx, DEV_ALLOC(ctx, &rows, sizeof(double) * nrows * nu));
+    ugram_kernel<T><<<(unsigned)blocks, 256, 0, ctx->stream>>>((const T *)pr->Yw, mo->ld, pr->ldp, md.m, (int)pr->S, p,
+                                                               (const T *)pr->Pq + (size_t)n * pr->ldp, rows);
+    ctx->launches++;
+    std::vector<double> h(nrows * nu);
+    PanelSmall sm;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), rows, sizeof(double) * nrows * nu, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&sm, pr->small, sizeof(sm), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    DEV_FREE(ctx, rows);
+    if (e != cudaSuccess) return fail(ctx, VP_ERR_CUDA, std::string("full Jacobian term: ") + cudaGetErrorString(e));
+    double U[VP_MAX_P][VP_MAX_P];
+    {
+        int t = 0;
+        for (int a = 0; a < p; ++a)
+            for (int b = a; b < p; ++b, ++t) {
+                double acc = 0.0;
+                for (size_t r = 0; r < nrows; ++r) acc += h[r * nu + t];
+                U[a][b] = U[b][a] = acc;
+            }
+    }
+    double Wm[VP_MAX_N][VP_MAX_N]; // R^-1 R^-T
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double acc = 0.0;
+            for (int c = 0; c < n; ++c) acc += sm.Rinv[c * VP_MAX_N + i] * sm.Rinv[c * VP_MAX_N + j];
+            Wm[i][j] = acc;
+        }
+    EvalOut *o = pr->out_host;
+    for (int a = 0; a < p; ++a)
+        for (int b = 0; b < p; ++b)
+            o->H[md.e_param[b] * q + md.e_param[a]] += Wm[md.e_basis[a]][md.e_basis[b]] * U[a][b];
+    for (int i = 0; i < q * q; ++i) o->finite = o->finite && std::isfinite(o->H[i]);
+    return VP_OK;
+}
+static int add_full_jacobian_term(vp_problem *pr)
+{
+    return pr->model->dtype == VP_F32 ? add_full_jacobian_term_t<float>(pr) : add_full_jacobian_term_t<double>(pr);
+}
+
 // Evaluate at `alpha` into coefficient buffer `cdst`; result in pr->out_host.
 static int evaluate_sync(vp_problem *pr, const double *alpha, int cdst)
 {
@@ -811,7 +871,9 @@ static int evaluate_sync(vp_problem *pr, const double *alpha, int cdst)
     if (rc != VP_OK) return rc;
     VP_CUDA(ctx, cudaMemcpyAsync(pr->out_host, pr->out_dev, sizeof(EvalOut), cudaMemcpyDeviceToHost, ctx->stream));
     VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return comm_check(pr);
+    rc = comm_check(pr);
+    if (rc == VP_OK && pr->jac_full) rc = add_full_jacobian_term(pr);
+    return rc;
 }
 
 static void evalout_to_lm(const EvalOut &o, int q, LmEval &ev)
@@ -980,6 +1042,24 @@ extern "C" int vp_params(const vp_problem *pr, double *alpha_out)
     return VP_OK;
 }
 
+extern "C" int vp_problem_set_jacobian(vp_problem *pr, int mode)
+{
+    if (!pr || (mode != VP_JACOBIAN_KAUFMAN && mode != VP_JACOBIAN_FULL)) return VP_ERR_INVALID_ARGUMENT;
+    if (pr->comm && mode == VP_JACOBIAN_FULL)
+        return fail(pr->ctx, VP_ERR_COMM, "the full Jacobian is not available for column-sharded problems");
+    pr->jac_full = mode == VP_JACOBIAN_FULL ? 1 : 0;
+    if (!pr->cached) return VP_OK;
+    // refresh the cached evaluation (its J^T J depends on the mode)
+    const int dst = pr->cur ^ 1;
+    int rc = evaluate_sync(pr, pr->alpha, dst);
+    if (rc == VP_ERR_NO_CACHED_CALCULATION) { pr->cached = false; return VP_OK; }
+    if (rc != VP_OK) { pr->cached = false; return rc; }
+    pr->cur = dst;
+    evalout_to_lm(*pr->out_host, pr->model->md.q, pr->eval);
+    pr->cached = pr->eval.finite != 0;
+    return VP_OK;
+}
+
 extern "C" int vp_reduce(vp_problem *pr, vp_reduced *out)
 {
     if (!pr || !out) return VP_ERR_INVALID_ARGUMENT;
@@ -1028,6 +1108,11 @@ static int materialise_t(vp_problem *pr, int what, void *out_host, void *out_dev
     } else if (what == 1) {
         jacobian_kernel<T><<<blocks, 256, 0, ctx->stream>>>(pr->ldp, md.m, (int)pr->S, md.n, md.p, md.q,
                                                             (const T *)pr->Pq + (size_t)md.n * pr->ldp, (const T *)pr->C[pr->cur], md, buf);
+        if (pr->jac_full) {
+            jacobian_full_term_kernel<T><<<blocks, 256, 0, ctx->stream>>>(md, (const T *)pr->Yw, mo->ld, pr->ldp, (int)pr->S,
+                                                                          (const T *)pr->Pq, pr->small, buf);
+            ctx->launches++;
+        }
     } else {
         if (mo->hosteval) {
             cudaMemcpyAsync(pr->phi_scratch, mo->pre_dev, sizeof(double) * (size_t)md.m * md.n, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1298,7 +1383,7 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
     // the evaluation at the current parameters is cached (builder / set_params)
     bool more = lm_advance(st, cfg, pr->eval);
     const char *mode = getenv("VP_FIT_MODE"); // "persistent" (default when the fused kernel exists), "graph" or "host"
-    if (more && pr->plan_fit >= 0 && !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph")))) {
+    if (more && pr->plan_fit >= 0 && !pr->jac_full && !(mode && (!strcmp(mode, "host") || !strcmp(mode, "graph")))) {
         // ---- persistent grid: the whole fit is ONE cooperative kernel launch ------------------
         vp_ctx *ctx = pr->ctx;
         cudaSetDevice(ctx->device);
@@ -1309,6 +1394,8 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
         if (rc != VP_OK) return rc;
         more = false;
     }
+    if (more && pr->comm && (pr->jac_full || pr->plan_fit < 0))
+        return fail(pr->ctx, VP_ERR_COMM, "column-sharded fits run on the persistent fit kernel only (Kaufman Jacobian)");
     if (more && pr->comm) return fail(pr->ctx, VP_ERR_COMM, "column-sharded fits run on the persistent fit kernel only");
     const char *single = getenv("VP_FIT_SINGLE"); // "queue": run single f64 fits on the work-queue kernel too
     if (more && (pr->plan_fit < 0 || (single && !strcmp(single, "queue"))) &&
@@ -1326,7 +1413,7 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
             return rc;
         }
     }
-    if (more && !(mode && !strcmp(mode, "host")) && !pr->model->hosteval) {
+    if (more && !(mode && !strcmp(mode, "host")) && !pr->model->hosteval && !pr->jac_full) {
         // ---- device-driven loop: one CUDA graph launch per fit ------------------------
         vp_ctx *ctx = pr->ctx;
         cudaSetDevice(ctx->device);
@@ -1381,7 +1468,7 @@ extern "C" int vp_fit(vp_problem *pr, const vp_lm_options *opt, vp_fit_report *r
 static int queue_kernel_for(const vp_problem *pr, int *lds_out)
 {
     const vp_model *mo = pr->model;
-    if (mo->hosteval || pr->comm || !pr->cached) return -1;
+    if (mo->hosteval || pr->comm || !pr->cached || pr->jac_full) return -1;
     const ModelDesc &md = mo->md;
     int lds = mo->ld;
     if (mo->dtype == VP_F64) { while (lds % 16 != 4) lds += 2; }

@@ -43,7 +43,7 @@ struct QueueFit {
     FitDevice *fit;
     double svd_eps;
     int ld, S, ldp, red_stride;
-    int ntiles, min_chunk_tiles, max_chunks;
+    int ntiles, min_chunk_tiles, max_chunks, adaptive, items_per_cta;
     // set by the finisher for every evaluation (read by the consumers with ld.global.cg):
     int chunk_tiles, nchunks;
     int cdst;         // coefficient buffer the current evaluation writes
@@ -167,10 +167,13 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             qf->cdst = cdst;
             // chunk size of this evaluation: about four items per CTA over the fits still running, so
             // that the last few fits are spread over the whole grid too
-            int active = ld_acquire_gpu_s32(&ctl->fits_left);
+            // qf->adaptive == 0: size the chunks for the initial number of fits, i.e. the SAME partition (and
+            // therefore bitwise the same rounding of the partial sums) in every evaluation of a fit
+            int active = qf->adaptive ? ld_acquire_gpu_s32(&ctl->fits_left) : nfits;
             if (active < 1) active = 1;
-            // many fits: ~4 items per CTA per round (balance); few fits: larger items (less per-item overhead)
-            const int per_cta = active >= 8 ? 4 : (active >= 3 ? 2 : 1);
+            // many fits: items_per_cta (default 2) items per CTA per round -- measured: per-item overhead (claim,
+            // fragment load, pipeline fill, publish ~ 7 us) against balance; few fits: larger items
+            const int per_cta = active >= 8 ? qf->items_per_cta : (active >= 3 ? min(2, qf->items_per_cta) : 1);
             const int target = (per_cta * (int)gridDim.x + active - 1) / active;
             int ct = (qf->ntiles + target - 1) / target;
             if (ct < qf->min_chunk_tiles) ct = qf->min_chunk_tiles;

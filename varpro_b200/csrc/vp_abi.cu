@@ -1557,6 +1557,9 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         f.ntiles = (int)((pr->S + DMMA_CT - 1) / DMMA_CT);
         f.min_chunk_tiles = min_chunk < 1 ? 1 : min_chunk;
         f.max_chunks = pr->max_grid; // one partial row per chunk
+        f.adaptive = env_int("VP_QUEUE_ADAPTIVE", 1);
+        f.items_per_cta = env_int("VP_QUEUE_ITEMS_PER_CTA", 2);
+        if (f.items_per_cta < 1) f.items_per_cta = 1;
         f.chunk_tiles = f.ntiles;
         f.nchunks = 1;
         f.cdst = pr->cur ^ 1;

@@ -114,3 +114,55 @@ def test_levenberg_marquardt_option_holder():
     assert (o.stepbound, o.patience, o.ftol, o.xtol, o.gtol, o.scale_diag) == (1.0, 1000, 1e-10, 1e-10, 1e-10, 0)
     t = vb.TerminationReason(5)
     assert t.was_successful() and repr(t) == "Converged{xtol}" and not vb.TerminationReason(8).was_successful()
+
+
+def test_closure_models_validate_like_the_reference_builder():
+    """Host closures with partial derivatives (src/model/builder/mod.rs:338-440): a missing derivative, a
+    derivative for a parameter the function does not take, or a duplicate derivative are build errors;
+    a complete closure model evaluates Phi and the non-zero derivative columns in (function, slot) order."""
+    import varpro_b200 as vb
+    x = np.linspace(0.0, 2.0, 5)
+
+    def f(x, tau):
+        return np.exp(-x / tau)
+
+    def df(x, tau):
+        return np.exp(-x / tau) * x / tau ** 2
+
+    with pytest.raises(vb.ModelBuildError):      # missing derivative
+        vb.SeparableModelBuilder(["tau"]).function(["tau"], f).independent_variable(x).initial_parameters([1.0]).build()
+    with pytest.raises(vb.ModelBuildError):      # derivative for a foreign parameter
+        (vb.SeparableModelBuilder(["tau", "w"]).function(["tau"], f).partial_deriv("w", df)
+         .function(["w"], vb.ExpDecay()).independent_variable(x).initial_parameters([1.0, 2.0]).build())
+    with pytest.raises(vb.ModelBuildError):      # duplicate derivative
+        (vb.SeparableModelBuilder(["tau"]).function(["tau"], f).partial_deriv("tau", df).partial_deriv("tau", df)
+         .independent_variable(x).initial_parameters([1.0]).build())
+    model = (vb.SeparableModelBuilder(["a", "b"])
+             .function(["b"], f).partial_deriv("b", df)            # function parameter order need not follow the model's
+             .function(["a", "b"], vb.ExpRateCos())
+             .invariant_function(lambda x: 2.0 * x)
+             .independent_variable(x).initial_parameters([0.5, 1.5]).build())
+    assert model.is_host_evaluated()
+    assert model.derivative_index() == [(0, 1), (1, 0), (1, 1)]
+    cols, dcols = model.eval_host(np.array([0.5, 1.5]))
+    assert len(cols) == 3 and len(dcols) == 3
+    assert np.allclose(cols[0], np.exp(-x / 1.5)) and np.allclose(cols[2], 2.0 * x)
+    assert np.allclose(cols[1], np.exp(-0.5 * x) * np.cos(1.5 * x))
+    assert np.allclose(dcols[1], -x * np.exp(-0.5 * x) * np.cos(1.5 * x))      # d/da
+    assert np.allclose(dcols[2], -x * np.exp(-0.5 * x) * np.sin(1.5 * x))      # d/db
+
+
+def test_fit_statistics_accessors_follow_the_reference_ordering():
+    """FitStatistics (src/statistics/mod.rs): covariance ordered (c..., alpha...), variances, correlation."""
+    import varpro_b200 as vb
+    cov = np.array([[4.0, 1.0, 0.5], [1.0, 9.0, -0.3], [0.5, -0.3, 1.0]])
+    st = vb.FitStatistics(cov, 0.25, 17, 2, np.array([1.0, 2.0]))
+    assert np.allclose(st.linear_coefficients_variance(), [4.0, 9.0])
+    assert np.allclose(st.nonlinear_parameters_variance(), [1.0])
+    assert abs(st.regression_standard_error() - 0.5) < 1e-15
+    corr = st.calculate_correlation_matrix()
+    assert np.allclose(np.diag(corr), 1.0) and abs(corr[0, 1] - 1.0 / 6.0) < 1e-15
+    from scipy import stats
+    assert np.allclose(st.confidence_band_radius(0.9), np.array([1.0, 2.0]) * stats.t.ppf(0.95, 17))
+    with pytest.raises(vb.VarproError):
+        st.confidence_band_radius(1.5)

@@ -5,6 +5,7 @@ Tolerances (BASELINE.json north_star): nonlinear parameters within 1e-8 relative
 norm within 1e-10 relative to ||Y_w||; element-wise quantities (residuals, Jacobian,
 coefficients) to 1e-9 relative to their scale. fp32 problems use stated looser bounds.
 """
+import os
 import numpy as np
 import pytest
 
@@ -659,3 +660,33 @@ def test_full_jacobian_fit_reaches_the_same_minimum():
         <= 1e-10 * a.minimization_report.objective_function
     # the exact Jacobian converges quadratically near the solution: no more evaluations than Kaufman's
     assert b.minimization_report.number_of_evaluations <= a.minimization_report.number_of_evaluations + 1
+
+
+def test_c2_full_size_matches_the_oracle():
+    """BASELINE config 2 at FULL size (m = 1024, S = 4096): the oracle needs about a second, so the fit is
+    compared directly -- parameters to 1e-8 relative, residual norm to 1e-10 ||Y||, every coefficient."""
+    import varpro_b200 as vb
+    from oracle import varpro_oracle as vo
+    wl = W.c2(S=4096)
+    vo.set_threads(os.cpu_count() or 1)
+    op = W.make_oracle(wl)
+    rep = op.fit()
+    vo.set_threads(1)
+    assert rep["successful"]
+    single = vb.LevMarSolver.default().fit(W.make_gpu_problem(wl))                      # persistent kernel
+    many = vb.LevMarSolver.default().fit_many([W.make_gpu_problem(wl) for _ in range(3)])  # work-queue kernel
+    Yn = np.linalg.norm(wl["Y"])
+    a_o = np.sort(op.params())
+    C_o = op.linear_coefficients()
+    if op.params()[0] > op.params()[1]:
+        C_o = C_o[[1, 0, 2]]
+    for r in [single] + many:
+        assert r.was_successful()
+        a = r.nonlinear_parameters()
+        C = r.linear_coefficients()
+        if a[0] > a[1]:
+            a, C = a[::-1], C[[1, 0, 2]]
+        assert np.max(np.abs(a - a_o) / a_o) <= REL_PARAM
+        rn = np.sqrt(2 * r.minimization_report.objective_function)
+        assert abs(rn - np.sqrt(2 * rep["objective_function"])) <= REL_RNORM * Yn
+        assert np.max(np.abs(C - C_o)) <= 1e-7 * np.abs(C_o).max()

@@ -352,6 +352,19 @@ def test_c4_fp32_full_size():
     assert np.max(np.abs(C[:, 1:] - wl["C_gen"][:, 1:])) <= 0.05 * np.abs(wl["C_gen"]).max()
     chi2 = 2 * res.minimization_report.objective_function / (1000 * 16384 - 3 * 16384 - 2)
     assert 0.5 * 3.2e-5 < chi2 < 2 * 3.2e-5 + 1e-4  # weighted noise level of the generator (sigma = 0.01, w = 1/sqrt(y))
+    # and directly against the fp64 oracle on the same fp32-rounded inputs (a few seconds with all host threads)
+    from oracle import varpro_oracle as vo
+    wl64 = dict(wl, x=wl["x"].astype(np.float64), Y=np.asfortranarray(wl["Y"].astype(np.float64)),
+                weights=wl["weights"].astype(np.float64))
+    vo.set_threads(os.cpu_count() or 1)
+    op = W.make_oracle(wl64)
+    rep = op.fit()
+    vo.set_threads(1)
+    assert rep["successful"]
+    assert np.max(np.abs(a - op.params()) / np.abs(op.params())) <= F32_PARAM_REL
+    rn_g, rn_o = np.sqrt(2 * res.minimization_report.objective_function), np.sqrt(2 * rep["objective_function"])
+    assert abs(rn_g - rn_o) <= 1e-4 * rn_o
+    assert np.max(np.abs(C - op.linear_coefficients())) <= 1e-3 * np.abs(op.linear_coefficients()).max()
 
 
 def _batch_model(wl, m):
@@ -364,7 +377,7 @@ def _batch_model(wl, m):
     return b.independent_variable(wl["x"]).initial_parameters([1.0] * wl["q"]).build()
 
 
-@pytest.mark.parametrize("m,P", [(256, 12), (1000, 5)])
+@pytest.mark.parametrize("m,P", [(256, 12), (1000, 5), (4096, 4)])  # 4096 = BASELINE config 3's sample count
 def test_c3_independent_batch_matches_oracle_per_problem(m, P):
     """BASELINE config 3 shape at test size: every problem of the batch against its own oracle fit."""
     import varpro_b200 as vb

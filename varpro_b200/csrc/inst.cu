@@ -50,7 +50,7 @@ static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0
 #elif VP_INST_PART == 4
 constexpr int BATCH_THREADS = 512;
 #define VP_BK(RPT, G) {N_, P_, RPT, BATCH_THREADS, G, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS, G>}
-static const BatchKernelEntry batch_tab[] = {VP_BK(1, 4), VP_BK(2, 4), VP_BK(4, 4), VP_BK(8, 4), VP_BK(8, 8), VP_BK(8, 2), VP_BK(8, 16)};
+static const BatchKernelEntry batch_tab[] = {VP_BK(1, 4), VP_BK(2, 4), VP_BK(4, 4), VP_BK(8, 4), VP_BK(8, 8)};
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, batch_tab, (int)(sizeof(batch_tab) / sizeof(batch_tab[0]))};
 #else
 constexpr int PANEL_HH_THREADS = 512;

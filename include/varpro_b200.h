@@ -299,11 +299,13 @@ int vp_batch_linear_coefficients(vp_batch *batch, double *C_out);   /* n x P */
 
 /* ---- diagnostics ---------------------------------------------------------
  * Device time (CUDA events on the context's stream, microseconds, averaged over
- * `iters`) of the two kernels of one evaluation at the current parameters:
- * the panel kernel (K1) and the Y-streaming reduce (K2). If flush_bytes > 0 a
- * scratch buffer of that size is overwritten before every iteration so that
- * the observations are read from HBM, not from L2. Also reports K2's grid size
- * and dynamic shared memory. */
+ * `iters`) of ONE evaluation at the current parameters. Problems with a fused
+ * evaluation kernel (fit_kernel_dmma: panel + streaming reduce in one launch) report
+ * it in stream_us with panel_us ~ 0; otherwise panel_us is the panel kernel (K1) and
+ * stream_us the Y-streaming reduce (K2). If flush_bytes > 0 a scratch buffer of that
+ * size is overwritten before every iteration so that the observations are read from
+ * HBM, not from L2. Also reports the streaming kernel's grid size and dynamic shared
+ * memory. */
 int vp_profile_evaluation(vp_problem *problem, int iters, int64_t flush_bytes, double *panel_us,
                           double *stream_us, int64_t *stream_grid, int64_t *stream_smem);
 

@@ -61,7 +61,9 @@ struct QueueCtl {
     int error;
     QueueItem *items;
     unsigned int cap;
+    unsigned long long *dbg; // optional (VP_QUEUE_DBG): per CTA 8 accumulators in ns / counts, see QDBG_*
 };
+enum { QDBG_ITEMS = 0, QDBG_CLAIM = 1, QDBG_FRAG = 2, QDBG_STREAM = 3, QDBG_PUBLISH = 4, QDBG_FINISH = 5, QDBG_NFINISH = 6, QDBG_TOTAL = 7 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
 {
@@ -216,8 +218,12 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     // prologue: first panels (the host has advanced every fit to its first trial point)
     for (int k = blockIdx.x; k < nfits; k += gridDim.x) start_evaluation(k);
 
+    unsigned long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // tid 0, only when ctl->dbg is set
+    const bool dbg_on = ctl->dbg != nullptr;
+    const unsigned long long t_kernel0 = dbg_on ? global_timer_ns() : 0ull;
     for (;;) {
         // ---- claim an item ----------------------------------------------------------------------
+        const unsigned long long t_a = dbg_on ? global_timer_ns() : 0ull;
         if (tid == 0) {
             const unsigned long long idx = atomicAdd(&ctl->head, 1ull);
             QueueItem *it = &ctl->items[idx % ctl->cap];
@@ -234,6 +240,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         __syncthreads();
         const int k = item_fit, chunk = item_chunk;
         if (k < 0) break;
+        const unsigned long long t_b = dbg_on ? global_timer_ns() : 0ull;
         QueueFit *qf = &fits[k];
         const int ld = qf->ld, S = qf->S, ldp = qf->ldp;
         const TY *Yk = static_cast<const TY *>(qf->Y);
@@ -286,6 +293,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             if (tid < N * N) rinv_s[tid] = __ldcg(&qf->small->Rinv[(tid / N) * VP_MAX_N + (tid % N)]);
         }
         __syncthreads();
+        const unsigned long long t_c = dbg_on ? global_timer_ns() : 0ull;
 
         // ---- stream the chunk (tile math of fit_kernel_dmma) -------------------------------------------
         double rn2 = 0.0;
@@ -373,6 +381,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             }
         }
         __syncthreads(); // every warp is done with every stage: the ring is idle
+        const unsigned long long t_d = dbg_on ? global_timer_ns() : 0ull;
 
         // ---- chunk partial -> global; the last chunk's CTA finishes the evaluation ---------------------
         StreamArgs<double> al{};
@@ -382,6 +391,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
 #pragma unroll
         for (int e2 = 0; e2 < VP_MAX_P; ++e2) { al.e_basis[e2] = qf->md.e_basis[e2]; al.e_param[e2] = qf->md.e_param[e2]; }
         cta_publish_partial<double, N, P, CT, NWARPS>(al, rn2, Gacc, Vacc, wsum_s, gv_s, &is_last, chunk, nchunks);
+        const unsigned long long t_e = dbg_on ? global_timer_ns() : 0ull;
         if (is_last) {
             stream_finalize<double, false, false>(al, N, P, nchunks, fin_sh, fin_scratch);
             __syncthreads();
@@ -422,6 +432,16 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             }
         }
         __syncthreads();
+        if (dbg_on && tid == 0) {
+            const unsigned long long t_f = global_timer_ns();
+            dacc[QDBG_ITEMS] += 1; dacc[QDBG_CLAIM] += t_b - t_a; dacc[QDBG_FRAG] += t_c - t_b; dacc[QDBG_STREAM] += t_d - t_c;
+            dacc[QDBG_PUBLISH] += t_e - t_d;
+            if (is_last) { dacc[QDBG_FINISH] += t_f - t_e; dacc[QDBG_NFINISH] += 1; }
+        }
+    }
+    if (dbg_on && tid == 0) {
+        dacc[QDBG_TOTAL] = global_timer_ns() - t_kernel0;
+        for (int i = 0; i < 8; ++i) ctl->dbg[(size_t)blockIdx.x * 8 + i] = dacc[i];
     }
 }
 

@@ -1592,6 +1592,15 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         hqp[i] = hq[(size_t)i];
     }
     hctl->head = 0; hctl->tail = 0; hctl->fits_left = K; hctl->error = 0; hctl->items = ditems; hctl->cap = cap;
+    unsigned long long *ddbg = nullptr;
+    const long long dbg_grid = (long long)ctx->sm_count * occ;
+    if (env_int("VP_QUEUE_DBG", 0)) { // per-CTA phase accumulators (diagnostics; printed to stderr after the launch)
+        if (DEV_ALLOC(ctx, &ddbg, sizeof(unsigned long long) * 8 * (size_t)dbg_grid) == cudaSuccess)
+            cudaMemsetAsync(ddbg, 0, sizeof(unsigned long long) * 8 * (size_t)dbg_grid, ctx->stream);
+        else
+            ddbg = nullptr;
+    }
+    hctl->dbg = ddbg;
     e = cudaMemcpyAsync(db, hb, total_bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ditems, 0, sizeof(QueueItem) * (size_t)cap, ctx->stream);
     int rc = VP_OK;
@@ -1605,6 +1614,21 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
     if (e == cudaSuccess) e = cudaMemcpyAsync(hb, db, off_ctl + sizeof(QueueCtl), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     const int qerr = hctl->error;
+    if (ddbg && e == cudaSuccess) {
+        std::vector<unsigned long long> hd(8 * (size_t)dbg_grid);
+        if (cudaMemcpy(hd.data(), ddbg, sizeof(unsigned long long) * hd.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            double acc[8] = {0};
+            for (long long b = 0; b < dbg_grid; ++b)
+                for (int i = 0; i < 8; ++i) acc[i] += (double)hd[(size_t)b * 8 + i];
+            const double it = acc[0] > 0 ? acc[0] : 1, nf = acc[6] > 0 ? acc[6] : 1;
+            fprintf(stderr, "[vp queue dbg] fits %d items %.0f (%.1f per CTA) | per item: claim %.2f us, fragments %.2f us, stream %.2f us, "
+                            "publish %.2f us | finisher (finalize + LM + panel + push) %.2f us x %.0f | CTA lifetime %.1f us, busy %.1f %%\n",
+                    K, acc[0], acc[0] / dbg_grid, 1e-3 * acc[1] / it, 1e-3 * acc[2] / it, 1e-3 * acc[3] / it, 1e-3 * acc[4] / it,
+                    1e-3 * acc[5] / nf, acc[6], 1e-3 * acc[7] / dbg_grid,
+                    100.0 * (acc[2] + acc[3] + acc[4] + acc[5]) / (acc[7] > 0 ? acc[7] : 1));
+        }
+    }
+    DEV_FREE(ctx, ddbg);
     DEV_FREE(ctx, db); DEV_FREE(ctx, ditems);
     if (e != cudaSuccess) { HOST_FREE(ctx, hb); return fail(ctx, VP_ERR_CUDA, std::string("vp_fit_many (queue): ") + cudaGetErrorString(e)); }
     if (qerr) { HOST_FREE(ctx, hb); return fail(ctx, VP_ERR_CUDA, "vp_fit_many: a wait inside the work-queue kernel timed out"); }

@@ -61,6 +61,15 @@ struct QueueCtl {
     int error;
     QueueItem *items;
     unsigned int cap;
+    // finish queue (optional, VP_QUEUE_FINISHERS=n): the CTA that completes the last chunk of an evaluation hands
+    // the fit to one of n dedicated CTAs (blockIdx.x < n) that only finalize / step the LM state machine / build
+    // panels. Built to test the hypothesis that the rarely executed LM + panel code was slow because of a cold
+    // instruction cache; the measurement (VP_QUEUE_DBG) rejected it -- the LM step itself averages ~31 us on one
+    // thread -- so the default stays 0: the last chunk's CTA finishes the evaluation itself.
+    unsigned long long fhead, ftail;
+    QueueItem *fitems;
+    unsigned int fcap;
+    int nfinishers;          // 0: the last chunk's CTA finishes the evaluation itself
     unsigned long long *dbg; // optional (VP_QUEUE_DBG): per CTA 8 accumulators in ns / counts, see QDBG_*
 };
 enum { QDBG_ITEMS = 0, QDBG_CLAIM = 1, QDBG_FRAG = 2, QDBG_STREAM = 3, QDBG_PUBLISH = 4, QDBG_FINISH = 5, QDBG_NFINISH = 6, QDBG_TOTAL = 7 };
@@ -115,6 +124,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     __shared__ double top[N][NPV];
     __shared__ double alpha_s[VP_MAX_Q];
     __shared__ int is_last, item_fit, item_chunk, more_s, push_n;
+    __shared__ unsigned long long fin_acc[8]; // VP_QUEUE_DBG: finisher sub-phases (finalize, state load, LM, state store, x/w + basis, factor + panel store, push, count)
     __shared__ unsigned long long push_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -126,6 +136,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
+        for (int i = 0; i < 8; ++i) fin_acc[i] = 0;
     }
     __syncthreads();
     uint32_t phase_bits = 0;
@@ -137,6 +148,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     auto start_evaluation = [&](const int k) {
         QueueFit *qf = &fits[k];
         const ModelDesc &md = qf->md;
+        const unsigned long long ts0 = global_timer_ns();
         if (tid < VP_MAX_Q) alpha_s[tid] = tid < md.q ? __ldcg(&qf->fit->st.x_trial[tid]) : 0.0;
         double xi[RPT], wi[RPT];
 #pragma unroll
@@ -151,6 +163,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         {
             double pa[RPT][NPV], pd0[RPT][P > 0 ? P : 1];
             const int bad = panel_eval_staged<N, P, RPT, THREADS>(md, xi, wi, alpha_s, staging, lds, pa, pd0);
+            if (tid == 0) fin_acc[4] += global_timer_ns() - ts0;
             panel_hh_factor<double, N, P, RPT, THREADS>(md, pa, pd0, bad, alpha_s, qf->svd_eps, qf->ldp, qf->Pq, qf->small, red, top,
                                                         nullptr);
         }
@@ -164,6 +177,8 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         fence_proxy_async_smem(); // generic writes to the staging area before later bulk copies into it
         __threadfence();
         __syncthreads();
+        const unsigned long long ts1 = global_timer_ns();
+        if (tid == 0) fin_acc[5] += ts1 - ts0;
         if (tid == 0) {
             const int cdst = __ldcg(&qf->fit->cur) ^ 1;
             qf->cdst = cdst;
@@ -203,6 +218,65 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
                 st_release_gpu_u64(&ctl->items[(base + j) % ctl->cap].seq, base + j + 1ull);
         }
         __syncthreads();
+        if (tid == 0) { fin_acc[6] += global_timer_ns() - ts1; fin_acc[7] += 1; }
+    };
+
+    // Fold the chunk partials of fit k, advance its lmder state machine, and either start the next
+    // evaluation or retire the fit. Executed by a whole CTA with an idle TMA ring.
+    auto finish_evaluation = [&](const int k) {
+        QueueFit *qf = &fits[k];
+        StreamArgs<double> al{};
+        al.small = qf->small;
+        al.partials = qf->partials; al.red_stride = qf->red_stride; al.ticket = qf->ticket; al.out = qf->out;
+        al.q = qf->md.q; al.dbg = nullptr; al.fit = nullptr;
+#pragma unroll
+        for (int e2 = 0; e2 < VP_MAX_P; ++e2) { al.e_basis[e2] = qf->md.e_basis[e2]; al.e_param[e2] = qf->md.e_param[e2]; }
+        const int nchunks = __ldcg(&qf->nchunks);
+        const unsigned long long tf0 = global_timer_ns();
+        stream_finalize<double, false, false>(al, N, P, nchunks, fin_sh, fin_scratch);
+        __syncthreads();
+        const unsigned long long tf1 = global_timer_ns();
+        // advance the lmder state machine of fit k on a shared-memory copy of its state
+        const int q = qf->md.q;
+        unsigned long long *fw = reinterpret_cast<unsigned long long *>(qf->fit);
+        unsigned long long *lw = reinterpret_cast<unsigned long long *>(fin_scratch);
+        for (int i = tid; i < FIT_WORDS; i += THREADS) lw[i] = __ldcg(fw + i);
+        __syncthreads();
+        const unsigned long long tf2 = global_timer_ns();
+        if (tid == 0) {
+            FitDevice *fd = reinterpret_cast<FitDevice *>(lw);
+            LmEval ev;
+            ev.rnorm2 = __ldcg(&qf->out->rnorm2);
+            ev.finite = __ldcg(&qf->out->finite);
+            for (int kk = 0; kk < VP_LM_MAXQ; ++kk) ev.g[kk] = kk < q ? __ldcg(&qf->out->g[kk]) : 0.0;
+            for (int kk = 0; kk < VP_LM_MAXQ * VP_LM_MAXQ; ++kk) ev.H[kk] = kk < q * q ? __ldcg(&qf->out->H[kk]) : 0.0;
+            const bool more = lm_advance(fd->st, fd->cfg, ev);
+            if (fd->st.last_accepted) {
+                fd->cur ^= 1;
+                fd->accepted = ev;
+            }
+            if (fd->evals < 48) {
+                double *tr = fd->trace + 4 * fd->evals;
+                tr[0] = sqrt(ev.rnorm2); tr[1] = fd->st.par; tr[2] = fd->st.delta; tr[3] = fd->st.last_accepted;
+            }
+            fd->evals += 1;
+            more_s = more ? 1 : 0;
+        }
+        __syncthreads();
+        const unsigned long long tf3 = global_timer_ns();
+        for (int i = tid; i < FIT_WORDS; i += THREADS) fw[i] = lw[i];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            fin_acc[0] += tf1 - tf0; fin_acc[1] += tf2 - tf1; fin_acc[2] += tf3 - tf2; fin_acc[3] += global_timer_ns() - tf3;
+        }
+        if (more_s) {
+            start_evaluation(k);
+        } else if (tid == 0) {
+            __threadfence();
+            atomicSub(&ctl->fits_left, 1);
+        }
+        __syncthreads();
     };
 
     // zero the pad rows [ld, lds) of every column slot once (the bulk copies never write them; the
@@ -217,6 +291,32 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
 
     // prologue: first panels (the host has advanced every fit to its first trial point)
     for (int k = blockIdx.x; k < nfits; k += gridDim.x) start_evaluation(k);
+
+    // ---- dedicated finisher CTAs -------------------------------------------------------------------
+    const int nfin = ctl->nfinishers;
+    if (nfin > 0 && (int)blockIdx.x < nfin) {
+        for (;;) {
+            if (tid == 0) {
+                const unsigned long long idx = atomicAdd(&ctl->fhead, 1ull);
+                QueueItem *it = &ctl->fitems[idx % ctl->fcap];
+                const unsigned long long t0 = global_timer_ns();
+                int got = 0;
+                for (;;) {
+                    if (ld_acquire_gpu_u64(&it->seq) == idx + 1ull) { got = 1; break; }
+                    if (ld_acquire_gpu_s32(&ctl->fits_left) <= 0) break;
+                    if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) { ctl->error = 1; break; }
+                }
+                item_fit = got ? it->fit : -1;
+            }
+            __syncthreads();
+            const int k = item_fit;
+            if (k < 0) break;
+            finish_evaluation(k);
+        }
+        if (ctl->dbg != nullptr && tid == 0)
+            for (int i = 0; i < 8; ++i) ctl->dbg[(size_t)blockIdx.x * 8 + i] = fin_acc[i];
+        return;
+    }
 
     unsigned long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // tid 0, only when ctl->dbg is set
     const bool dbg_on = ctl->dbg != nullptr;
@@ -393,42 +493,18 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         cta_publish_partial<double, N, P, CT, NWARPS>(al, rn2, Gacc, Vacc, wsum_s, gv_s, &is_last, chunk, nchunks);
         const unsigned long long t_e = dbg_on ? global_timer_ns() : 0ull;
         if (is_last) {
-            stream_finalize<double, false, false>(al, N, P, nchunks, fin_sh, fin_scratch);
-            __syncthreads();
-            // advance the lmder state machine of fit k on a shared-memory copy of its state
-            const int q = qf->md.q;
-            unsigned long long *fw = reinterpret_cast<unsigned long long *>(qf->fit);
-            unsigned long long *lw = reinterpret_cast<unsigned long long *>(fin_scratch);
-            for (int i = tid; i < FIT_WORDS; i += THREADS) lw[i] = __ldcg(fw + i);
-            __syncthreads();
-            if (tid == 0) {
-                FitDevice *fd = reinterpret_cast<FitDevice *>(lw);
-                LmEval ev;
-                ev.rnorm2 = qf->out->rnorm2;
-                ev.finite = qf->out->finite;
-                for (int kk = 0; kk < VP_LM_MAXQ; ++kk) ev.g[kk] = kk < q ? qf->out->g[kk] : 0.0;
-                for (int kk = 0; kk < VP_LM_MAXQ * VP_LM_MAXQ; ++kk) ev.H[kk] = kk < q * q ? qf->out->H[kk] : 0.0;
-                const bool more = lm_advance(fd->st, fd->cfg, ev);
-                if (fd->st.last_accepted) {
-                    fd->cur ^= 1;
-                    fd->accepted = ev;
+            if (nfin > 0) {
+                // hand the fit to a finisher CTA (the partial rows were released by the ticket atomics)
+                if (tid == 0) {
+                    const unsigned long long base = atomicAdd(&ctl->ftail, 1ull);
+                    QueueItem *it = &ctl->fitems[base % ctl->fcap];
+                    it->fit = k;
+                    it->chunk = -1;
+                    __threadfence();
+                    st_release_gpu_u64(&it->seq, base + 1ull);
                 }
-                if (fd->evals < 48) {
-                    double *tr = fd->trace + 4 * fd->evals;
-                    tr[0] = sqrt(ev.rnorm2); tr[1] = fd->st.par; tr[2] = fd->st.delta; tr[3] = fd->st.last_accepted;
-                }
-                fd->evals += 1;
-                more_s = more ? 1 : 0;
-            }
-            __syncthreads();
-            for (int i = tid; i < FIT_WORDS; i += THREADS) fw[i] = lw[i];
-            __threadfence();
-            __syncthreads();
-            if (more_s) {
-                start_evaluation(k);
-            } else if (tid == 0) {
-                __threadfence();
-                atomicSub(&ctl->fits_left, 1);
+            } else {
+                finish_evaluation(k);
             }
         }
         __syncthreads();

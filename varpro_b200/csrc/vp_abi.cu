@@ -1592,6 +1592,20 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         hqp[i] = hq[(size_t)i];
     }
     hctl->head = 0; hctl->tail = 0; hctl->fits_left = K; hctl->error = 0; hctl->items = ditems; hctl->cap = cap;
+    // finish queue + dedicated finisher CTAs: OFF by default. Measured (profiles/r02v_queue_phase_breakdown.txt):
+    // 8 finishers cannot keep up with 20-60 fits because one evaluation costs them ~54 us, of which the
+    // single-thread LM step is ~31 us -- the work is slow by itself, not because of a cold instruction cache.
+    QueueItem *dfitems = nullptr;
+    const unsigned int fcap = (unsigned int)K + 64u;
+    int nfin = env_int("VP_QUEUE_FINISHERS", 0);
+    if (nfin > ctx->sm_count / 4) nfin = ctx->sm_count / 4;
+    if (nfin > 0) {
+        if (DEV_ALLOC(ctx, &dfitems, sizeof(QueueItem) * (size_t)fcap) == cudaSuccess)
+            cudaMemsetAsync(dfitems, 0, sizeof(QueueItem) * (size_t)fcap, ctx->stream);
+        else
+            nfin = 0;
+    }
+    hctl->fhead = 0; hctl->ftail = 0; hctl->fitems = dfitems; hctl->fcap = fcap; hctl->nfinishers = nfin;
     unsigned long long *ddbg = nullptr;
     const long long dbg_grid = (long long)ctx->sm_count * occ;
     if (env_int("VP_QUEUE_DBG", 0)) { // per-CTA phase accumulators (diagnostics; printed to stderr after the launch)
@@ -1617,9 +1631,14 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
     if (ddbg && e == cudaSuccess) {
         std::vector<unsigned long long> hd(8 * (size_t)dbg_grid);
         if (cudaMemcpy(hd.data(), ddbg, sizeof(unsigned long long) * hd.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
-            double acc[8] = {0};
+            double acc[8] = {0}, fin[8] = {0};
             for (long long b = 0; b < dbg_grid; ++b)
-                for (int i = 0; i < 8; ++i) acc[i] += (double)hd[(size_t)b * 8 + i];
+                for (int i = 0; i < 8; ++i) (b < nfin ? fin[i] : acc[i]) += (double)hd[(size_t)b * 8 + i];
+            if (nfin > 0 && fin[7] > 0)
+                fprintf(stderr, "[vp queue dbg] %d finisher CTAs, %.0f evaluations started | per evaluation: finalize %.2f us, state load %.2f us, "
+                                "LM step %.2f us, state store %.2f us, x/w + basis %.2f us, basis + factor + panel store %.2f us, push %.2f us\n",
+                        nfin, fin[7], 1e-3 * fin[0] / fin[7], 1e-3 * fin[1] / fin[7], 1e-3 * fin[2] / fin[7], 1e-3 * fin[3] / fin[7],
+                        1e-3 * fin[4] / fin[7], 1e-3 * fin[5] / fin[7], 1e-3 * fin[6] / fin[7]);
             const double it = acc[0] > 0 ? acc[0] : 1, nf = acc[6] > 0 ? acc[6] : 1;
             fprintf(stderr, "[vp queue dbg] fits %d items %.0f (%.1f per CTA) | per item: claim %.2f us, fragments %.2f us, stream %.2f us, "
                             "publish %.2f us | finisher (finalize + LM + panel + push) %.2f us x %.0f | CTA lifetime %.1f us, busy %.1f %%\n",
@@ -1629,6 +1648,7 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         }
     }
     DEV_FREE(ctx, ddbg);
+    DEV_FREE(ctx, dfitems);
     DEV_FREE(ctx, db); DEV_FREE(ctx, ditems);
     if (e != cudaSuccess) { HOST_FREE(ctx, hb); return fail(ctx, VP_ERR_CUDA, std::string("vp_fit_many (queue): ") + cudaGetErrorString(e)); }
     if (qerr) { HOST_FREE(ctx, hb); return fail(ctx, VP_ERR_CUDA, "vp_fit_many: a wait inside the work-queue kernel timed out"); }

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define VP_ABI_VERSION 1
+#define VP_ABI_VERSION 2
 #define VP_MAX_BASIS_PARAMS 4 /* parameters one basis function may depend on */
 #define VP_MAX_N 8            /* basis functions (linear coefficients) */
 #define VP_MAX_Q 8            /* nonlinear parameters */
@@ -112,9 +112,11 @@ typedef enum {
 } vp_termination;
 
 /* LevenbergMarquardt::new().with_*() knobs (src/solvers/levmar/mod.rs:221).
- * A value <= 0 (scale_diag < 0) selects the crate default: ftol = xtol = gtol =
+ * A NEGATIVE value (or NaN) selects the crate default: ftol = xtol = gtol =
  * 30*eps(dtype), stepbound = 100, patience = 100 (maxfev = patience*(q+1)),
- * scale_diag = true. */
+ * scale_diag = true. ftol / xtol / gtol = 0 are legal and pass through (they
+ * disable the respective convergence criterion, as in the crate); stepbound and
+ * patience must be positive, so 0 selects their defaults as well. */
 typedef struct {
     double ftol, xtol, gtol;
     double stepbound;
@@ -157,6 +159,19 @@ const char *vp_last_error(const vp_ctx *ctx);
 int64_t vp_ctx_kernel_launches(const vp_ctx *ctx);
 /* the CUDA stream (cudaStream_t) all work of this context is enqueued on */
 void *vp_ctx_stream(const vp_ctx *ctx);
+/* Tunables of a context (strings; unknown keys / values -> VP_ERR_INVALID_ARGUMENT). Defaults are read from
+ * the environment once, in vp_ctx_create (VP_FIT_MODE, VP_EVAL_KERNEL, ...: the upper-cased key with a VP_
+ * prefix); nothing on the fit path reads the environment. Keys:
+ *   fit_mode        auto (default: persistent kernel / work queue / CUDA-graph loop by availability) | host | graph
+ *   eval_kernel     fused (default) | split (K1 panel kernel + K2 streaming kernel); applies to problems created later
+ *   stream_kernel   auto (default) | simt | generic; applies to problems created later
+ *   panel_generic, stream_stages, stream_ct, stream_occ, queue_items_per_cta, batch_slots, pool_mb,
+ *   max_ctas (integers; max_ctas caps the grid of problems created later so that contexts can share a GPU)
+ *   trace, queue_dbg, dbg_fit (0 | 1: diagnostics on stderr / in-kernel timelines) */
+int vp_ctx_set_option(vp_ctx *ctx, const char *key, const char *value);
+/* Return the context's idle cached device / pinned buffers to the CUDA allocator (the cache is capped at
+ * pool_mb, default 1024 MiB; co-resident frameworks may want the memory back). Synchronises the stream. */
+int vp_ctx_trim(vp_ctx *ctx);
 
 /* ---- model: replaces SeparableModel / SeparableNonlinearModel evaluation --
  * (src/model/mod.rs:239-363 trait, :441-512 eval / eval_partial_deriv).
@@ -218,8 +233,10 @@ int vp_best_fit_device(vp_problem *problem, void *out_device);
  * VP_JACOBIAN_KAUFMAN (default) = what the reference implements (src/solvers/levmar/mod.rs:101-201);
  * VP_JACOBIAN_FULL adds the second Golub-Pereyra term the reference leaves as a TODO (:188-190;
  * matlab/varpro.m:696-731): exact derivative of the projected residual, faster convergence on
- * large-residual problems. Costs one more pass over Y per evaluation and uses the host-driven LM
- * loop. Re-evaluates at the current parameters. */
+ * large-residual problems. The fused kernels (fp64 models of the compiled shapes) accumulate the
+ * extra p x p sum in the same single pass over Y, so vp_fit / vp_fit_many / column-sharded fits run
+ * at full speed in either mode; other problems pay one more pass per evaluation and use the
+ * host-driven LM loop. Re-evaluates at the current parameters. */
 enum { VP_JACOBIAN_KAUFMAN = 0, VP_JACOBIAN_FULL = 1 };
 int vp_problem_set_jacobian(vp_problem *problem, int mode);
 /* ||r||^2, J^T r and J^T J of the current parameters without materialising r or J */
@@ -240,11 +257,16 @@ int vp_reduce(vp_problem *problem, vp_reduced *out);
  * Setup: (1) every rank calls vp_comm_create and receives the 64-byte CUDA IPC
  * handle of its mailbox; (2) the host all-gathers the handles in rank order
  * (torch.distributed / MPI / any transport); (3) every rank calls
- * vp_comm_connect with the world*64 bytes. world == 1 needs no connect. */
+ * vp_comm_connect with the world*64 bytes. world == 1 needs no connect.
+ * ONE process driving several GPUs (one context and one host thread per GPU, as a Rust caller would)
+ * skips the IPC handles: create the `world` communicators and pass them in rank order to
+ * vp_comm_connect_local (peer access is enabled between the devices; several contexts on ONE device
+ * work too -- that is how the test-suite exercises world = 2 on a one-GPU box). */
 #define VP_COMM_HANDLE_BYTES 64
 typedef struct vp_comm vp_comm;
 int vp_comm_create(vp_ctx *ctx, int rank, int world, vp_comm **out, void *local_handle_out);
 int vp_comm_connect(vp_comm *comm, const void *all_handles);
+int vp_comm_connect_local(vp_comm **comms_in_rank_order, int world);
 int vp_comm_destroy(vp_comm *comm);
 /* comm == NULL detaches. Re-evaluates at the current parameters (collective). */
 int vp_problem_set_comm(vp_problem *problem, vp_comm *comm);
@@ -254,14 +276,14 @@ int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *rep
 /* Fit n independent problems of one context (throughput mode): what a caller of the reference
  * does in a loop over LevMarSolver::fit (e.g. benches/multiple_right_hand_sides.rs:97-101 per
  * criterion iteration). Like-shaped problems are fitted by ONE persistent kernel whose CTAs take
- * (fit, chunk-of-columns) work items from a device-side queue, so the latency-bound phases of
+ * (fit, group-of-columns) work items from a device-side queue, so the latency-bound phases of
  * one fit (panel, reduction, LM step) overlap the HBM streaming of the others and the load is
- * balanced dynamically. Results are identical to n calls of vp_fit up to the summation order of
- * the partial sums. max_concurrent is only used by the alternative VP_FIT_MANY=streams mode
- * (one persistent kernel per fit on #SMs / min(n, max_concurrent) SMs). reports: n entries.
+ * balanced dynamically. Results are BITWISE those of n calls of vp_fit (same partition of the
+ * columns into partial sums, same fold, same LM code): same parameters, same number of
+ * evaluations. `reserved` is ignored (ABI v1 had a concurrency hint there). reports: n entries.
  * Returns the first error, VP_OK otherwise. */
 int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *options, vp_fit_report *reports,
-                int32_t max_concurrent);
+                int32_t reserved);
 
 /* ---- fit statistics: replaces FitStatistics::try_calculate (src/statistics/mod.rs:352-441) ----
  * The reference computes statistics for a single right-hand side only

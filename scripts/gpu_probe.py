@@ -54,8 +54,8 @@ def dump_timeline(title):
     k2 = t[:-1]
     print(title)
     names = {8: "eval_start", 9: "basis_evaluated", 10: "panel_done", 1: "frags_loaded", 2: "first_tile", 3: "loop_done",
-             4: "publish_begin", 14: "partial_written", 5: "published", 11: "fin_prefetch", 12: "fin_partials",
-             13: "fin_assembled", 7: "before_lm", 15: "lm_step_done", 6: "released/acquired"}
+             4: "publish_begin", 14: "counted_in", 5: "all_arrived", 12: "rows_folded", 13: "assembled",
+             15: "lm_step_done(t0)", 6: "evaluation_end"}
     for i, nm in names.items():
         col = k2[:, i][k2[:, i] >= 0]
         if len(col):
@@ -63,7 +63,7 @@ def dump_timeline(title):
 
 
 if os.environ.get("FIT_TIMELINE"):
-    os.environ["VP_DBG_FIT"] = "1"
+    vb.set_option("dbg_fit", 1)
     gp.set_params(wl["alpha0"])
     res = vb.LevMarSolver.default().fit(gp)
     dump_timeline("persistent fit, last evaluation (ns relative to the earliest stamp):")

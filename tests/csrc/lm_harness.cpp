@@ -10,6 +10,7 @@ using namespace vp;
 struct Harness {
     LmState st;
     LmConfig cfg;
+    int generic = 0; // 1: force the run-time-q instantiation (lm_advance_generic) instead of the q-specialised one
 };
 
 extern "C" {
@@ -32,8 +33,12 @@ int lmh_advance(Harness *h, double rnorm2, const double *g, const double *H /* q
     ev.rnorm2 = rnorm2; ev.finite = finite;
     for (int k = 0; k < q; ++k) ev.g[k] = g[k];
     for (int i = 0; i < q * q; ++i) ev.H[i] = H[i];
-    return lm_advance(h->st, h->cfg, ev) ? 1 : 0;
+    return (h->generic ? lm_advance_generic(h->st, h->cfg, ev) : lm_advance(h->st, h->cfg, ev)) ? 1 : 0;
 }
+void lmh_set_generic(Harness *h, int on) { h->generic = on; }
+// raw state words (bitwise comparison of the specialised and the generic instantiation)
+int lmh_state_bytes(void) { return (int)sizeof(LmState); }
+void lmh_state(const Harness *h, void *out) { std::memcpy(out, &h->st, sizeof(LmState)); }
 void lmh_trial(const Harness *h, double *x) { for (int k = 0; k < h->st.q; ++k) x[k] = h->st.x_trial[k]; }
 void lmh_accepted(const Harness *h, double *x) { for (int k = 0; k < h->st.q; ++k) x[k] = h->st.x[k]; }
 int lmh_termination(const Harness *h) { return h->st.termination; }

@@ -37,6 +37,9 @@ def lib():
         for n in ("lmh_fnorm", "lmh_par", "lmh_delta"):
             getattr(L, n).argtypes = [C.c_void_p]
             getattr(L, n).restype = C.c_double
+        L.lmh_set_generic.argtypes = [C.c_void_p, C.c_int]
+        L.lmh_state_bytes.restype = C.c_int
+        L.lmh_state.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -46,12 +49,14 @@ def _dp(a):
 
 
 class LmHarness:
-    def __init__(self, x0, ftol=None, xtol=None, gtol=None, stepbound=100.0, patience=100, scale_diag=True):
+    def __init__(self, x0, ftol=None, xtol=None, gtol=None, stepbound=100.0, patience=100, scale_diag=True, generic=False):
         eps = np.finfo(np.float64).eps
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         self.q = len(x0)
         self._h = lib().lmh_new(self.q, _dp(x0), ftol or 30 * eps, xtol or 30 * eps, gtol or 30 * eps, stepbound,
                                 patience * (self.q + 1), int(scale_diag), eps)
+        if generic:
+            lib().lmh_set_generic(self._h, 1)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -71,6 +76,12 @@ class LmHarness:
         x = np.empty(self.q)
         lib().lmh_accepted(self._h, _dp(x))
         return x
+
+    def state_bytes(self):
+        """The raw LmState (bitwise comparison of the q-specialised and the generic instantiation)."""
+        buf = C.create_string_buffer(lib().lmh_state_bytes())
+        lib().lmh_state(self._h, buf)
+        return buf.raw
 
     termination = property(lambda self: lib().lmh_termination(self._h))
     nfev = property(lambda self: lib().lmh_nfev(self._h))

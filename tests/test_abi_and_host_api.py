@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/varpro_b200.h but not exported"
     assert set(declared) == set(_lib.SYMBOLS), "ctypes table and header disagree"
-    assert lib.vp_abi_version() == 1
+    assert lib.vp_abi_version() == 2
     assert lib.vp_status_string(3).decode() == "x or y must have nonzero number of elements"
 
 
@@ -42,8 +42,7 @@ def test_product_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("the oracle", "").lower() or f == "api.py" and False, \
-                    f"{f} mentions the oracle directory"
+                assert "oracle" not in src.replace("the oracle", "").lower(), f"{f} mentions the oracle directory"
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -185,10 +185,25 @@ def test_c2_full_size_properties():
     assert np.max(np.abs(R2 - R1)) <= 1e-9 * np.abs(Y[:, :128]).max()
 
 
-def test_generic_kernel_matches_fast_kernel(monkeypatch):
+@pytest.fixture
+def ctx_options():
+    """Set tunables of the default context for one test (vp_ctx_set_option) and restore the defaults."""
+    import varpro_b200 as vb
+    defaults = {"fit_mode": "auto", "eval_kernel": "fused", "stream_kernel": "auto", "panel_generic": 0, "max_ctas": 0}
+    touched = []
+
+    def set_option(key, value, slot=0):
+        touched.append((key, slot))
+        vb.set_option(key, value, slot=slot)
+    yield set_option
+    for key, slot in touched:
+        vb.set_option(key, defaults[key], slot=slot)
+
+
+def test_generic_kernel_matches_fast_kernel(ctx_options):
     wl = W.c2(S=40)
     fast = W.make_gpu_problem(wl)
-    monkeypatch.setenv("VP_STREAM_GENERIC", "1")
+    ctx_options("stream_kernel", "generic")
     gen = W.make_gpu_problem(wl)
     rf, rg = fast.reduce(), gen.reduce()
     assert abs(rf["rnorm2"] - rg["rnorm2"]) <= 1e-10 * rf["rnorm2"]
@@ -223,13 +238,13 @@ def test_nonfinite_parameters_give_none_and_numerical_termination():
     assert not ei.value.result.was_successful()
 
 
-def test_fused_kernel_matches_split_kernels(monkeypatch):
+def test_fused_kernel_matches_split_kernels(ctx_options):
     """fit_kernel_dmma (panel fused into the streaming pass) against K1 + K2 launched separately."""
     wl = W.c2(S=200)
     fused = W.make_gpu_problem(wl)
-    monkeypatch.setenv("VP_EVAL_KERNEL", "split")
+    ctx_options("eval_kernel", "split")
     split = W.make_gpu_problem(wl)
-    monkeypatch.delenv("VP_EVAL_KERNEL")
+    ctx_options("eval_kernel", "fused")
     for alpha in ([2.0, 6.5], [1.1, 2.9]):
         fused.set_params(alpha)
         split.set_params(alpha)
@@ -241,15 +256,15 @@ def test_fused_kernel_matches_split_kernels(monkeypatch):
         assert np.max(np.abs(Cf - Cs)) <= 1e-12 * np.abs(Cs).max()
 
 
-@pytest.mark.parametrize("mode", ["persistent", "graph", "host"])
-def test_fit_modes_agree(monkeypatch, mode):
-    """The persistent whole-fit kernel, the CUDA-graph loop and the host-driven loop run the same
-    lmder state machine on the same reductions."""
+@pytest.mark.parametrize("mode", ["auto", "graph", "host"])
+def test_fit_modes_agree(ctx_options, mode):
+    """The persistent whole-fit kernel (auto), the CUDA-graph loop (the driver of model shapes without a fused
+    kernel) and the host-driven loop run the same lmder state machine on the same reductions."""
     import varpro_b200 as vb
     wl = W.c2(S=96)
-    monkeypatch.setenv("VP_FIT_MODE", mode)
-    if mode != "persistent":
-        monkeypatch.setenv("VP_EVAL_KERNEL", "split")
+    ctx_options("fit_mode", mode)
+    if mode != "auto":
+        ctx_options("eval_kernel", "split")
     gp = W.make_gpu_problem(wl)
     res = vb.LevMarSolver.default().fit(gp)
     assert res.was_successful()
@@ -279,12 +294,9 @@ def test_sharded_fit_world1_exercises_the_mailbox_protocol():
     comm.close()
 
 
-@pytest.mark.parametrize("many_mode", ["queue", "streams"])
-def test_fit_many_equals_sequential_fits(monkeypatch, many_mode):
-    """vp_fit_many against one vp_fit per problem: the work-queue kernel (all SMs serve all fits, default)
-    and the per-fit persistent kernels on SM slices (VP_FIT_MANY=streams)."""
+def test_fit_many_equals_sequential_fits():
+    """vp_fit_many (work-queue kernel: all SMs serve all fits) against one vp_fit per problem."""
     import varpro_b200 as vb
-    monkeypatch.setenv("VP_FIT_MANY", many_mode)
     solver = vb.LevMarSolver.default()
     wls = [W.c2(S=64 + 8 * k, seed=100 + k) for k in range(6)] + [W.mrhs20(3), W.lmfit_case(True)]
     seq = [solver.fit(W.make_gpu_problem(wl)) for wl in wls]
@@ -302,6 +314,35 @@ def test_fit_many_equals_sequential_fits(monkeypatch, many_mode):
     res = solver.fit_many([W.make_gpu_problem(wl) for _ in range(200)])
     assert all(r.was_successful() for r in res)
     assert all(np.allclose(np.sort(r.nonlinear_parameters()), [1.0, 3.0], atol=1e-8) for r in res)
+
+
+@pytest.mark.parametrize("items_per_cta", [1, 2, 5])
+def test_fit_many_is_bitwise_vp_fit(ctx_options, items_per_cta):
+    """The work-queue kernel folds the same canonical parts in the same order as the persistent fit kernel and runs
+    the same LM code: identical parameters, coefficients, objective and evaluation counts, whatever the work-item
+    size -- on the noise-free benchmark data too, where rounding decides the last LM steps."""
+    import varpro_b200 as vb
+    vb.set_option("queue_items_per_cta", items_per_cta)
+    try:
+        solver = vb.LevMarSolver.default()
+        rng = np.random.default_rng(5)
+        wls = [W.c2(S=1500 + 40 * k, seed=300 + k) for k in range(5)]
+        for k, wl in enumerate(wls[1:], 1):  # different truths / noise => different LM paths and evaluation counts
+            x = wl["x"]
+            tau = (1.0 + 0.2 * k, 3.0 + 0.5 * k)
+            Phi = np.stack([np.exp(-x / tau[0]), np.exp(-x / tau[1]), np.ones_like(x)], axis=1)
+            wl["Y"] = np.asfortranarray(Phi @ wl["C_true"] + (1e-3 * k) * rng.standard_normal((x.shape[0], wl["Y"].shape[1])))
+        seq = [solver.fit(W.make_gpu_problem(wl)) for wl in wls]
+        many = solver.fit_many([W.make_gpu_problem(wl) for wl in wls])
+        assert len({r.minimization_report.number_of_evaluations for r in seq}) > 1
+        for a, b in zip(seq, many):
+            assert a.was_successful() and b.was_successful()
+            assert np.array_equal(a.nonlinear_parameters(), b.nonlinear_parameters())
+            assert a.minimization_report.number_of_evaluations == b.minimization_report.number_of_evaluations
+            assert a.minimization_report.objective_function == b.minimization_report.objective_function
+            assert np.array_equal(a.linear_coefficients(), b.linear_coefficients())
+    finally:
+        vb.set_option("queue_items_per_cta", 2)
 
 
 # fp32 (BASELINE config 4). The reference is generic over the scalar but no reference test runs an f32

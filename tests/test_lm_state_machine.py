@@ -60,3 +60,25 @@ def test_rank_deficient_normal_matrix_is_handled():
     assert hh.advance(10.0, g, H, finite=True)
     t = hh.trial()
     assert np.all(np.isfinite(t)) and t[1] == 2.0 and abs(t[0] - 0.5) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["c1", "lmfit_w", "oleary", "c2_16"])
+def test_q_specialised_step_is_bitwise_the_generic_step(name):
+    """lm_step.cuh runs q = 1..4 on register-resident, fully unrolled instantiations and q > 4 on the
+    run-time-indexed one: same floating-point operations in the same order => identical state words
+    after every evaluation."""
+    wl = {"c1": W.c1, "lmfit_w": lambda: W.lmfit_case(True), "oleary": W.oleary, "c2_16": lambda: W.c2(S=16)}[name]()
+    op = W.make_oracle(wl)
+    a = LH.LmHarness(wl["alpha0"])
+    b = LH.LmHarness(wl["alpha0"], generic=True)
+    x = np.asarray(wl["alpha0"], dtype=np.float64)
+    more, steps = True, 0
+    while more:
+        assert op.set_params(x)
+        r, J = op.residuals(), op.jacobian()
+        more = a.advance(r @ r, J.T @ r, J.T @ J)
+        assert b.advance(r @ r, J.T @ r, J.T @ J) == more
+        assert a.state_bytes() == b.state_bytes(), f"states differ after evaluation {steps + 1}"
+        x = a.trial()
+        steps += 1
+    assert steps >= 5 and a.termination in (2, 3, 4, 5, 6)

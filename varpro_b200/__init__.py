@@ -6,7 +6,7 @@ from .api import (  # noqa: F401
     BatchFitResult, Constant, ExpDecay, ExpRateCos, FitError, FitResult, FitStatistics, HostFunction, IndependentBatch, LevenbergMarquardt, LevMarSolver, LinearX,
     MinimizationReport, ModelBuildError, ModelError, SeparableModel, SeparableModelBuilder,
     SeparableProblem, SeparableProblemBuilder, SeparableProblemBuilderError, SinPhase,
-    TerminationReason, VarproError, kernel_launches,
+    TerminationReason, VarproError, kernel_launches, set_option,
 )
 
 __all__ = [n for n in dir() if not n.startswith("_")]

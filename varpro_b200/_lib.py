@@ -55,6 +55,8 @@ SYMBOLS = {
     "vp_last_error": (C.c_char_p, [_vp]),
     "vp_ctx_kernel_launches": (C.c_int64, [_vp]),
     "vp_ctx_stream": (C.c_void_p, [_vp]),
+    "vp_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "vp_ctx_trim": (C.c_int, [_vp]),
     "vp_model_create": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, C.c_int32, C.c_int32,
                                   C.POINTER(BasisDesc), _pp]),
     "vp_model_create_hosteval": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
@@ -76,6 +78,7 @@ SYMBOLS = {
     "vp_reduce": (C.c_int, [_vp, C.POINTER(Reduced)]),
     "vp_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _pp, _vp]),
     "vp_comm_connect": (C.c_int, [_vp, _vp]),
+    "vp_comm_connect_local": (C.c_int, [_pp, C.c_int]),
     "vp_comm_destroy": (C.c_int, [_vp]),
     "vp_problem_set_comm": (C.c_int, [_vp, _vp]),
     "vp_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),

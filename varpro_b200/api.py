@@ -221,8 +221,21 @@ class _Ctx:
     def kernel_launches(self) -> int:
         return int(_lib.load().vp_ctx_kernel_launches(self.h))
 
+    def set_option(self, key: str, value) -> None:
+        """vp_ctx_set_option: tunables of this context (see include/varpro_b200.h)."""
+        _check(_lib.load().vp_ctx_set_option(self.h, str(key).encode(), str(value).encode()), self.h)
+
+    def trim(self) -> None:
+        """vp_ctx_trim: hand the idle cached buffers back to the CUDA allocator."""
+        _check(_lib.load().vp_ctx_trim(self.h), self.h)
+
     def stream(self) -> int:
         return int(_lib.load().vp_ctx_stream(self.h) or 0)
+
+
+def set_option(key: str, value, device: int = 0, slot: int = 0) -> None:
+    """Set a tunable of the (device, slot) context, e.g. set_option("fit_mode", "host")."""
+    _Ctx.get(device, slot).set_option(key, value)
 
 
 def kernel_launches(device: int = 0) -> int:
@@ -664,10 +677,12 @@ class MinimizationReport:
 
 
 class LevenbergMarquardt:
-    """Option holder with the levenberg-marquardt crate's builder knobs (0 => crate default)."""
+    """Option holder with the levenberg-marquardt crate's builder knobs. Unset knobs are passed as -1 (= crate
+    default: ftol = xtol = gtol = 30 eps, stepbound 100, patience 100, scale_diag on); a tolerance of 0 is a legal
+    value and disables that criterion, as in the crate."""
 
     def __init__(self):
-        self._o = _lib.LmOptions(0.0, 0.0, 0.0, 0.0, 0, -1)
+        self._o = _lib.LmOptions(-1.0, -1.0, -1.0, -1.0, -1, -1)
 
     @classmethod
     def new(cls):
@@ -800,10 +815,11 @@ class LevMarSolver:
         return result, (st[0] if problem.single_rhs else st)
 
     def fit_many(self, problems: Sequence[SeparableProblem], max_concurrent: int = 0) -> List[FitResult]:
-        """Fit independent problems concurrently (vp_fit_many): the loop a caller of the reference
-        writes around LevMarSolver::fit, executed as concurrent persistent kernels on slices of the
-        SMs. Returns one FitResult per problem in order; unsuccessful fits are returned (not raised)
-        -- check `was_successful()` as with the reference's Err(FitResult)."""
+        """Fit independent problems together (vp_fit_many): the loop a caller of the reference writes around
+        LevMarSolver::fit, executed by ONE persistent kernel whose CTAs take (fit, group-of-columns) work items
+        from a device-side queue. Results are bitwise those of `fit` per problem. Returns one FitResult per
+        problem in order; unsuccessful fits are returned (not raised) -- check `was_successful()` as with the
+        reference's Err(FitResult). `max_concurrent` is ignored (kept for callers of the first ABI version)."""
         problems = list(problems)
         if not problems:
             return []

@@ -2,7 +2,7 @@
 
 The templated kernels are instantiated in separate translation units (csrc/inst.cu compiled once
 per entry of VP_KERNEL_GROUPS in csrc/kernel_tables.h) which are built in parallel and linked with
-the host side (csrc/vp_abi.cu) into libvarpro_b200.so. Objects go to gpurun_out/_obj/ (scratch: git-ignored,
+the host side (csrc/vp_*.cu) into libvarpro_b200.so. Objects go to gpurun_out/_obj/ (scratch: git-ignored,
 never shipped) and are reused when neither their source, nor a header, nor the flags changed; the .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 nvcc cross-compiles without a GPU.
 """
@@ -23,7 +23,9 @@ HEADER = os.path.join(HERE, "..", "include", "varpro_b200.h")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
-LINK_LIBS: list[str] = []
+LINK_LIBS: list[str] = ["-ldl"]  # NVTX v3 is header-only and dlopens its injection library
+# host side of the C ABI (see csrc/vp_internal.h)
+HOST_UNITS = ["vp_ctx", "vp_problem", "vp_fit", "vp_batch", "vp_diag"]
 
 
 def _groups():
@@ -37,7 +39,7 @@ def _deps():
 
 def _units():
     """(object path, source, extra flags) of every translation unit."""
-    units = [(os.path.join(OBJ, "vp_abi.o"), os.path.join(CSRC, "vp_abi.cu"), [])]
+    units = [(os.path.join(OBJ, f"{u}.o"), os.path.join(CSRC, f"{u}.cu"), []) for u in HOST_UNITS]
     for tag, ctype, dt, n, p, part in _groups():
         variant = re.search(r"(\d+)$", tag)
         flags = [f"-DVP_INST_TAG={tag}", f"-DVP_INST_T={ctype}", f"-DVP_INST_DT={dt}", f"-DVP_INST_N={n}",

@@ -7,19 +7,23 @@
 //   repeat
 //     every CTA : panel at the trial parameters (Phi_w, D, Householder QR, E = P_perp D, M, R1^-1)
 //                 redundantly in its own registers / shared memory        [K1 without HBM round trip]
-//                 -> DMMA A-fragments -> stream its share of the Y tiles   [K2]
-//                 -> publish the CTA partial, take a ticket
-//     last CTA  : fold the partials in a fixed order -> (||r||^2, g, H)
-//                 -> (multi-GPU: exchange with the peer GPUs over NVLink, see vp_comm)
-//                 -> advance the lmder state machine (lm_step.cuh) -> broadcast (x_trial, more)
-//     other CTAs: spin on the generation flag (acquire), with the first tiles of the next
-//                 evaluation already in flight (Y does not depend on alpha)
-//   until the state machine terminates
+//                 -> DMMA A-fragments -> stream its part of the Y tiles    [K2, dmma_tile.cuh]
+//                 -> publish the part's partial row, count itself in (one atomic)
+//                 -> wait until every CTA is in, fold ALL partial rows in a fixed order
+//                    -> (||r||^2, g, H)      [multi-GPU: the last CTA in sends this GPU's sums to
+//                    the peers over NVLink; every CTA sums the mailbox slots in rank order]
+//                 -> advance its own shared-memory copy of the lmder state machine (lm_step.cuh)
+//   until the state machine terminates; CTA 0 writes the final state back.
+//
+// Every CTA computes the same sums in the same order, so all copies of the LM state take the same
+// decisions: no broadcast hop, no state round trip through HBM, and the only grid-wide
+// communication per evaluation is the partial rows + one counter. (Round 1 had the last CTA fold,
+// step and broadcast: ~6 us more per evaluation.) While a CTA waits, the first tiles of the next
+// evaluation are already in flight (Y does not depend on alpha).
 //
 // Why: a C2 evaluation streams 33.5 MB in ~4 us but the two-kernel graph loop costs ~48 us per
 // evaluation (K1 12 us on ONE SM while 147 idle, launch gaps, conditional-node relaunch;
-// profiles/r01a_timeline_c2.txt). Fusing removes every launch from the loop; the panel costs
-// each CTA a few microseconds of latency that overlap the initial tile prefetch.
+// profiles/r01a_timeline_c2.txt). Fusing removes every launch from the loop.
 // Reference mapping: the loop body is impl LeastSquaresProblem for SeparableProblem
 // (src/solvers/levmar/mod.rs:42-201) and the loop itself LevenbergMarquardt::minimize (:247).
 //
@@ -27,26 +31,23 @@
 // grid-wide wait (ordinary launch) -- used by set_params / problem creation / profiling.
 #pragma once
 
+#include "dmma_tile.cuh"
 #include "panel_kernel_hh.cuh"
-#include "stream_kernel_dmma.cuh"
 
 namespace vp {
 
-// what the last CTA broadcasts to the grid after every evaluation of a fit
-struct FitBcast {
-    double x_trial[VP_MAX_Q];
-    int more;         // 1: another evaluation follows
-    int cdst;         // coefficient buffer the next evaluation writes
-    unsigned int gen; // evaluation e publishes gen = e + 1
-    int error;        // 1: a grid-wide wait timed out (should never happen on a co-resident grid)
+// grid-wide control words of one fit launch (device memory, zeroed by the host before the launch)
+struct FitCtl {
+    unsigned int arrived; // partial rows published so far, counted over all evaluations of the launch
+    int error;            // 1: a grid-wide wait timed out (should never happen on a co-resident grid)
 };
 
 // One-shot all-to-all exchange of the reduced vector between the GPUs of a column-sharded
 // global fit (vp_comm): rank r stores its contribution into slot r of every peer's mailbox
-// through NVLink peer mappings and then a flag; each rank sums the W slots in rank order, so all
-// ranks obtain bitwise identical sums and the replicated LM step stays in lock step.
+// through NVLink peer mappings and then a flag; every CTA of every rank sums the W slots in rank
+// order, so all ranks obtain bitwise identical sums and the replicated LM step stays in lock step.
 constexpr int COMM_MAX_WORLD = 8;
-constexpr int COMM_SLOT_DOUBLES = 80; // >= 1 + VP_MAX_Q + VP_MAX_Q^2 (rnorm2, g, H) + nonfinite
+constexpr int COMM_SLOT_DOUBLES = 80; // >= fused_red_count(n, p) + 1 for every instantiated shape
 struct CommMailbox { // lives in this rank's HBM, mapped into every peer
     double slot[2][COMM_MAX_WORLD][COMM_SLOT_DOUBLES];
     unsigned long long flag[2][COMM_MAX_WORLD];
@@ -64,8 +65,9 @@ struct FitArgs {
     const double *w; // m weights or nullptr
     double svd_eps;
     const double *alpha_dev; // parameters of the first evaluation
-    FitBcast *bc;            // fit mode only
+    FitCtl *ctl;             // fit mode only
     CommArgs comm;           // comm.world == 0: no communicator
+    int jac_full;            // 1: add the second Golub-Pereyra term to J^T J (vp_problem_set_jacobian)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
@@ -77,6 +79,12 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p
 __device__ __forceinline__ void st_release_gpu_u32(unsigned int *p, unsigned int v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu_u32(unsigned int *p, unsigned int v)
+{
+    unsigned int prev;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(prev) : "l"(p), "r"(v) : "memory");
+    return prev;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
 {
@@ -95,16 +103,12 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 
 constexpr unsigned long long SPIN_TIMEOUT_NS = 4000000000ull; // 4 s: a dead peer / lost CTA must not hang the GPU
 
-// Sum `vals[0..nv)` (shared memory, this rank's contribution) over all ranks; executed by the
-// whole CTA; on return vals holds the global sums (identical bits on every rank). Returns 0 on
-// success, 1 on timeout.
-__device__ __forceinline__ int comm_allreduce(const CommArgs &c, double *vals, int nv, int *flag_s)
+// Send `vals[0..nv)` (shared memory, this rank's contribution to exchange number `ep`) to every rank's
+// mailbox. Executed by ONE whole CTA per rank.
+__device__ __forceinline__ void comm_send(const CommArgs &c, const double *vals, const int nv, const unsigned long long ep)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int W = c.world;
-    const unsigned long long ep = *c.epoch + 1; // same on every rank: all ranks make the same sequence of evaluations
-    const int par = (int)(ep & 1ull);
-    __syncthreads();
+    const int W = c.world, par = (int)(ep & 1ull);
     for (int idx = tid; idx < W * nv; idx += nt) {
         const int r = idx / nv, k = idx - r * nv;
         c.box[r]->slot[par][c.rank][k] = vals[k];
@@ -112,6 +116,13 @@ __device__ __forceinline__ int comm_allreduce(const CommArgs &c, double *vals, i
     __threadfence_system();
     __syncthreads();
     if (tid < W) st_release_sys_u64(&c.box[tid]->flag[par][c.rank], ep);
+}
+// Wait for the W contributions to exchange `ep` in this rank's own mailbox and sum them in rank order
+// into vals[0..nv) (shared memory). Executed by whole CTAs (any number per rank). Returns 1 on timeout.
+__device__ __forceinline__ int comm_recv(const CommArgs &c, double *vals, const int nv, const unsigned long long ep, int *flag_s)
+{
+    const int tid = threadIdx.x;
+    const int W = c.world, par = (int)(ep & 1ull);
     if (tid == 0) *flag_s = 0;
     __syncthreads();
     if (tid < W) {
@@ -129,12 +140,95 @@ __device__ __forceinline__ int comm_allreduce(const CommArgs &c, double *vals, i
         for (int r = 0; r < W; ++r) s += __ldcv(&mine->slot[par][r][tid]);
         vals[tid] = s;
     }
-    if (tid == 0) {
-        *c.epoch = ep;
-        if (timed_out) *c.error = 1;
-    }
     __syncthreads();
     return timed_out;
+}
+
+// Sum nv values over the nrows partial rows (written by other CTAs: ld.global.cg) into sh[0..nv).
+// 16 threads per value: thread (k = tid%16, c0 = tid/16) sums value k over the rows c0, c0 + nt/16, ...
+// with four independent accumulators (loads in flight together); the 16-column table is then folded
+// in a fixed order => bitwise reproducible for a given partition. scratch: >= 16 * (nt/16) doubles.
+__device__ __forceinline__ void fold_rows(const double *rows, const int rs, const int nrows, const int nv, double *sh, double *scratch)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int k = tid & 15, c0 = tid >> 4, nc0 = nt >> 4;
+#pragma unroll 1
+    for (int base = 0; base < nv; base += 16) {
+        double s = 0.0;
+        if (base + k < nv) {
+            const double *src = rows + base + k;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int c = c0;
+            for (; c + 3 * nc0 < nrows; c += 4 * nc0) {
+                const double l0 = __ldcg(src + (size_t)c * rs), l1 = __ldcg(src + (size_t)(c + nc0) * rs);
+                const double l2 = __ldcg(src + (size_t)(c + 2 * nc0) * rs), l3 = __ldcg(src + (size_t)(c + 3 * nc0) * rs);
+                s0 += l0; s1 += l1; s2 += l2; s3 += l3;
+            }
+            for (; c < nrows; c += nc0) s0 += __ldcg(src + (size_t)c * rs);
+            s = (s0 + s1) + (s2 + s3);
+        }
+        scratch[c0 * 16 + k] = s;
+        __syncthreads();
+        if (tid < 16 && base + tid < nv) {
+            double t = 0.0;
+            for (int c = 0; c < nc0; ++c) t += scratch[c * 16 + tid];
+            sh[base + tid] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// (||r||^2, G, V, U) sums in sh -> the evaluation (rnorm2, g = J^T r, H = J^T J) in *ev (shared memory):
+//   g_k = -(sum_{e in k} V_e),   H_kl = sum_{e in k, f in l} M_ef G_{j(e) j(f)}   [Kaufman]
+//   jac_full:  H_kl += sum_{e in k, f in l} (R1^-1 R1^-T)_{j(e) j(f)} U_ef        [Golub-Pereyra]
+// One thread per entry of g and of the lower triangle of H. Msh: E^T E (ld ldm); rinv: Rinv (n x n, ld N).
+template <int N, int P>
+__device__ __forceinline__ void fused_assemble(const double *sh, const double *Msh, const int ldm, const double *rinv,
+                                               const int *e_basis, const int *e_param, const int q, const int jac_full,
+                                               const int nonfinite, LmEval *ev)
+{
+    constexpr int NG = N * (N + 1) / 2;
+    const int tid = threadIdx.x;
+    int ok = 1;
+    if (tid == 0) {
+        ev->rnorm2 = sh[0];
+        ok = isfinite(sh[0]) && !nonfinite;
+    }
+    if (tid >= 32 && tid < 32 + q) {
+        const int kk = tid - 32;
+        double gk = 0.0;
+        for (int e = 0; e < P; ++e)
+            if (e_param[e] == kk) gk -= sh[1 + NG + e];
+        ev->g[kk] = gk;
+        ok = isfinite(gk);
+    }
+    if (tid >= 64 && tid < 64 + q * q) {
+        const int kk = (tid - 64) / q, l = (tid - 64) % q;
+        if (l <= kk) {
+            double h = 0.0;
+            for (int e = 0; e < P; ++e) {
+                if (e_param[e] != kk) continue;
+                for (int f = 0; f < P; ++f) {
+                    if (e_param[f] != l) continue;
+                    int i = e_basis[e], j = e_basis[f];
+                    if (i > j) { const int t = i; i = j; j = t; }
+                    h += Msh[f * ldm + e] * sh[g_index(N, i, j)];
+                    if (jac_full) {
+                        double wij = 0.0;
+                        for (int c = 0; c < N; ++c) wij += rinv[c * N + i] * rinv[c * N + j];
+                        const int e1 = e < f ? e : f, f1 = e < f ? f : e;
+                        h += wij * sh[1 + NG + P + e1 * P - e1 * (e1 - 1) / 2 + (f1 - e1)];
+                    }
+                }
+            }
+            ev->H[l * q + kk] = h;
+            ev->H[kk * q + l] = h;
+            ok = isfinite(h);
+        }
+    }
+    ok = __syncthreads_and(ok);
+    if (tid == 0) ev->finite = ok;
+    __syncthreads();
 }
 
 // Weighted basis functions and derivative columns of this thread's rows, evaluated through a
@@ -225,24 +319,28 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
     constexpr int PROWS = 4 * KSTEPS * NWARPS;
     constexpr int RPT = PROWS / THREADS; // panel rows per thread
     constexpr int KMAX = (NPV > 8) ? NPV : 8;
+    constexpr int NGPU = TileAcc<N, P>::NG + P + TileAcc<N, P>::NU;
     static_assert(NPV + 1 <= CT && N <= 4, "one DMMA row block / k block only; panel + zero column fit one stage");
     static_assert(KSTEPS % 8 == 0, "whole panel rows per thread");
-    static_assert(THREADS >= 64 + VP_MAX_Q, "panel_hh_body's small-output writers");
+    static_assert(THREADS >= 64 + VP_MAX_Q * VP_MAX_Q, "fused_assemble / panel_hh_body's small-output writers");
+    static_assert(1 + NGPU + 1 <= COMM_SLOT_DOUBLES, "mailbox slot too small");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STREAM_MAX_STAGES];
     __shared__ __align__(16) double part[NWARPS * 64];
     __shared__ __align__(16) double bu[64]; // bu[dot*8 + col]
     __shared__ double rinv_s[N * N];
-    __shared__ double fin_scratch[FIN_SCRATCH];
+    __shared__ double fold_scratch[16 * (THREADS / 16)];
     __shared__ double wsum_s[NWARPS];
-    __shared__ double gv_s[DMMA_CT * (N * (N + 1) / 2 + P)];
-    __shared__ double fin_sh[COMM_SLOT_DOUBLES];
+    __shared__ double gv_s[CT * NGPU];
+    __shared__ double sums_s[COMM_SLOT_DOUBLES];
     __shared__ double red[2][NWARPS * KMAX];
     __shared__ double top[N][NPV];
     __shared__ double alpha_s[VP_MAX_Q];
     __shared__ PanelSmall small_s;
-    __shared__ int is_last, ctrl_more, ctrl_cdst, flag_s;
+    __shared__ LmEval ev_s;
+    __shared__ __align__(8) FitDevice fd_s; // this CTA's copy of the LM state (fit mode)
+    __shared__ int is_last, ctrl_more, flag_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = lane >> 2, tig = lane & 3; // mma "groupID" and "threadID_in_group"
@@ -250,16 +348,16 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
     const size_t stage_elems = (size_t)CT * lds;
     double *tiles = reinterpret_cast<double *>(smem_raw);
     const bool fit_mode = a.fit != nullptr;
-    StreamArgs<double> al = a; // local copy whose `small` points at this CTA's shared-memory panel outputs
-    al.small = &small_s;
+    const int grid = (int)gridDim.x;
 
+    // canonical partition: CTA b owns part b = the contiguous tiles [tile0, tile0 + my)
     const int my = a.tiles_base + ((int)blockIdx.x < a.tiles_rem ? 1 : 0);
+    const int tile0 = (int)blockIdx.x * a.tiles_base + min((int)blockIdx.x, a.tiles_rem);
     dbg_mark(a.dbg, 0);
 
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
-        ctrl_cdst = fit_mode ? (__ldcg(&a.fit->cur) ^ 1) : a.cdst;
         ctrl_more = 0;
     }
     // zero the pad rows [ld, lds) of every column slot (never written by the copies)
@@ -275,14 +373,24 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
         xi[r] = in ? f.x[i] : 0.0;
         wi[r] = in ? (f.w ? f.w[i] : 1.0) : 0.0;
     }
+    // every CTA keeps its own copy of the LM state
+    if (fit_mode) {
+        const unsigned long long *fw = reinterpret_cast<const unsigned long long *>(a.fit);
+        unsigned long long *lw = reinterpret_cast<unsigned long long *>(&fd_s);
+        for (int i = tid; i < FIT_WORDS; i += THREADS) lw[i] = __ldcg(fw + i);
+    }
+    for (int i = tid; i < (int)(sizeof(LmEval) / 8); i += THREADS) reinterpret_cast<unsigned long long *>(&ev_s)[i] = 0ull;
+    const unsigned long long epoch0 = f.comm.world >= 1 ? *f.comm.epoch : 0ull;
+    int ebasis[P > 0 ? P : 1];
+#pragma unroll
+    for (int e2 = 0; e2 < P; ++e2) ebasis[e2] = a.e_basis[e2];
     __syncthreads();
 
     // Producer (see stream_kernel_dmma): column c of a tile is fetched by warp c % NWARPS, lane 0.
     int next_i = 0, next_st = 0;
     const uint32_t col_bytes = (uint32_t)(ld * sizeof(double));
     auto issue = [&]() {
-        const int tile = blockIdx.x + next_i * gridDim.x;
-        const int col0 = tile * CT;
+        const int col0 = (tile0 + next_i) * CT;
         const int nc = min(CT, S - col0);
         if (lane == 0) {
             if (warp == 0) mbar_arrive_expect_tx(&full_bar[next_st], col_bytes * nc);
@@ -301,16 +409,14 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
 
     double *pstage = tiles + (size_t)(nst - 1) * stage_elems;
     uint32_t phase_bits = 0; // bit st: parity of the next completion to wait for on stage st
-    // phase-2 column permutation: mma column n <-> tile column pi(n) = n/2 + 4*(n%2)
-    const int pcol_b = (grp >> 1) + 4 * (grp & 1);
-    const int pcol_c0 = tig, pcol_c1 = tig + 4;
 
     for (unsigned int e = 0;; ++e) {
         // ---- parameters of this evaluation ------------------------------------------------
         if (tid < VP_MAX_Q)
-            alpha_s[tid] = tid < q ? (e == 0 ? __ldcg(&f.alpha_dev[tid]) : __ldcg(&f.bc->x_trial[tid])) : 0.0;
+            alpha_s[tid] = tid < q ? ((e == 0 || !fit_mode) ? __ldcg(&f.alpha_dev[tid]) : fd_s.st.x_trial[tid]) : 0.0;
         __syncthreads();
-        double *Cout = ctrl_cdst ? a.C1 : a.C0;
+        const int cdst = fit_mode ? (fd_s.cur ^ 1) : a.cdst;
+        double *Cout = cdst ? a.C1 : a.C0;
 
         // ---- K1: the panel, in this CTA ---------------------------------------------------
         dbg_mark(a.dbg, 8);
@@ -344,99 +450,21 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
         if (next_i < my) issue();
         dbg_mark(a.dbg, 1);
 
-        // ---- K2: stream this CTA's tiles ----------------------------------------------------
-        double rn2 = 0.0;
-        double Gacc[N * (N + 1) / 2];
-        double Vacc[P > 0 ? P : 1];
-#pragma unroll
-        for (int i = 0; i < N * (N + 1) / 2; ++i) Gacc[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < (P > 0 ? P : 1); ++i) Vacc[i] = 0.0;
-
+        // ---- K2: stream this CTA's part -----------------------------------------------------
+        TileAcc<N, P> acc;
+        acc.clear();
         int st = 0;
         for (int i = 0; i < my; ++i) {
-            const int tile = blockIdx.x + i * gridDim.x;
-            const int col0 = tile * CT;
+            const int col0 = (tile0 + i) * CT;
             const int nc = min(CT, S - col0);
             const double *tp = tiles + (size_t)st * stage_elems;
             mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
             phase_bits ^= 1u << st;
             if (i == 0) dbg_mark(a.dbg, 2);
             if (++st == nst) st = 0;
-
-            // phase 1: C(8 dots x 8 cols) += A1(8 x 4) * Y(4 rows x 8 cols) over the warp's rows
-            {
-                double c[4][2];
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) c[ch][0] = c[ch][1] = 0.0;
-                const double *bp = tp + (size_t)grp * lds + 4 * (warp * KSTEPS) + tig;
-#pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    double b;
-                    if (EXACT) b = bp[4 * ks];
-                    else b = (4 * (warp * KSTEPS + ks) + tig < lds) ? bp[4 * ks] : 0.0;
-                    dmma_8x8x4(c[ks & 3][0], c[ks & 3][1], a1[ks], b);
-                }
-                const double s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
-                const double s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
-                *reinterpret_cast<double2 *>(&part[warp * 64 + grp * 8 + 2 * tig]) = make_double2(s0, s1);
-            }
-            __syncthreads(); // (A) every warp is past phase 2 of the previous tile
-            if (i >= 1 && next_i < my) issue(); // refill the stage tile i-1 used
-            if (tid < 64) {
-                double s = 0.0;
-#pragma unroll
-                for (int w2 = 0; w2 < NWARPS; ++w2) s += part[w2 * 64 + tid];
-                bu[tid] = s;
-            }
-            __syncthreads(); // (B) b_s, u_s of the 8 columns are complete
-
-            // solve: c_s = R1^-1 b_s ; accumulate G and V (one thread per column)
-            if (tid < nc) {
-                double coef[N];
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int c2 = r; c2 < N; ++c2) s += rinv_s[c2 * N + r] * bu[c2 * 8 + tid];
-                    coef[r] = s;
-                    Cout[(size_t)(col0 + tid) * N + r] = s;
-                }
-                int gi = 0;
-#pragma unroll
-                for (int r = 0; r < N; ++r)
-#pragma unroll
-                    for (int c2 = r; c2 < N; ++c2) Gacc[gi++] += coef[r] * coef[c2];
-#pragma unroll
-                for (int e2 = 0; e2 < P; ++e2) {
-                    double cj = 0.0;
-#pragma unroll
-                    for (int r = 0; r < N; ++r) cj = (a.e_basis[e2] == r) ? coef[r] : cj;
-                    Vacc[e2] += cj * bu[(N + e2) * 8 + tid];
-                }
-            }
-
-            // phase 2: R(8 rows x 8 cols) = Y + Q(8 x 4) * (-b)(4 x 8); accumulate r^2
-            {
-                const double b2 = (tig < N) ? -bu[tig * 8 + pcol_b] : 0.0;
-                const double *cp0 = tp + (size_t)pcol_c0 * lds + 8 * (warp * RSTEPS) + grp;
-                const double *cp1 = tp + (size_t)pcol_c1 * lds + 8 * (warp * RSTEPS) + grp;
-                double q0 = 0.0, q1 = 0.0;
-#pragma unroll
-                for (int rs = 0; rs < RSTEPS; ++rs) {
-                    double d0, d1;
-                    if (EXACT) { d0 = cp0[8 * rs]; d1 = cp1[8 * rs]; }
-                    else {
-                        const bool ok = 8 * (warp * RSTEPS + rs) + grp < lds;
-                        d0 = ok ? cp0[8 * rs] : 0.0;
-                        d1 = ok ? cp1[8 * rs] : 0.0;
-                    }
-                    dmma_8x8x4(d0, d1, a2[rs], b2);
-                    q0 = fma(d0, d0, q0);
-                    q1 = fma(d1, d1, q1);
-                }
-                rn2 += (pcol_c0 < nc ? q0 : 0.0) + (pcol_c1 < nc ? q1 : 0.0);
-            }
+            dmma_tile<double, N, P, KSTEPS, NWARPS, EXACT>(tp, lds, nc, col0, a1, a2, rinv_s, part, bu, Cout, ebasis, acc, [&]() {
+                if (i >= 1 && next_i < my) issue(); // refill the stage tile i-1 used
+            });
         }
         dbg_mark(a.dbg, 3);
         __syncthreads(); // every warp is done with every stage
@@ -447,87 +475,108 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
         if (fit_mode)
             for (int i = 0; i < nst - 1 && i < my; ++i) issue();
 
-        // ---- CTA partial -> global; the last CTA folds, steps the LM state machine, broadcasts -----
-        cta_publish_partial<double, N, P, CT, NWARPS>(al, rn2, Gacc, Vacc, wsum_s, gv_s, &is_last);
-        if (is_last) {
-            stream_finalize<double, true, false>(al, N, P, gridDim.x, fin_sh, fin_scratch);
-            __syncthreads();
-            if (f.comm.world >= 1) { // world == 1: exchange with itself (exercises the protocol on one GPU)
-                // fold this GPU's (||r||^2, g, H) with the peers' (all linear in the column sums)
-                const int nv = 2 + q + q * q;
-                if (tid == 0) {
-                    fin_sh[0] = a.out->rnorm2;
-                    for (int k = 0; k < q; ++k) fin_sh[1 + k] = a.out->g[k];
-                    for (int k = 0; k < q * q; ++k) fin_sh[1 + q + k] = a.out->H[k];
-                    fin_sh[1 + q + q * q] = a.out->finite ? 0.0 : 1.0;
-                }
-                comm_allreduce(f.comm, fin_sh, nv, &flag_s);
-                if (tid == 0) {
-                    EvalOut *o = a.out;
-                    o->rnorm2 = fin_sh[0];
-                    for (int k = 0; k < q; ++k) o->g[k] = fin_sh[1 + k];
-                    for (int k = 0; k < q * q; ++k) o->H[k] = fin_sh[1 + q + k];
-                    o->finite = (fin_sh[1 + q + q * q] == 0.0) && isfinite(fin_sh[0]);
-                }
-                __syncthreads();
-            }
-            dbg_mark(a.dbg, 7);
-            if (fit_mode) {
-                // advance the lmder state machine on a shared-memory copy of the state
-                unsigned long long *fw = reinterpret_cast<unsigned long long *>(a.fit);
-                unsigned long long *lw = reinterpret_cast<unsigned long long *>(fin_scratch);
-                for (int i = tid; i < FIT_WORDS; i += THREADS) lw[i] = __ldcg(fw + i);
-                __syncthreads();
-                if (tid == 0) {
-                    FitDevice *fd = reinterpret_cast<FitDevice *>(lw);
-                    LmEval ev;
-                    ev.rnorm2 = a.out->rnorm2;
-                    ev.finite = a.out->finite;
-                    for (int kk = 0; kk < VP_LM_MAXQ; ++kk) ev.g[kk] = kk < q ? a.out->g[kk] : 0.0;
-                    for (int kk = 0; kk < VP_LM_MAXQ * VP_LM_MAXQ; ++kk) ev.H[kk] = kk < q * q ? a.out->H[kk] : 0.0;
-                    const bool more = lm_advance(fd->st, fd->cfg, ev);
-                    if (fd->st.last_accepted) {
-                        fd->cur ^= 1;
-                        fd->accepted = ev;
-                    }
-                    if (fd->evals < 48) {
-                        double *tr = fd->trace + 4 * fd->evals;
-                        tr[0] = sqrt(ev.rnorm2); tr[1] = fd->st.par; tr[2] = fd->st.delta; tr[3] = fd->st.last_accepted;
-                    }
-                    fd->evals += 1;
-                    for (int kk = 0; kk < VP_MAX_Q; ++kk) f.bc->x_trial[kk] = fd->st.x_trial[kk];
-                    f.bc->cdst = fd->cur ^ 1;
-                    f.bc->more = more ? 1 : 0;
-                    ctrl_more = more ? 1 : 0;
-                    ctrl_cdst = fd->cur ^ 1;
-                    dbg_mark(a.dbg, 15);
-                }
-                __syncthreads();
-                for (int i = tid; i < FIT_WORDS; i += THREADS) fw[i] = lw[i];
-                __threadfence();
-                __syncthreads();
-                if (tid == 0) st_release_gpu_u32(&f.bc->gen, e + 1u);
-            }
-            dbg_mark(a.dbg, 6);
-        } else if (fit_mode) {
-            if (tid == 0) {
-                const unsigned long long t0 = global_timer_ns();
-                int ok = 1;
-                while (ld_acquire_gpu_u32(&f.bc->gen) != e + 1u) {
-                    if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) { ok = 0; break; }
-                }
-                dbg_mark(a.dbg, 6);
-                if (ok) {
-                    ctrl_more = __ldcg(&f.bc->more);
-                    ctrl_cdst = __ldcg(&f.bc->cdst);
-                } else {
-                    ctrl_more = 0;
-                    f.bc->error = 1;
-                }
+        // ---- part row -> global (double-buffered by evaluation parity), count this CTA in ------------
+        double *rows = a.partials + (size_t)(fit_mode ? (e & 1u) : 0u) * grid * a.red_stride;
+        dbg_mark(a.dbg, 4);
+        part_stage<N, P, CT, NWARPS>(acc, wsum_s, gv_s);
+        __syncthreads();
+        if (warp == 0) {
+            part_flush<N, P, CT, NWARPS>(wsum_s, gv_s, rows + (size_t)blockIdx.x * a.red_stride, lane);
+            __syncwarp();
+            if (lane == 0) {
+                // release/acquire at gpu scope: orders the row before the count and, in whoever
+                // observes the full count, the count before the reads of everybody's rows
+                const unsigned int prev = atom_add_acq_rel_gpu_u32(fit_mode ? &f.ctl->arrived : a.ticket, 1u);
+                is_last = fit_mode ? (prev == (e + 1u) * (unsigned int)grid - 1u) : (prev == (unsigned int)grid - 1u);
             }
         }
+        dbg_mark(a.dbg, 14);
+        constexpr int NVF = 1 + NGPU; // values of a partial row
+        const bool comm_on = f.comm.world >= 1; // world == 1: exchange with itself (exercises the protocol on one GPU)
+        int timed_out = 0;
+        if (!fit_mode) {
+            __syncthreads();
+            if (!is_last) break;
+            __threadfence();
+        } else if (!comm_on) {
+            if (tid == 0) {
+                const unsigned int want = (e + 1u) * (unsigned int)grid;
+                const unsigned long long t0 = global_timer_ns();
+                int ok = 1;
+                while (ld_acquire_gpu_u32(&f.ctl->arrived) < want) {
+                    if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) { ok = 0; break; }
+                }
+                flag_s = ok ? 0 : 1;
+            }
+            __syncthreads();
+            timed_out = flag_s;
+        } else {
+            __syncthreads();
+        }
+        dbg_mark(a.dbg, 5);
+        // ---- fold: every CTA (fit mode) / the last CTA (single evaluation, or the sender of a sharded fit) ----
+        const bool folds_local = !comm_on || is_last;
+        if (folds_local && !timed_out) {
+            fold_rows(rows, a.red_stride, grid, NVF, sums_s, fold_scratch);
+            if (tid == 0) sums_s[NVF] = small_s.nonfinite ? 1.0 : 0.0;
+            __syncthreads();
+        }
+        if (comm_on) {
+            const unsigned long long ep = epoch0 + e + 1ull;
+            if (is_last) comm_send(f.comm, sums_s, NVF + 1, ep);
+            timed_out = comm_recv(f.comm, sums_s, NVF + 1, ep, &flag_s);
+            if (timed_out && tid == 0) *f.comm.error = 1;
+        }
+        dbg_mark(a.dbg, 12);
+        fused_assemble<N, P>(sums_s, small_s.M, VP_MAX_P, rinv_s, a.e_basis, a.e_param, q, f.jac_full, sums_s[NVF] != 0.0, &ev_s);
+        dbg_mark(a.dbg, 13);
+        if (!fit_mode) {
+            if (tid == 0) {
+                EvalOut *o = a.out;
+                o->rnorm2 = ev_s.rnorm2;
+                for (int k = 0; k < q; ++k) o->g[k] = ev_s.g[k];
+                for (int k = 0; k < q * q; ++k) o->H[k] = ev_s.H[k];
+                o->finite = ev_s.finite;
+                *a.ticket = 0; // re-arm for the next launch
+                if (comm_on) *f.comm.epoch = epoch0 + 1ull;
+            }
+            dbg_mark(a.dbg, 6);
+            break;
+        }
+        // ---- the LM step, redundantly in every CTA (identical inputs => identical decisions) ----------
+        if (tid == 0) {
+            bool more = false;
+            if (timed_out) {
+                f.ctl->error = 1;
+            } else {
+                more = lm_advance(fd_s.st, fd_s.cfg, ev_s);
+                if (fd_s.st.last_accepted) fd_s.cur ^= 1;
+                if (fd_s.evals < 48) {
+                    double *tr = fd_s.trace + 4 * fd_s.evals;
+                    tr[0] = sqrt(ev_s.rnorm2); tr[1] = fd_s.st.par; tr[2] = fd_s.st.delta; tr[3] = fd_s.st.last_accepted;
+                }
+                fd_s.evals += 1;
+            }
+            ctrl_more = more ? 1 : 0;
+            dbg_mark(a.dbg, 15);
+        }
         __syncthreads();
-        if (!fit_mode || !ctrl_more) break;
+        dbg_mark(a.dbg, 6);
+        if (!timed_out && fd_s.st.last_accepted) { // the evaluation becomes the accepted one (cooperative copy)
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(&fd_s.accepted);
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&ev_s);
+            for (int i = tid; i < (int)(sizeof(LmEval) / 8); i += THREADS) dst[i] = src[i];
+        }
+        if (!ctrl_more) {
+            __syncthreads();
+            if (blockIdx.x == 0) { // final state -> global (the host reads it after the launch)
+                unsigned long long *fw = reinterpret_cast<unsigned long long *>(a.fit);
+                const unsigned long long *lw = reinterpret_cast<const unsigned long long *>(&fd_s);
+                for (int i = tid; i < FIT_WORDS; i += THREADS) fw[i] = lw[i];
+                if (comm_on && tid == 0) *f.comm.epoch = epoch0 + e + 1ull;
+            }
+            break;
+        }
     }
     // drain the tiles that were put in flight for an evaluation that is not going to happen
     if (fit_mode)

@@ -12,8 +12,21 @@
 // The streaming kernel produces (||r||^2, g, H) in one pass over Y, so the LM
 // step never touches an O(m*S) object.
 //
-// The code is __host__ __device__: the host-driven vp_fit loop and the
-// device-resident LM step of the graph path share it.
+// The step is the serial link between two evaluations of a fit (one thread, a chain of
+// dependent fp64 divisions and square roots), so it is written for latency: every routine
+// is a template on QT, the number of nonlinear parameters known at compile time
+// (QT = 1..VP_LM_SPECIALISED; QT = 0: any q <= VP_LM_MAXQ at run time). For QT > 0 all loops
+// have constant trip counts and every array index is a compile-time constant -- the pivot
+// permutation is applied through select chains (lm_get / lm_put) -- so the whole state lives
+// in registers and the only long-latency operations left are the divisions and square roots
+// of the algorithm itself. The first version ran lmder on run-time-indexed arrays in local
+// memory: ~31 us per step on B200 (profiles/r02v_queue_phase_breakdown.txt), more than
+// streaming the observations six times.
+// The specialised and the generic instantiation execute the same floating-point operations
+// in the same order (tests/test_lm_state_machine.py checks bitwise equality).
+//
+// The code is __host__ __device__: the host-driven vp_fit loop, the in-kernel LM step and
+// the CPU test harness (tests/csrc/lm_harness.cpp) share it.
 #pragma once
 
 #include <math.h>
@@ -26,8 +39,17 @@
 #define VP_HD inline
 #endif
 #endif
+#ifdef __CUDACC__
+#define VP_LM_NOINLINE static __host__ __device__ __noinline__
+// full unrolling for the compile-time-q instantiations only (the generic one keeps its loops rolled)
+#define VP_LM_UNROLL _Pragma("unroll (QT > 0 ? 64 : 1)")
+#else
+#define VP_LM_NOINLINE static inline
+#define VP_LM_UNROLL
+#endif
 
 #define VP_LM_MAXQ 8
+#define VP_LM_SPECIALISED 4 // q = 1..4 run the register-resident instantiations
 
 namespace vp {
 
@@ -57,31 +79,61 @@ struct LmConfig {
 struct LmEval {
     double rnorm2;                     // ||r||^2
     double g[VP_LM_MAXQ];              // J^T r
-    double H[VP_LM_MAXQ * VP_LM_MAXQ]; // J^T J, column-major q x q
+    double H[VP_LM_MAXQ * VP_LM_MAXQ]; // J^T J, column-major q x q (leading dimension q)
     int finite;
 };
 
-struct LmState {
+// The lmder state between two evaluations. NQ = capacity of the arrays; matrices are packed
+// with leading dimension q, so LmStateT<q> is a prefix-compatible view of LmStateT<VP_LM_MAXQ>.
+template <int NQ>
+struct LmStateT {
     int q;
     int phase;        // 0: waiting for the evaluation at x0, 1: waiting for a trial evaluation
     int termination;  // Termination
     int nfev, iter;
     int last_accepted; // 1 if the most recent trial was accepted (trial buffers hold the state of x)
-    double x[VP_LM_MAXQ];       // last accepted parameters
-    double x_trial[VP_LM_MAXQ]; // parameters the next evaluation must be made at
-    double step[VP_LM_MAXQ];    // x_trial - x
+    double x[NQ];       // last accepted parameters
+    double x_trial[NQ]; // parameters the next evaluation must be made at
+    double step[NQ];    // x_trial - x
     double fnorm, xnorm, gnorm, delta, par, pnorm;
-    double diag[VP_LM_MAXQ];
-    double R[VP_LM_MAXQ * VP_LM_MAXQ]; // upper triangle of the pivoted Cholesky factor, col-major
-    double qtf[VP_LM_MAXQ];
-    double acnorm[VP_LM_MAXQ];
-    int ipvt[VP_LM_MAXQ];
+    double diag[NQ];
+    double R[NQ * NQ]; // upper triangle of the pivoted Cholesky factor, col-major, leading dimension q
+    double qtf[NQ];
+    double acnorm[NQ];
+    int ipvt[NQ];
 };
+typedef LmStateT<VP_LM_MAXQ> LmState;
 
-VP_HD double lm_enorm(int n, const double *v)
+// ---- indexing with a run-time index into a register-resident array --------------------------
+template <int QT, typename T, int NA>
+VP_HD T lm_get(const T (&a)[NA], const int idx)
+{
+    if constexpr (QT > 0) {
+        T v = a[0];
+        VP_LM_UNROLL
+        for (int k = 1; k < QT; ++k) v = (idx == k) ? a[k] : v;
+        return v;
+    } else {
+        return a[idx];
+    }
+}
+template <int QT, typename T, int NA>
+VP_HD void lm_put(T (&a)[NA], const int idx, const T v)
+{
+    if constexpr (QT > 0) {
+        VP_LM_UNROLL
+        for (int k = 0; k < QT; ++k) a[k] = (idx == k) ? v : a[k];
+    } else {
+        a[idx] = v;
+    }
+}
+
+template <int QT, int NA>
+VP_HD double lm_enorm(const int n, const double (&v)[NA])
 {
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s += v[i] * v[i];
+    VP_LM_UNROLL
+    for (int i = 0; i < (QT > 0 ? QT : n); ++i) s += v[i] * v[i];
     return sqrt(s);
 }
 
@@ -89,78 +141,105 @@ VP_HD double lm_enorm(int n, const double *v)
 // P^T H P = R^T R, pivot = largest remaining diagonal of the Schur complement
 // (= largest remaining column norm of J, qrfac's rule). Rank deficiency gives
 // zero rows, which lmpar treats like qrfac's zero diagonals.
-VP_HD void lm_pivoted_cholesky(int n, const double *H, double *R, int *ipvt, double *acnorm)
+template <int QT, int NQ>
+VP_HD void lm_pivoted_cholesky(const int nrt, const double *H, double (&R)[NQ * NQ], int (&ipvt)[NQ], double (&acnorm)[NQ])
 {
-    double A[VP_LM_MAXQ * VP_LM_MAXQ];
+    const int n = QT > 0 ? QT : nrt;
+    double A[NQ * NQ];
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
         ipvt[j] = j;
         acnorm[j] = sqrt(fmax(H[j * n + j], 0.0));
+        VP_LM_UNROLL
         for (int i = 0; i < n; ++i) {
             A[j * n + i] = H[j * n + i];
             R[j * n + i] = 0.0;
         }
     }
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
         int kmax = j;
+        double dmax = A[j * n + j];
+        VP_LM_UNROLL
         for (int k = j + 1; k < n; ++k)
-            if (A[k * n + k] > A[kmax * n + kmax]) kmax = k;
-        if (kmax != j) {
-            // symmetric swap of rows/columns j and kmax of the working matrix,
-            // and of the already computed columns of R
-            for (int i = 0; i < n; ++i) { double t = A[j * n + i]; A[j * n + i] = A[kmax * n + i]; A[kmax * n + i] = t; }
-            for (int i = 0; i < n; ++i) { double t = A[i * n + j]; A[i * n + j] = A[i * n + kmax]; A[i * n + kmax] = t; }
-            for (int i = 0; i < j; ++i) { double t = R[j * n + i]; R[j * n + i] = R[kmax * n + i]; R[kmax * n + i] = t; }
-            int t = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = t;
+            if (A[k * n + k] > dmax) { kmax = k; dmax = A[k * n + k]; }
+        // symmetric swap of rows/columns j and kmax of the working matrix, and of the already
+        // computed columns of R (the loop over k finds kmax with compile-time indices)
+        VP_LM_UNROLL
+        for (int k = j + 1; k < n; ++k) {
+            if (k != kmax) continue;
+            VP_LM_UNROLL
+            for (int i = 0; i < n; ++i) { const double t = A[j * n + i]; A[j * n + i] = A[k * n + i]; A[k * n + i] = t; }
+            VP_LM_UNROLL
+            for (int i = 0; i < n; ++i) { const double t = A[i * n + j]; A[i * n + j] = A[i * n + k]; A[i * n + k] = t; }
+            VP_LM_UNROLL
+            for (int i = 0; i < j; ++i) { const double t = R[j * n + i]; R[j * n + i] = R[k * n + i]; R[k * n + i] = t; }
+            const int t = ipvt[j]; ipvt[j] = ipvt[k]; ipvt[k] = t;
         }
-        double d = A[j * n + j];
+        const double d = A[j * n + j];
         if (!(d > 0.0)) {
             // remaining block is (numerically) zero: rank deficient
+            VP_LM_UNROLL
             for (int k = j; k < n; ++k) R[k * n + j] = 0.0;
+            VP_LM_UNROLL
             for (int k = j + 1; k < n; ++k) A[k * n + k] = 0.0;
             continue;
         }
-        double rjj = sqrt(d);
+        const double rjj = sqrt(d);
         R[j * n + j] = rjj;
+        VP_LM_UNROLL
         for (int k = j + 1; k < n; ++k) R[k * n + j] = A[k * n + j] / rjj;
-        for (int k = j + 1; k < n; ++k)
+        VP_LM_UNROLL
+        for (int k = j + 1; k < n; ++k) {
+            VP_LM_UNROLL
             for (int i = j + 1; i <= k; ++i) {
                 A[k * n + i] -= R[i * n + j] * R[k * n + j];
                 A[i * n + k] = A[k * n + i];
             }
+        }
     }
 }
 
 // MINPACK qrsolv on a private copy S of R (R itself is left untouched).
-VP_HD void lm_qrsolv(int n, const double *R, const int *ipvt, const double *diag,
-                     const double *qtb, double *x, double *sdiag, double *S)
+template <int QT, int NQ>
+VP_HD void lm_qrsolv(const int nrt, const double (&R)[NQ * NQ], const int (&ipvt)[NQ], const double (&diag)[NQ],
+                     const double (&qtb)[NQ], double (&x)[NQ], double (&sdiag)[NQ], double (&S)[NQ * NQ])
 {
-    double wa[VP_LM_MAXQ];
+    const int n = QT > 0 ? QT : nrt;
+    double wa[NQ];
     // S holds r^T in its strict lower triangle during the sweep (MINPACK stores
     // it inside r); S(i,j) i>j.
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
+        VP_LM_UNROLL
         for (int i = 0; i < n; ++i) S[j * n + i] = R[j * n + i];
     }
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
+        VP_LM_UNROLL
         for (int i = j; i < n; ++i) S[j * n + i] = S[i * n + j];
         x[j] = S[j * n + j];
         wa[j] = qtb[j];
     }
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
-        int l = ipvt[j];
-        if (diag[l] != 0.0) {
+        const double dl = lm_get<QT>(diag, ipvt[j]);
+        if (dl != 0.0) {
+            VP_LM_UNROLL
             for (int k = j; k < n; ++k) sdiag[k] = 0.0;
-            sdiag[j] = diag[l];
+            sdiag[j] = dl;
             double qtbpj = 0.0;
+            VP_LM_UNROLL
             for (int k = j; k < n; ++k) {
                 if (sdiag[k] == 0.0) continue;
                 double c, s;
-                double rkk = S[k * n + k];
+                const double rkk = S[k * n + k];
                 if (fabs(rkk) < fabs(sdiag[k])) {
-                    double cotan = rkk / sdiag[k];
+                    const double cotan = rkk / sdiag[k];
                     s = 0.5 / sqrt(0.25 + 0.25 * cotan * cotan);
                     c = s * cotan;
                 } else {
-                    double t = sdiag[k] / rkk;
+                    const double t = sdiag[k] / rkk;
                     c = 0.5 / sqrt(0.25 + 0.25 * t * t);
                     s = c * t;
                 }
@@ -168,6 +247,7 @@ VP_HD void lm_qrsolv(int n, const double *R, const int *ipvt, const double *diag
                 double temp = c * wa[k] + s * qtbpj;
                 qtbpj = -s * wa[k] + c * qtbpj;
                 wa[k] = temp;
+                VP_LM_UNROLL
                 for (int i = k + 1; i < n; ++i) {
                     temp = c * S[k * n + i] + s * sdiag[i];
                     sdiag[i] = -s * S[k * n + i] + c * sdiag[i];
@@ -179,99 +259,123 @@ VP_HD void lm_qrsolv(int n, const double *R, const int *ipvt, const double *diag
         S[j * n + j] = x[j];
     }
     int nsing = n;
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
         if (sdiag[j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa[j] = 0.0;
     }
-    for (int k = 1; k <= nsing; ++k) {
-        int j = nsing - k;
+    // back substitution over j = nsing-1 .. 0 (constant trip count, predicated)
+    VP_LM_UNROLL
+    for (int j = n - 1; j >= 0; --j) {
+        if (j >= nsing) continue;
         double sum = 0.0;
-        for (int i = j + 1; i < nsing; ++i) sum += S[j * n + i] * wa[i];
+        VP_LM_UNROLL
+        for (int i = j + 1; i < n; ++i)
+            if (i < nsing) sum += S[j * n + i] * wa[i];
         wa[j] = (wa[j] - sum) / sdiag[j];
     }
-    for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
+    VP_LM_UNROLL
+    for (int j = 0; j < n; ++j) lm_put<QT>(x, ipvt[j], wa[j]);
 }
 
 // MINPACK lmpar: determines par such that ||D x|| ~ delta. x receives the
 // solution of (J^T J + par D^2) x = J^T r.
-VP_HD void lm_lmpar(int n, const double *R, const int *ipvt, const double *diag,
-                    const double *qtb, double delta, double *par, double *x)
+template <int QT, int NQ>
+VP_HD void lm_lmpar(const int nrt, const double (&R)[NQ * NQ], const int (&ipvt)[NQ], const double (&diag)[NQ],
+                    const double (&qtb)[NQ], const double delta, double &par, double (&x)[NQ])
 {
+    const int n = QT > 0 ? QT : nrt;
     const double dwarf = DBL_MIN;
-    double wa1[VP_LM_MAXQ], wa2[VP_LM_MAXQ], sdiag[VP_LM_MAXQ];
-    double S[VP_LM_MAXQ * VP_LM_MAXQ];
+    double wa1[NQ], wa2[NQ], sdiag[NQ];
+    double S[NQ * NQ];
     int nsing = n;
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
         wa1[j] = qtb[j];
         if (R[j * n + j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa1[j] = 0.0;
     }
-    for (int k = 1; k <= nsing; ++k) {
-        int j = nsing - k;
+    VP_LM_UNROLL
+    for (int j = n - 1; j >= 0; --j) {
+        if (j >= nsing) continue;
         wa1[j] /= R[j * n + j];
-        double temp = wa1[j];
+        const double temp = wa1[j];
+        VP_LM_UNROLL
         for (int i = 0; i < j; ++i) wa1[i] -= R[j * n + i] * temp;
     }
-    for (int j = 0; j < n; ++j) x[ipvt[j]] = wa1[j];
+    VP_LM_UNROLL
+    for (int j = 0; j < n; ++j) lm_put<QT>(x, ipvt[j], wa1[j]);
     int iter = 0;
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
-    double dxnorm = lm_enorm(n, wa2);
+    double dxnorm = lm_enorm<QT>(n, wa2);
     double fp = dxnorm - delta;
-    if (fp <= 0.1 * delta) { *par = 0.0; return; }
+    if (fp <= 0.1 * delta) { par = 0.0; return; }
     double parl = 0.0;
     if (nsing >= n) {
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) {
-            int l = ipvt[j];
-            wa1[j] = diag[l] * (wa2[l] / dxnorm);
+            const int l = ipvt[j];
+            wa1[j] = lm_get<QT>(diag, l) * (lm_get<QT>(wa2, l) / dxnorm);
         }
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) {
             double sum = 0.0;
+            VP_LM_UNROLL
             for (int i = 0; i < j; ++i) sum += R[j * n + i] * wa1[i];
             wa1[j] = (wa1[j] - sum) / R[j * n + j];
         }
-        double temp = lm_enorm(n, wa1);
+        const double temp = lm_enorm<QT>(n, wa1);
         parl = ((fp / delta) / temp) / temp;
     }
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
         double sum = 0.0;
+        VP_LM_UNROLL
         for (int i = 0; i <= j; ++i) sum += R[j * n + i] * qtb[i];
-        wa1[j] = sum / diag[ipvt[j]];
+        wa1[j] = sum / lm_get<QT>(diag, ipvt[j]);
     }
-    double gnorm = lm_enorm(n, wa1);
+    const double gnorm = lm_enorm<QT>(n, wa1);
     double paru = gnorm / delta;
     if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
-    *par = fmax(*par, parl);
-    *par = fmin(*par, paru);
-    if (*par == 0.0) *par = gnorm / dxnorm;
+    par = fmax(par, parl);
+    par = fmin(par, paru);
+    if (par == 0.0) par = gnorm / dxnorm;
     for (;;) {
         ++iter;
-        if (*par == 0.0) *par = fmax(dwarf, 0.001 * paru);
-        double temp = sqrt(*par);
+        if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
+        double temp = sqrt(par);
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
-        lm_qrsolv(n, R, ipvt, wa1, qtb, x, sdiag, S);
+        lm_qrsolv<QT, NQ>(n, R, ipvt, wa1, qtb, x, sdiag, S);
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
-        dxnorm = lm_enorm(n, wa2);
+        dxnorm = lm_enorm<QT>(n, wa2);
         temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) {
-            int l = ipvt[j];
-            wa1[j] = diag[l] * (wa2[l] / dxnorm);
+            const int l = ipvt[j];
+            wa1[j] = lm_get<QT>(diag, l) * (lm_get<QT>(wa2, l) / dxnorm);
         }
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) {
             wa1[j] /= sdiag[j];
             temp = wa1[j];
+            VP_LM_UNROLL
             for (int i = j + 1; i < n; ++i) wa1[i] -= S[j * n + i] * temp;
         }
-        temp = lm_enorm(n, wa1);
-        double parc = ((fp / delta) / temp) / temp;
-        if (fp > 0.0) parl = fmax(parl, *par);
-        if (fp < 0.0) paru = fmin(paru, *par);
-        *par = fmax(parl, *par + parc);
+        temp = lm_enorm<QT>(n, wa1);
+        const double parc = ((fp / delta) / temp) / temp;
+        if (fp > 0.0) parl = fmax(parl, par);
+        if (fp < 0.0) paru = fmin(paru, par);
+        par = fmax(parl, par + parc);
     }
 }
 
-VP_HD void lm_init(LmState &st, int q, const double *x0)
+template <int NQ>
+VP_HD void lm_init(LmStateT<NQ> &st, const int q, const double *x0)
 {
     st.q = q;
     st.phase = 0;
@@ -280,68 +384,206 @@ VP_HD void lm_init(LmState &st, int q, const double *x0)
     st.iter = 1;
     st.last_accepted = 1;
     st.fnorm = st.xnorm = st.gnorm = st.delta = st.par = st.pnorm = 0.0;
-    for (int j = 0; j < VP_LM_MAXQ; ++j) {
+    for (int j = 0; j < NQ; ++j) {
         st.x[j] = j < q ? x0[j] : 0.0;
         st.x_trial[j] = st.x[j];
         st.step[j] = 0.0;
         st.diag[j] = 1.0;
+        st.qtf[j] = 0.0;
+        st.acnorm[j] = 0.0;
+        st.ipvt[j] = j;
     }
+    for (int j = 0; j < NQ * NQ; ++j) st.R[j] = 0.0;
 }
 
 // Start of an lmder outer iteration: factor H at the accepted point, form qtf,
 // the scaled gradient norm and the diag rescale. Returns false on termination.
-VP_HD bool lm_outer_prepare(LmState &st, const LmConfig &cfg, const LmEval &ev)
+template <int QT, int NQ>
+VP_HD bool lm_outer_prepare(LmStateT<NQ> &st, const LmConfig &cfg, const double *Hev, const double *gev)
 {
-    const int n = st.q;
-    lm_pivoted_cholesky(n, ev.H, st.R, st.ipvt, st.acnorm);
+    const int n = QT > 0 ? QT : st.q;
+    lm_pivoted_cholesky<QT, NQ>(n, Hev, st.R, st.ipvt, st.acnorm);
     if (st.iter == 1) {
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) {
             st.diag[j] = cfg.scale_diag ? st.acnorm[j] : 1.0;
             if (cfg.scale_diag && st.acnorm[j] == 0.0) st.diag[j] = 1.0;
         }
-        double wa3[VP_LM_MAXQ];
+        double wa3[NQ];
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) wa3[j] = st.diag[j] * st.x[j];
-        st.xnorm = lm_enorm(n, wa3);
+        st.xnorm = lm_enorm<QT>(n, wa3);
         st.delta = cfg.stepbound * st.xnorm;
         if (st.delta == 0.0) st.delta = cfg.stepbound;
     }
     // qtf = R^-T P^T g (forward substitution; zero for the rank-deficient tail)
+    double gl[NQ];
+    VP_LM_UNROLL
+    for (int j = 0; j < n; ++j) gl[j] = gev[j];
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
-        double sum = ev.g[st.ipvt[j]];
+        double sum = lm_get<QT>(gl, st.ipvt[j]);
+        VP_LM_UNROLL
         for (int i = 0; i < j; ++i) sum -= st.R[j * n + i] * st.qtf[i];
         st.qtf[j] = (st.R[j * n + j] != 0.0) ? sum / st.R[j * n + j] : 0.0;
     }
     st.gnorm = 0.0;
     if (st.fnorm != 0.0) {
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) {
-            int l = st.ipvt[j];
-            if (st.acnorm[l] != 0.0) {
+            const double acl = lm_get<QT>(st.acnorm, st.ipvt[j]);
+            if (acl != 0.0) {
                 double sum = 0.0;
+                VP_LM_UNROLL
                 for (int i = 0; i <= j; ++i) sum += st.R[j * n + i] * (st.qtf[i] / st.fnorm);
-                st.gnorm = fmax(st.gnorm, fabs(sum / st.acnorm[l]));
+                st.gnorm = fmax(st.gnorm, fabs(sum / acl));
             }
         }
     }
     if (!isfinite(st.gnorm)) { st.termination = TERM_NUMERICAL; return false; }
     if (st.gnorm <= cfg.gtol) { st.termination = TERM_ORTHOGONAL; return false; }
-    if (cfg.scale_diag)
+    if (cfg.scale_diag) {
+        VP_LM_UNROLL
         for (int j = 0; j < n; ++j) st.diag[j] = fmax(st.diag[j], st.acnorm[j]);
+    }
     return true;
 }
 
 // lmder inner loop head: lmpar -> trial point.
-VP_HD void lm_inner_propose(LmState &st)
+template <int QT, int NQ>
+VP_HD void lm_inner_propose(LmStateT<NQ> &st)
 {
-    const int n = st.q;
-    double p[VP_LM_MAXQ], wa3[VP_LM_MAXQ];
-    lm_lmpar(n, st.R, st.ipvt, st.diag, st.qtf, st.delta, &st.par, p);
+    const int n = QT > 0 ? QT : st.q;
+    double p[NQ], wa3[NQ];
+    lm_lmpar<QT, NQ>(n, st.R, st.ipvt, st.diag, st.qtf, st.delta, st.par, p);
+    VP_LM_UNROLL
     for (int j = 0; j < n; ++j) {
         st.step[j] = -p[j];
         st.x_trial[j] = st.x[j] + st.step[j];
         wa3[j] = st.diag[j] * st.step[j];
     }
-    st.pnorm = lm_enorm(n, wa3);
+    st.pnorm = lm_enorm<QT>(n, wa3);
     if (st.iter == 1) st.delta = fmin(st.delta, st.pnorm);
+}
+
+// The state machine proper on a state with compile-time capacity (see lm_advance below).
+template <int QT, int NQ>
+VP_HD bool lm_advance_core(LmStateT<NQ> &st, const LmConfig &cfg, const double rnorm2, const int finite, const double *gev,
+                           const double *Hev)
+{
+    const int n = QT > 0 ? QT : st.q;
+    if (st.termination != TERM_RUNNING) return false;
+    bool prepare; // a new outer iteration starts: refactor H at the (new) accepted point
+    if (st.phase == 0) {
+        st.nfev = 1;
+        st.last_accepted = 1;
+        if (n == 0) { st.termination = TERM_NO_PARAMETERS; return false; }
+        const double fn = sqrt(rnorm2);
+        if (!finite || !isfinite(fn)) { st.fnorm = fn; st.termination = TERM_NUMERICAL; return false; }
+        st.fnorm = fn;
+        if (fn == 0.0) { st.termination = TERM_RESIDUALS_ZERO; return false; }
+        st.par = 0.0;
+        st.iter = 1;
+        st.phase = 1;
+        prepare = true;
+    } else {
+        // trial evaluation
+        st.nfev += 1;
+        const double fnorm1 = sqrt(rnorm2);
+        if (!finite || !isfinite(fnorm1)) { st.last_accepted = 0; st.termination = TERM_NUMERICAL; return false; }
+        double actred = -1.0;
+        if (0.1 * fnorm1 < st.fnorm) actred = 1.0 - (fnorm1 / st.fnorm) * (fnorm1 / st.fnorm);
+        double wa3[NQ];
+        VP_LM_UNROLL
+        for (int j = 0; j < n; ++j) wa3[j] = 0.0;
+        VP_LM_UNROLL
+        for (int j = 0; j < n; ++j) {
+            const double temp = lm_get<QT>(st.step, st.ipvt[j]);
+            VP_LM_UNROLL
+            for (int i = 0; i <= j; ++i) wa3[i] += st.R[j * n + i] * temp;
+        }
+        const double temp1 = lm_enorm<QT>(n, wa3) / st.fnorm;
+        const double temp2 = (sqrt(st.par) * st.pnorm) / st.fnorm;
+        const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+        const double dirder = -(temp1 * temp1 + temp2 * temp2);
+        const double ratio = (prered != 0.0) ? actred / prered : 0.0;
+        if (ratio <= 0.25) {
+            double temp = (actred >= 0.0) ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
+            if (0.1 * fnorm1 >= st.fnorm || temp < 0.1) temp = 0.1;
+            st.delta = temp * fmin(st.delta, st.pnorm / 0.1);
+            st.par /= temp;
+        } else if (st.par == 0.0 || ratio >= 0.75) {
+            st.delta = st.pnorm / 0.5;
+            st.par *= 0.5;
+        }
+        const bool accepted = ratio >= 1e-4;
+        if (accepted) {
+            VP_LM_UNROLL
+            for (int j = 0; j < n; ++j) { st.x[j] = st.x_trial[j]; wa3[j] = st.diag[j] * st.x[j]; }
+            st.xnorm = lm_enorm<QT>(n, wa3);
+            st.fnorm = fnorm1;
+            st.iter += 1;
+        }
+        st.last_accepted = accepted ? 1 : 0;
+        if (st.fnorm == 0.0) { st.termination = TERM_RESIDUALS_ZERO; return false; }
+        const bool f_ok = fabs(actred) <= cfg.ftol && prered <= cfg.ftol && 0.5 * ratio <= 1.0;
+        const bool x_ok = st.delta <= cfg.xtol * st.xnorm;
+        if (f_ok && x_ok) { st.termination = TERM_CONVERGED_FTOL_XTOL; return false; }
+        if (f_ok) { st.termination = TERM_CONVERGED_FTOL; return false; }
+        if (x_ok) { st.termination = TERM_CONVERGED_XTOL; return false; }
+        if (st.nfev >= cfg.maxfev) { st.termination = TERM_LOST_PATIENCE; return false; }
+        if ((fabs(actred) <= cfg.epsmch && prered <= cfg.epsmch && 0.5 * ratio <= 1.0) ||
+            st.delta <= cfg.epsmch * st.xnorm || st.gnorm <= cfg.epsmch) {
+            st.termination = TERM_NO_IMPROVEMENT_POSSIBLE;
+            return false;
+        }
+        prepare = accepted;
+    }
+    // one copy of the factorisation / lmpar code for both entry points (the step is straight-line
+    // code of tens of KB once unrolled; the instruction cache is cold every time it runs)
+    if (prepare) {
+        if (!lm_outer_prepare<QT, NQ>(st, cfg, Hev, gev)) return false;
+    }
+    lm_inner_propose<QT, NQ>(st);
+    return true;
+}
+
+// Specialised step: copy the q-sized prefix of the state into a register-resident LmStateT<QT>,
+// advance, copy back. `st` may live in shared, global or host memory.
+template <int QT>
+VP_LM_NOINLINE bool lm_advance_q(LmState &st, const LmConfig &cfg, const LmEval &ev)
+{
+    LmStateT<QT> s;
+    s.q = QT; s.phase = st.phase; s.termination = st.termination; s.nfev = st.nfev; s.iter = st.iter;
+    s.last_accepted = st.last_accepted;
+    s.fnorm = st.fnorm; s.xnorm = st.xnorm; s.gnorm = st.gnorm; s.delta = st.delta; s.par = st.par; s.pnorm = st.pnorm;
+    double g[QT], H[QT * QT];
+    VP_LM_UNROLL
+    for (int j = 0; j < QT; ++j) {
+        s.x[j] = st.x[j]; s.x_trial[j] = st.x_trial[j]; s.step[j] = st.step[j]; s.diag[j] = st.diag[j];
+        s.qtf[j] = st.qtf[j]; s.acnorm[j] = st.acnorm[j]; s.ipvt[j] = st.ipvt[j];
+        g[j] = ev.g[j];
+    }
+    VP_LM_UNROLL
+    for (int j = 0; j < QT * QT; ++j) { s.R[j] = st.R[j]; H[j] = ev.H[j]; }
+    const bool more = lm_advance_core<QT, QT>(s, cfg, ev.rnorm2, ev.finite, g, H);
+    st.phase = s.phase; st.termination = s.termination; st.nfev = s.nfev; st.iter = s.iter;
+    st.last_accepted = s.last_accepted;
+    st.fnorm = s.fnorm; st.xnorm = s.xnorm; st.gnorm = s.gnorm; st.delta = s.delta; st.par = s.par; st.pnorm = s.pnorm;
+    VP_LM_UNROLL
+    for (int j = 0; j < QT; ++j) {
+        st.x[j] = s.x[j]; st.x_trial[j] = s.x_trial[j]; st.step[j] = s.step[j]; st.diag[j] = s.diag[j];
+        st.qtf[j] = s.qtf[j]; st.acnorm[j] = s.acnorm[j]; st.ipvt[j] = s.ipvt[j];
+    }
+    VP_LM_UNROLL
+    for (int j = 0; j < QT * QT; ++j) st.R[j] = s.R[j];
+    return more;
+}
+
+// Any q <= VP_LM_MAXQ with run-time loop bounds (the arrays are indexed dynamically).
+VP_LM_NOINLINE bool lm_advance_generic(LmState &st, const LmConfig &cfg, const LmEval &ev)
+{
+    return lm_advance_core<0, VP_LM_MAXQ>(st, cfg, ev.rnorm2, ev.finite, ev.g, ev.H);
 }
 
 // Feed the evaluation made at st.x_trial. Returns true if another evaluation
@@ -352,74 +594,13 @@ VP_HD void lm_inner_propose(LmState &st)
 // as the residual norm, so no second pass is needed.
 VP_HD bool lm_advance(LmState &st, const LmConfig &cfg, const LmEval &ev)
 {
-    const int n = st.q;
-    if (st.termination != TERM_RUNNING) return false;
-    if (st.phase == 0) {
-        st.nfev = 1;
-        st.last_accepted = 1;
-        if (n == 0) { st.termination = TERM_NO_PARAMETERS; return false; }
-        double fn = sqrt(ev.rnorm2);
-        if (!ev.finite || !isfinite(fn)) { st.fnorm = fn; st.termination = TERM_NUMERICAL; return false; }
-        st.fnorm = fn;
-        if (fn == 0.0) { st.termination = TERM_RESIDUALS_ZERO; return false; }
-        st.par = 0.0;
-        st.iter = 1;
-        if (!lm_outer_prepare(st, cfg, ev)) return false;
-        lm_inner_propose(st);
-        st.phase = 1;
-        return true;
+    switch (st.q) {
+    case 1: return lm_advance_q<1>(st, cfg, ev);
+    case 2: return lm_advance_q<2>(st, cfg, ev);
+    case 3: return lm_advance_q<3>(st, cfg, ev);
+    case 4: return lm_advance_q<4>(st, cfg, ev);
+    default: return lm_advance_generic(st, cfg, ev);
     }
-    // trial evaluation
-    st.nfev += 1;
-    double fnorm1 = sqrt(ev.rnorm2);
-    if (!ev.finite || !isfinite(fnorm1)) { st.last_accepted = 0; st.termination = TERM_NUMERICAL; return false; }
-    double actred = -1.0;
-    if (0.1 * fnorm1 < st.fnorm) actred = 1.0 - (fnorm1 / st.fnorm) * (fnorm1 / st.fnorm);
-    double wa3[VP_LM_MAXQ];
-    for (int j = 0; j < n; ++j) wa3[j] = 0.0;
-    for (int j = 0; j < n; ++j) {
-        double temp = st.step[st.ipvt[j]];
-        for (int i = 0; i <= j; ++i) wa3[i] += st.R[j * n + i] * temp;
-    }
-    double temp1 = lm_enorm(n, wa3) / st.fnorm;
-    double temp2 = (sqrt(st.par) * st.pnorm) / st.fnorm;
-    double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
-    double dirder = -(temp1 * temp1 + temp2 * temp2);
-    double ratio = (prered != 0.0) ? actred / prered : 0.0;
-    if (ratio <= 0.25) {
-        double temp = (actred >= 0.0) ? 0.5 : 0.5 * dirder / (dirder + 0.5 * actred);
-        if (0.1 * fnorm1 >= st.fnorm || temp < 0.1) temp = 0.1;
-        st.delta = temp * fmin(st.delta, st.pnorm / 0.1);
-        st.par /= temp;
-    } else if (st.par == 0.0 || ratio >= 0.75) {
-        st.delta = st.pnorm / 0.5;
-        st.par *= 0.5;
-    }
-    const bool accepted = ratio >= 1e-4;
-    if (accepted) {
-        for (int j = 0; j < n; ++j) { st.x[j] = st.x_trial[j]; wa3[j] = st.diag[j] * st.x[j]; }
-        st.xnorm = lm_enorm(n, wa3);
-        st.fnorm = fnorm1;
-        st.iter += 1;
-    }
-    st.last_accepted = accepted ? 1 : 0;
-    if (st.fnorm == 0.0) { st.termination = TERM_RESIDUALS_ZERO; return false; }
-    const bool f_ok = fabs(actred) <= cfg.ftol && prered <= cfg.ftol && 0.5 * ratio <= 1.0;
-    const bool x_ok = st.delta <= cfg.xtol * st.xnorm;
-    if (f_ok && x_ok) { st.termination = TERM_CONVERGED_FTOL_XTOL; return false; }
-    if (f_ok) { st.termination = TERM_CONVERGED_FTOL; return false; }
-    if (x_ok) { st.termination = TERM_CONVERGED_XTOL; return false; }
-    if (st.nfev >= cfg.maxfev) { st.termination = TERM_LOST_PATIENCE; return false; }
-    if ((fabs(actred) <= cfg.epsmch && prered <= cfg.epsmch && 0.5 * ratio <= 1.0) ||
-        st.delta <= cfg.epsmch * st.xnorm || st.gnorm <= cfg.epsmch) {
-        st.termination = TERM_NO_IMPROVEMENT_POSSIBLE;
-        return false;
-    }
-    if (accepted) {
-        if (!lm_outer_prepare(st, cfg, ev)) return false;
-    }
-    lm_inner_propose(st);
-    return true;
 }
 
 VP_HD bool lm_successful(int termination)

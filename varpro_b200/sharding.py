@@ -49,19 +49,33 @@ def gather_handles(local: bytes, world: int, rank: int, group=None) -> bytes:
 class Communicator:
     """vp_comm: this rank's mailbox plus the peers' mailboxes mapped over NVLink."""
 
-    def __init__(self, rank: int, world: int, device: int = 0, group=None):
+    def __init__(self, rank: int, world: int, device: int = 0, group=None, ctx_slot: int = 0, connect: bool = True):
         lib = _lib.load()
-        self._ctx = _Ctx.get(device)
+        self._ctx = _Ctx.get(device, ctx_slot)
         self.rank, self.world = rank, world
         self._h = C.c_void_p()
         handle = (C.c_ubyte * HANDLE_BYTES)()
         _check(lib.vp_comm_create(self._ctx.h, rank, world, C.byref(self._h), handle), self._ctx.h)
-        if world > 1:
+        if world > 1 and connect:
             allh = gather_handles(bytes(handle), world, rank, group)
             if len(allh) != world * HANDLE_BYTES:
                 raise VarproError("handle exchange returned the wrong number of bytes")
             buf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
             _check(lib.vp_comm_connect(self._h, buf), self._ctx.h)
+
+    @classmethod
+    def local_group(cls, world: int, devices=None, ctx_slots=None):
+        """The `world` communicators of ONE process that drives several GPUs (vp_comm_connect_local): rank r
+        lives on (devices[r], ctx_slots[r]); no IPC handles, peer access between the devices. Several contexts
+        of one device work too. Each rank's collective calls (attach, set_params, fit) must then be made from
+        its own host thread, concurrently with the other ranks'."""
+        devices = list(devices) if devices is not None else [0] * world
+        ctx_slots = list(ctx_slots) if ctx_slots is not None else list(range(world))
+        comms = [cls(r, world, device=devices[r], ctx_slot=ctx_slots[r], connect=False) for r in range(world)]
+        if world > 1:
+            arr = (C.c_void_p * world)(*[c._h for c in comms])
+            _check(_lib.load().vp_comm_connect_local(arr, world), comms[0]._ctx.h)
+        return comms
 
     def attach(self, problem: SeparableProblem) -> SeparableProblem:
         """Make `problem` (built from this rank's columns) a shard of the global fit. Collective."""

@@ -166,7 +166,7 @@ void *vp_ctx_stream(const vp_ctx *ctx);
  *   eval_kernel     fused (default) | split (K1 panel kernel + K2 streaming kernel); applies to problems created later
  *   stream_kernel   auto (default) | simt | generic; applies to problems created later
  *   panel_generic, stream_stages, stream_ct, stream_occ, queue_items_per_cta, batch_slots, pool_mb,
- *   max_ctas (integers; max_ctas caps the grid of problems created later so that contexts can share a GPU)
+ *   max_ctas, fit_warps (integers; max_ctas caps the grid of problems created later so that contexts can share a GPU)
  *   trace, queue_dbg, dbg_fit (0 | 1: diagnostics on stderr / in-kernel timelines) */
 int vp_ctx_set_option(vp_ctx *ctx, const char *key, const char *value);
 /* Return the context's idle cached device / pinned buffers to the CUDA allocator (the cache is capped at
@@ -330,6 +330,11 @@ int vp_batch_linear_coefficients(vp_batch *batch, double *C_out);   /* n x P */
  * memory. */
 int vp_profile_evaluation(vp_problem *problem, int iters, int64_t flush_bytes, double *panel_us,
                           double *stream_us, int64_t *stream_grid, int64_t *stream_smem);
+
+/* fp64 ALU peaks of the context's GPU measured on its stream: dependent-chain-free DFMA throughput (TFLOP/s) and
+ * double-precision exp() throughput (Gexp/s). The denominators of the fp64-ALU roofline of the independent-batch
+ * kernel (bench.py); MEASURED_PEAKS.json has no fp64 entry. */
+int vp_measure_fp64_peaks(vp_ctx *ctx, double *dfma_tflops, double *dexp_gexps);
 
 /* One evaluation with the in-kernel timeline enabled (diagnostics): `out`
  * receives (grid+1)*16 %globaltimer stamps in ns relative to the earliest one,

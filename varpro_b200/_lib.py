@@ -91,6 +91,7 @@ SYMBOLS = {
     "vp_batch_params": (C.c_int, [_vp, _dp]),
     "vp_batch_set_params": (C.c_int, [_vp, _dp]),
     "vp_batch_linear_coefficients": (C.c_int, [_vp, _dp]),
+    "vp_measure_fp64_peaks": (C.c_int, [_vp, _dp, _dp]),
     "vp_debug_timeline": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.c_int64, C.POINTER(C.c_int64)]),
     "vp_profile_evaluation": (C.c_int, [_vp, C.c_int, C.c_int64, _dp, _dp, C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int64)]),

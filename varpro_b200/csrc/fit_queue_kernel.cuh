@@ -121,6 +121,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     __shared__ double alpha_s[VP_MAX_Q];
     __shared__ LmEval ev_s;
     __shared__ __align__(8) FitDevice fd_s;
+    __shared__ __align__(8) QueueFit qf_s; // the claimed fit's descriptor: ONE cooperative L2 read per item instead of chains of dependent loads
     __shared__ int is_last, item_fit, item_idx, more_s, nonfinite_s;
     __shared__ unsigned long long fin_acc[8]; // queue_dbg: finisher sub-phases
     __shared__ unsigned long long push_base;
@@ -144,8 +145,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     // Panel of fit k at the parameters in alpha_s -> HBM, then publish the items of the evaluation.
     // Executed by the whole CTA; all TMA stages must be idle (stage 0 is the staging area). xi / wi:
     // this thread's rows of the fit's x and w.
-    auto start_evaluation = [&](const int k, const double (&xi)[RPT], const double (&wi)[RPT], const int cdst) {
-        QueueFit *qf = &fits[k];
+    auto start_evaluation = [&](const int k, const QueueFit *qf, const double (&xi)[RPT], const double (&wi)[RPT], const int cdst) {
         const ModelDesc &md = qf->md;
         const unsigned long long ts0 = dbg_on ? global_timer_ns() : 0ull;
         {
@@ -164,7 +164,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         }
         fence_proxy_async_smem(); // generic writes to the staging area before later bulk copies into it
         if (tid == 0) {
-            qf->cdst = cdst;
+            fits[k].cdst = cdst;
             *qf->ticket = 0u;
         }
         __threadfence(); // panel, small outputs, cdst, ticket and (finisher) the stored LM state before the items
@@ -206,7 +206,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     // Fold the part rows of fit k, advance its lmder state machine, and either start the next
     // evaluation or retire the fit. Executed by a whole CTA with an idle TMA ring.
     auto finish_evaluation = [&](const int k) {
-        QueueFit *qf = &fits[k];
+        const QueueFit *qf = &qf_s; // the finisher just processed an item of fit k
         const int q = qf->md.q;
         const unsigned long long tf0 = dbg_on ? global_timer_ns() : 0ull;
         // everything the LM step and the next panel need that does not depend on the fold is requested
@@ -244,7 +244,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         for (int i = tid; i < FIT_WORDS; i += THREADS) fw[i] = lw[i];
         if (dbg_on && tid == 0) { fin_acc[0] += tf1 - tf0; fin_acc[1] += tf2 - tf1; }
         if (more_s) {
-            start_evaluation(k, xi, wi, fd_s.cur ^ 1); // fences the state stores before the items
+            start_evaluation(k, qf, xi, wi, fd_s.cur ^ 1); // fences the state stores before the items
         } else {
             __threadfence();
             __syncthreads();
@@ -265,13 +265,13 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
 
     // prologue: first panels (the host has advanced every fit to its first trial point)
     for (int k = blockIdx.x; k < nfits; k += gridDim.x) {
-        QueueFit *qf = &fits[k];
+        const QueueFit *qf = &fits[k];
         if (tid < VP_MAX_Q) alpha_s[tid] = tid < qf->md.q ? __ldcg(&qf->fit->st.x_trial[tid]) : 0.0;
         double xi[RPT], wi[RPT];
         load_xw(qf, xi, wi);
         const int cdst = __ldcg(&qf->fit->cur) ^ 1;
         __syncthreads();
-        start_evaluation(k, xi, wi, cdst);
+        start_evaluation(k, qf, xi, wi, cdst);
     }
 
     unsigned long long dacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // tid 0, only when ctl->dbg is set
@@ -295,8 +295,15 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         __syncthreads();
         const int k = item_fit, item = item_idx;
         if (k < 0) break;
+        {
+            static_assert(sizeof(QueueFit) % 8 == 0, "QueueFit is copied in 8-byte words");
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&fits[k]);
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(&qf_s);
+            for (int i = tid; i < (int)(sizeof(QueueFit) / 8); i += THREADS) dst[i] = __ldcg(src + i);
+        }
+        __syncthreads();
         const unsigned long long t_b = dbg_on ? global_timer_ns() : 0ull;
-        QueueFit *qf = &fits[k];
+        const QueueFit *qf = &qf_s;
         const int ld = qf->ld, S = qf->S, ldp = qf->ldp;
         const TY *Yk = static_cast<const TY *>(qf->Y);
         const TilePartition tpn = qf->part;
@@ -305,7 +312,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         const int t_begin = part_first_tile(tpn, p_begin);
         const int my = part_first_tile(tpn, p_end) - t_begin;
         const int nitems = qf->nitems;
-        TY *Cout = static_cast<TY *>(__ldcg(&qf->cdst) ? qf->C1 : qf->C0);
+        TY *Cout = static_cast<TY *>(qf->cdst ? qf->C1 : qf->C0);
         int ebasis[P > 0 ? P : 1];
 #pragma unroll
         for (int e2 = 0; e2 < P; ++e2) ebasis[e2] = qf->md.e_basis[e2];
@@ -370,9 +377,10 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
                 if (i >= 1 && next_i < my) issue(); // refill the stage tile i-1 used
                 if (pending_row >= 0) {             // the row of the part that ended with the previous tile
                     if (warp == NWARPS - 1) {
+                        // no fence here: the row is ordered before the item's ticket by the barriers in between
+                        // and the release of the ticket atomic (cumulative over the CTA's earlier writes)
                         part_flush<N, P, CT, NWARPS>(wsum_s[pending_buf], gv_s[pending_buf],
                                                      qf->partials + (size_t)pending_row * qf->red_stride, lane);
-                        __threadfence();
                     }
                     pending_row = -1;
                 }

@@ -156,6 +156,7 @@ static int parse_option(CtxOptions &o, const char *key, const char *value)
     if (k == "batch_slots") return as_int(o.batch_slots);
     if (k == "pool_mb") return as_int(o.pool_mb);
     if (k == "max_ctas") return as_int(o.max_ctas);
+    if (k == "fit_warps") return as_int(o.fit_warps);
     return VP_ERR_INVALID_ARGUMENT;
 }
 
@@ -166,7 +167,8 @@ static void options_from_env(CtxOptions &o)
         {"VP_FIT_MODE", "fit_mode"}, {"VP_EVAL_KERNEL", "eval_kernel"}, {"VP_STREAM_KERNEL", "stream_kernel"},
         {"VP_PANEL_GENERIC", "panel_generic"}, {"VP_STREAM_STAGES", "stream_stages"}, {"VP_STREAM_CT", "stream_ct"},
         {"VP_STREAM_OCC", "stream_occ"}, {"VP_QUEUE_ITEMS_PER_CTA", "queue_items_per_cta"}, {"VP_QUEUE_DBG", "queue_dbg"},
-        {"VP_TRACE", "trace"}, {"VP_DBG_FIT", "dbg_fit"}, {"VP_BATCH_SLOTS", "batch_slots"}, {"VP_POOL_MB", "pool_mb"}, {"VP_MAX_CTAS", "max_ctas"}};
+        {"VP_TRACE", "trace"}, {"VP_DBG_FIT", "dbg_fit"}, {"VP_BATCH_SLOTS", "batch_slots"}, {"VP_POOL_MB", "pool_mb"}, {"VP_MAX_CTAS", "max_ctas"},
+        {"VP_FIT_WARPS", "fit_warps"}};
     for (const auto &m : map) {
         const char *s = getenv(m[0]);
         if (s && *s) parse_option(o, m[1], s);

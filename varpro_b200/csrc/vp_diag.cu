@@ -97,3 +97,54 @@ extern "C" int vp_debug_timeline(vp_problem *pr, long long *out, int64_t capacit
     if (grid_out) *grid_out = (int64_t)rows;
     return VP_OK;
 }
+
+// ----------------------------------------------------------------------------
+// fp64 ALU peaks of this GPU, measured on the context's stream (bench.py: denominator of the fp64-ALU
+// roofline of the independent-batch kernel; MEASURED_PEAKS.json has no fp64 entry)
+// ----------------------------------------------------------------------------
+__global__ void vp_peak_dfma_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void vp_peak_dexp_kernel(double *out, int iters)
+{
+    double x = -1.0 - threadIdx.x * 1e-3, s = 0;
+    for (int i = 0; i < iters; ++i) { s += exp(x); x -= 1e-6; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int vp_measure_fp64_peaks(vp_ctx *ctx, double *dfma_tflops, double *dexp_gexps)
+{
+    if (!ctx) return VP_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 20000;
+    double *out = nullptr;
+    VP_CUDA(ctx, DEV_ALLOC(ctx, &out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t ev[4];
+    for (auto &e : ev) cudaEventCreate(&e);
+    for (int rep = 0; rep < 2; ++rep) { // first round warms up
+        cudaEventRecord(ev[0], ctx->stream);
+        vp_peak_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters);
+        cudaEventRecord(ev[1], ctx->stream);
+        cudaEventRecord(ev[2], ctx->stream);
+        vp_peak_dexp_kernel<<<blocks, threads, 0, ctx->stream>>>(out, iters / 10);
+        cudaEventRecord(ev[3], ctx->stream);
+        ctx->launches += 2;
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    float ms_fma = 0, ms_exp = 0;
+    cudaEventElapsedTime(&ms_fma, ev[0], ev[1]);
+    cudaEventElapsedTime(&ms_exp, ev[2], ev[3]);
+    for (auto &x : ev) cudaEventDestroy(x);
+    DEV_FREE(ctx, out);
+    if (e != cudaSuccess) return vp_fail(ctx, VP_ERR_CUDA, cudaGetErrorString(e));
+    if (dfma_tflops) *dfma_tflops = 2.0 * 8 * iters * (double)blocks * threads / ms_fma / 1e9;
+    if (dexp_gexps) *dexp_gexps = (double)(iters / 10) * blocks * threads / ms_exp / 1e6;
+    return VP_OK;
+}

@@ -230,8 +230,9 @@ static int queue_kernel_for(const vp_problem *pr, int *lds_out)
         const int rows = 4 * k.ksteps * k.nwarps;
         if (rows < mo->ld) continue;
         if (k.exact && rows > lds) continue;
-        const int prow = pick < 0 ? 0 : 4 * tab[(size_t)pick].ksteps * tab[(size_t)pick].nwarps;
-        if (pick < 0 || rows < prow || (rows == prow && k.exact && !tab[(size_t)pick].exact)) pick = (int)i;
+        if (pick < 0 || vp_better_tiling(k.ksteps, k.nwarps, k.exact, tab[(size_t)pick].ksteps, tab[(size_t)pick].nwarps,
+                                         tab[(size_t)pick].exact, pr->ctx->opt.fit_warps))
+            pick = (int)i;
     }
     if (lds_out) *lds_out = lds;
     return pick;
@@ -359,7 +360,6 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
     hctl->dbg = ddbg;
     e = cudaMemcpyAsync(db, hb, total_bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ditems, 0, sizeof(QueueItem) * (size_t)cap, ctx->stream);
-    for (int i = 0; i < K && e == cudaSuccess; ++i) e = cudaMemsetAsync(prs[(size_t)i]->ticket, 0, sizeof(unsigned int), ctx->stream);
     if (e == cudaSuccess) {
         int nf = K, lds_arg = lds, nst_arg = nst;
         void *args[] = {(void *)&dctl, (void *)&dq, (void *)&nf, (void *)&lds_arg, (void *)&nst_arg};

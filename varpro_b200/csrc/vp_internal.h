@@ -80,6 +80,7 @@ struct CtxOptions {
     int dbg_fit = 0;                  // 1: in-kernel timeline of the persistent fit (vp_debug_timeline reads it)
     int batch_slots = 8;              // independent-batch kernel: problems in flight per CTA
     int pool_mb = 1024;               // cap of the idle device-buffer cache
+    int fit_warps = 8;                // fused / work-queue kernels: preferred warps per CTA among the tilings that cover m
     int max_ctas = 0;                 // > 0: cap on the grid of the fused / streaming kernels (problems created later);
                                       // lets several contexts share one GPU concurrently
 };
@@ -204,6 +205,16 @@ struct KernelTables {
     std::vector<QueueKernelEntry> queue;
 };
 const KernelTables &vp_kernel_tables(); // thread-safe, built on first use
+
+// Row tilings of the DMMA-based kernels: (ksteps, nwarps) covers 4*ksteps*nwarps rows. Better = fewer rows (less
+// padding work), then the unpredicated EXACT variant, then the preferred warp count.
+inline bool vp_better_tiling(int ks, int nw, int exact, int ks0, int nw0, int exact0, int prefer_warps)
+{
+    const int rows = 4 * ks * nw, rows0 = 4 * ks0 * nw0;
+    if (rows != rows0) return rows < rows0;
+    if ((exact != 0) != (exact0 != 0)) return exact != 0;
+    return nw == prefer_warps && nw0 != prefer_warps;
+}
 
 // ----------------------------------------------------------------------------
 // internal entry points shared between the translation units

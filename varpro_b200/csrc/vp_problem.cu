@@ -14,9 +14,20 @@ static int plan_fit_kernel(vp_problem *pr, const DmmaKernelEntry &dk, int lds)
     if (ctx->opt.eval_split) return VP_OK;  // K1 + K2 requested
     if (pr->model->hosteval) return VP_OK; // the fused kernels evaluate the built-in device basis functions
     const KernelTables &KT = vp_kernel_tables();
+    // the best row tiling among the fused instantiations of this shape (independent of the split kernels' choice)
+    int pick = -1;
     for (size_t i = 0; i < KT.fit.size(); ++i) {
         const FitKernelEntry &k = KT.fit[i];
-        if (k.n != dk.n || k.p != dk.p || k.ksteps != dk.ksteps || k.nwarps != dk.nwarps || k.exact != dk.exact) continue;
+        if (k.n != dk.n || k.p != dk.p) continue;
+        const int rows = 4 * k.ksteps * k.nwarps;
+        if (rows < pr->model->ld || (k.exact && rows > lds)) continue;
+        if (pick < 0 || vp_better_tiling(k.ksteps, k.nwarps, k.exact, KT.fit[(size_t)pick].ksteps, KT.fit[(size_t)pick].nwarps,
+                                         KT.fit[(size_t)pick].exact, ctx->opt.fit_warps))
+            pick = (int)i;
+    }
+    for (size_t i = 0; i < KT.fit.size(); ++i) {
+        if ((int)i != pick) continue;
+        const FitKernelEntry &k = KT.fit[i];
         const size_t stage_bytes = (size_t)DMMA_CT * lds * sizeof(double);
         cudaFuncAttributes fa{};
         VP_CUDA(ctx, cudaFuncGetAttributes(&fa, k.fn));
@@ -38,6 +49,7 @@ static int plan_fit_kernel(vp_problem *pr, const DmmaKernelEntry &dk, int lds)
         if (grid > ntiles) grid = ntiles;
         if (grid > pr->max_grid) grid = pr->max_grid;
         pr->plan_fit = (int)i;
+        if (4 * k.ksteps * k.nwarps > pr->plan_rows) pr->plan_rows = 4 * k.ksteps * k.nwarps;
         pr->fit_grid = (int)grid;
         pr->fit_nst = nst;
         pr->fit_smem = smem;

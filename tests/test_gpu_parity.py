@@ -345,6 +345,32 @@ def test_fit_many_is_bitwise_vp_fit(ctx_options, items_per_cta):
         vb.set_option("queue_items_per_cta", 2)
 
 
+def test_fit_many_is_deterministic_and_bitwise_vp_fit_on_the_2048_row_tiling():
+    """m = 1500 runs the 16-warp tiling of the fused kernels (1024 < m <= 2048): repeated vp_fit_many launches and
+    vp_fit must agree bitwise there too (different thread count, same canonical partition)."""
+    import varpro_b200 as vb
+    solver = vb.LevMarSolver.default()
+    rng = np.random.default_rng(9)
+    m = 1500
+    x = np.linspace(0.0, 12.0, m)
+    wls = []
+    for k in range(6):
+        tau = (1.0 + 0.1 * k, 3.0 + 0.3 * k)
+        S = 700 + 64 * k
+        Cs = rng.uniform(0.0, 100.0, size=(3, S))
+        Phi = np.stack([np.exp(-x / tau[0]), np.exp(-x / tau[1]), np.ones_like(x)], axis=1)
+        wls.append(dict(x=x, Y=np.asfortranarray(Phi @ Cs), basis=W.DOUBLE_EXP, q=2, alpha0=[2.0, 6.5], weights=None))
+    seq = [solver.fit(W.make_gpu_problem(wl)) for wl in wls]
+    ref = [(r.nonlinear_parameters(), r.minimization_report.number_of_evaluations, r.linear_coefficients()) for r in seq]
+    for rep in range(4):
+        many = solver.fit_many([W.make_gpu_problem(wl) for wl in wls])
+        for (a, nf, Cc), b in zip(ref, many):
+            assert b.was_successful()
+            assert np.array_equal(a, b.nonlinear_parameters()), rep
+            assert nf == b.minimization_report.number_of_evaluations, rep
+            assert np.array_equal(Cc, b.linear_coefficients()), rep
+
+
 # fp32 (BASELINE config 4). The reference is generic over the scalar but no reference test runs an f32
 # fit (SURVEY.md 8c "unpinned"), so fp32 results are pinned against the fp64 oracle on the SAME
 # (fp32-rounded) inputs. Stated tolerances: the kernels keep Q, E and Y in fp32 (eps = 6e-8) and

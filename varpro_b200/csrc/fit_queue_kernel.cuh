@@ -7,7 +7,10 @@
 //   part       = one entry of the canonical partition of a problem's tiles (dmma_tile.cuh): the SAME
 //                partition, and therefore bitwise the same partial sums, as fit_kernel_dmma uses
 //   work item  = (fit k, item j): `parts_per_item` consecutive parts of fit k at its current trial
-//                parameters (fixed for the whole launch: sized from the number of fits)
+//                parameters. The finisher sizes the items of every evaluation from the number of fits still
+//                running (about items_per_cta items per CTA and round): many fits -> few large items per
+//                fit (little per-item overhead), last fits -> one part per item (the whole grid serves the
+//                tail). The partial sums are per PART, so the item size never changes a result.
 //   any CTA    : claims the next item (atomic head counter, per-slot sequence flag), loads the
 //                DMMA A-fragments of fit k's panel [Q|E] from L2, streams the item's tiles through
 //                the TMA ring (tile math of dmma_tile.cuh), writes one partial row per part and takes
@@ -44,10 +47,12 @@ struct QueueFit {
     int ld, S, ldp, red_stride;
     int ntiles;
     TilePartition part; // canonical partition (one partial row per part)
-    int parts_per_item, nitems;
+    int items_per_cta;  // work-item sizing target (ctx option queue_items_per_cta)
     int jac_full;
-    // set by the finisher for every evaluation (read by the consumers with ld.global.cg):
-    int cdst;         // coefficient buffer the current evaluation writes
+    // set by the finisher for every evaluation (the consumers copy the descriptor with ld.global.cg):
+    int parts_per_item, nitems; // work items of the current evaluation: item j = parts [j*ppi, (j+1)*ppi)
+    int cdst;           // coefficient buffer the current evaluation writes
+    int pad_;
 };
 
 struct QueueItem {
@@ -122,7 +127,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     __shared__ LmEval ev_s;
     __shared__ __align__(8) FitDevice fd_s;
     __shared__ __align__(8) QueueFit qf_s; // the claimed fit's descriptor: ONE cooperative L2 read per item instead of chains of dependent loads
-    __shared__ int is_last, item_fit, item_idx, more_s, nonfinite_s;
+    __shared__ int is_last, item_fit, item_idx, more_s, nonfinite_s, push_n;
     __shared__ unsigned long long fin_acc[8]; // queue_dbg: finisher sub-phases
     __shared__ unsigned long long push_base;
 
@@ -164,6 +169,16 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         }
         fence_proxy_async_smem(); // generic writes to the staging area before later bulk copies into it
         if (tid == 0) {
+            // items of this evaluation: about items_per_cta items per CTA over the fits still running
+            int active = ld_acquire_gpu_s32(&ctl->fits_left);
+            if (active < 1) active = 1;
+            const int nparts = qf->part.nparts;
+            int want = (qf->items_per_cta * (int)gridDim.x + active - 1) / active;
+            want = want < 1 ? 1 : (want > nparts ? nparts : want);
+            const int ppi = (nparts + want - 1) / want;
+            push_n = (nparts + ppi - 1) / ppi;
+            fits[k].parts_per_item = ppi;
+            fits[k].nitems = push_n;
             fits[k].cdst = cdst;
             *qf->ticket = 0u;
         }
@@ -171,9 +186,9 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         __syncthreads();
         const unsigned long long ts1 = dbg_on ? global_timer_ns() : 0ull;
         if (dbg_on && tid == 0) fin_acc[3] += ts1 - ts0;
-        const int nitems = qf->nitems;
-        if (tid == 0) push_base = atomicAdd(&ctl->tail, (unsigned long long)nitems);
+        if (tid == 0) push_base = atomicAdd(&ctl->tail, (unsigned long long)push_n);
         __syncthreads();
+        const int nitems = push_n;
         // publish the items: all threads fill slots, one fence, then the sequence flags (a slot is
         // valid once its flag holds item index + 1; consumers read it with ld.acquire)
         {

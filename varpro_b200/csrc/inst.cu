@@ -34,7 +34,7 @@ static const FitKernelEntry fit_tab[] = {VP_FK(8, 4, 0), VP_FK(16, 8, 0)};
 #elif VP_INST_VARIANT == 1
 static const FitKernelEntry fit_tab[] = {VP_FK(32, 8, 0), VP_FK(32, 8, 1)};
 #else
-static const FitKernelEntry fit_tab[] = {VP_FK(32, 16, 0), VP_FK(16, 16, 0), VP_FK(16, 16, 1)};
+static const FitKernelEntry fit_tab[] = {VP_FK(32, 16, 0)};
 #endif
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, fit_tab, (int)(sizeof(fit_tab) / sizeof(fit_tab[0]))};
 #elif VP_INST_PART == 5
@@ -44,7 +44,7 @@ static const QueueKernelEntry queue_tab[] = {VP_QK(8, 4, 0), VP_QK(16, 8, 0)};
 #elif VP_INST_VARIANT == 1
 static const QueueKernelEntry queue_tab[] = {VP_QK(32, 8, 0), VP_QK(32, 8, 1)};
 #else
-static const QueueKernelEntry queue_tab[] = {VP_QK(32, 16, 0), VP_QK(16, 16, 0), VP_QK(16, 16, 1)};
+static const QueueKernelEntry queue_tab[] = {VP_QK(32, 16, 0)};
 #endif
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, queue_tab, (int)(sizeof(queue_tab) / sizeof(queue_tab[0]))};
 #elif VP_INST_PART == 4

@@ -281,9 +281,6 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
     const size_t smem = plan->smem;
     const long long grid = (long long)ctx->sm_count * occ;
 
-    // work-item size: about queue_items_per_cta items per CTA and evaluation round over the K fits, FIXED for the
-    // whole launch; the partial sums are per part of the canonical partition and do not depend on it
-    const long long target_items = (ctx->opt.queue_items_per_cta * grid + K - 1) / K;
     std::vector<QueueFit> hq((size_t)K);
     long long total_items = 0;
     for (int i = 0; i < K; ++i) {
@@ -315,13 +312,12 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         int nparts = pr->plan_fit >= 0 ? pr->fit_grid : (f.ntiles < ctx->sm_count ? f.ntiles : ctx->sm_count);
         if (nparts > pr->max_grid) nparts = pr->max_grid;
         f.part = make_partition(f.ntiles, nparts);
-        long long want = target_items < 1 ? 1 : target_items;
-        if (want > f.part.nparts) want = f.part.nparts;
-        f.parts_per_item = (int)((f.part.nparts + want - 1) / want);
-        f.nitems = (f.part.nparts + f.parts_per_item - 1) / f.parts_per_item;
+        f.items_per_cta = ctx->opt.queue_items_per_cta; // the kernel sizes the work items of every evaluation itself
+        f.parts_per_item = f.part.nparts;
+        f.nitems = 1;
         f.jac_full = pr->jac_full;
         f.cdst = pr->cur ^ 1;
-        total_items += f.nitems;
+        total_items += f.part.nparts; // upper bound of the items one evaluation of this fit can have
     }
     // One pinned host block and one device block: [FitDevice x K | QueueCtl | QueueFit x K]. One copy
     // in; one copy out (states + control word).
@@ -379,10 +375,10 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
                 for (int i = 0; i < QDBG_SLOTS; ++i) acc[i] += (double)hd[(size_t)b * QDBG_SLOTS + i];
             const double it = acc[QDBG_ITEMS] > 0 ? acc[QDBG_ITEMS] : 1, nfin = acc[QDBG_NFINISH] > 0 ? acc[QDBG_NFINISH] : 1;
             const double nstart = acc[13] > 0 ? acc[13] : 1;
-            fprintf(stderr, "[vp queue dbg] fits %d items %.0f (%.1f per CTA; %d parts/item) | per item: claim %.2f us, fragments %.2f us, "
+            fprintf(stderr, "[vp queue dbg] fits %d items %.0f (%.1f per CTA) | per item: claim %.2f us, fragments %.2f us, "
                             "stream %.2f us, publish %.2f us | finisher %.2f us x %.0f = fold+assemble %.2f, LM step %.2f, basis %.2f, "
                             "panel (basis+factor+store) %.2f, push %.2f | CTA lifetime %.1f us, busy %.1f %%\n",
-                    K, acc[QDBG_ITEMS], acc[QDBG_ITEMS] / grid, hq[0].parts_per_item, 1e-3 * acc[QDBG_CLAIM] / it,
+                    K, acc[QDBG_ITEMS], acc[QDBG_ITEMS] / grid, 1e-3 * acc[QDBG_CLAIM] / it,
                     1e-3 * acc[QDBG_FRAG] / it, 1e-3 * acc[QDBG_STREAM] / it, 1e-3 * acc[QDBG_PUBLISH] / it,
                     1e-3 * acc[QDBG_FINISH] / nfin, acc[QDBG_NFINISH], 1e-3 * acc[QDBG_F_FOLD] / nfin, 1e-3 * acc[QDBG_F_LM] / nfin,
                     1e-3 * acc[QDBG_F_BASIS] / nstart, 1e-3 * acc[QDBG_F_FACTOR] / nstart, 1e-3 * acc[QDBG_F_PUSH] / nstart,

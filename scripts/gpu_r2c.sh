@@ -3,7 +3,7 @@
 # e2e host-thread sweep.
 TAG=${1:-r2c}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -k "bitwise or deterministic or fit_many or world2 or c4_fp32 or different_sizes" > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
+timeout 600 python -m pytest tests -m gpu -q -x -k "bitwise or deterministic or fit_many or reusable or world2 or c_program" > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/${TAG}_pytest_gpu.log
 tail -8 gpurun_out/${TAG}_pytest_gpu.log
 summ='import json,sys
 d=json.loads(sys.stdin.read()); print("value",round(d["value"]),"frac",round(d["roofline"]["frac"],3),"evals",d["config"]["evals_per_fit_mean"],"launch_ms",d["config"]["launch_ms"],"K1",round(d["by_concurrency"]["1"]["fits_per_s"]),"latency",round(d["latency_mode"]["value"]),"e2e",round(d["e2e"]["value"]), "raw_h2d", round(d["e2e"]["h2d_GBps_raw_memcpy_all_ranks_concurrent"],1))'

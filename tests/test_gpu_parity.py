@@ -345,6 +345,26 @@ def test_fit_many_is_bitwise_vp_fit(ctx_options, items_per_cta):
         vb.set_option("queue_items_per_cta", 2)
 
 
+def test_problems_are_reusable_after_fit_many():
+    """vp_fit_many leaves every problem ready for the next call: set_params back to the start gives bitwise the
+    evaluation of a fresh problem (the per-problem ticket is re-armed), and a second fit_many repeats the first."""
+    import varpro_b200 as vb
+    solver = vb.LevMarSolver.default()
+    wls = [W.c2(S=900 + 100 * k, seed=500 + k) for k in range(7)]
+    probs = [W.make_gpu_problem(wl) for wl in wls]
+    fresh = [W.make_gpu_problem(wl).reduce() for wl in wls]
+    first = solver.fit_many(probs)
+    ref = [(r.nonlinear_parameters(), r.minimization_report.number_of_evaluations) for r in first]
+    for rep in range(3):
+        for p, wl, fr in zip(probs, wls, fresh):
+            p.set_params(wl["alpha0"])
+            red = p.reduce()
+            assert red["rnorm2"] == fr["rnorm2"] and np.array_equal(red["H"], fr["H"]) and np.array_equal(red["g"], fr["g"])
+        again = solver.fit_many(probs)
+        for (a, nf), b in zip(ref, again):
+            assert np.array_equal(a, b.nonlinear_parameters()) and nf == b.minimization_report.number_of_evaluations
+
+
 def test_fit_many_is_deterministic_and_bitwise_vp_fit_on_the_2048_row_tiling():
     """m = 1500 runs the 16-warp tiling of the fused kernels (1024 < m <= 2048): repeated vp_fit_many launches and
     vp_fit must agree bitwise there too (different thread count, same canonical partition)."""

@@ -175,7 +175,8 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             const int nparts = qf->part.nparts;
             int want = (qf->items_per_cta * (int)gridDim.x + active - 1) / active;
             want = want < 1 ? 1 : (want > nparts ? nparts : want);
-            const int ppi = (nparts + want - 1) / want;
+            int ppi = (nparts + want - 1) / want;
+            if (qf->items_per_cta < 0) ppi = -qf->items_per_cta > nparts ? nparts : -qf->items_per_cta; // fixed size (diagnostics)
             push_n = (nparts + ppi - 1) / ppi;
             fits[k].parts_per_item = ppi;
             fits[k].nitems = push_n;
@@ -235,6 +236,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         load_xw(qf, xi, wi);
         // rinv_s still holds Rinv of this fit's current panel (loaded with the item's fragments)
         fold_rows(qf->partials, qf->red_stride, qf->part.nparts, NVF, sums_s, fold_scratch);
+        if (tid == 0) *qf->ticket = 0u; // re-arm: the next evaluation of this problem may be a single-evaluation launch (vp_set_params)
         fused_assemble<N, P>(sums_s, Msh, P, rinv_s, qf->md.e_basis, qf->md.e_param, q, qf->jac_full, nonfinite_s, &ev_s);
         const unsigned long long tf1 = dbg_on ? global_timer_ns() : 0ull;
         if (tid == 0) {

@@ -312,7 +312,8 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         int nparts = pr->plan_fit >= 0 ? pr->fit_grid : (f.ntiles < ctx->sm_count ? f.ntiles : ctx->sm_count);
         if (nparts > pr->max_grid) nparts = pr->max_grid;
         f.part = make_partition(f.ntiles, nparts);
-        f.items_per_cta = ctx->opt.queue_items_per_cta; // the kernel sizes the work items of every evaluation itself
+        // the kernel sizes the work items of every evaluation itself (negative: fixed number of parts per item)
+        f.items_per_cta = ctx->opt.queue_parts_per_item > 0 ? -ctx->opt.queue_parts_per_item : ctx->opt.queue_items_per_cta;
         f.parts_per_item = f.part.nparts;
         f.nitems = 1;
         f.jac_full = pr->jac_full;

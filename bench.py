@@ -18,10 +18,11 @@ criterion bench builds the problem in its un-timed setup closure and times `fit`
           between); value comes from the MEDIAN launch, min / max are reported next to it.
           `by_concurrency` repeats this for K = 1 (one fit on the whole GPU: vp_fit, L2 flushed before
           every launch), K = --steps and K = 60; `latency_mode` is the K fits made one after the other.
-  e2e   : the same metric through the reference-facing API with HOST buffers: every step builds
-          the problem from pinned host memory (H2D of Y inside the timed region), fits, and
-          reads parameters + linear coefficients back (D2H); a few host threads pipeline steps so
-          that one step's copy overlaps another step's fit (PCIe-bound: 33.6 MB per step). The line
+  e2e   : the same metric through the reference-facing API with HOST buffers (LevMarSolver.fit_host_batch =
+          vp_fit_host_batch): every step builds the problem from pinned host memory (H2D of Y inside the
+          timed region), fits, and reads parameters + linear coefficients back (D2H); three worker threads
+          of the library pipeline steps so that one step's copy overlaps another step's fit (PCIe-bound:
+          33.6 MB per step). The line
           carries the achieved H2D GB/s per GPU next to the raw pinned-memcpy bandwidth measured in
           the same run with all ranks copying at once (the ceiling of this number).
   roofline : the dominant kernel of the timed region (fit_queue_kernel): algorithmic bytes = 8*m*S per
@@ -308,7 +309,6 @@ def run_gpu(args, rank, world, local_rank):
     # host memory (one H2D of Y per step), fit, read the step's parameters and coefficients back (D2H). The
     # copies of one thread overlap the fits of another; every step still pays its own copies.
     NTH = int(os.environ.get("VP_E2E_THREADS", "3"))
-    CH = int(os.environ.get("VP_E2E_CHUNK", "1"))  # steps a worker builds, fits together (vp_fit_many) and reads back
     Yh = [torch.from_numpy(np.ascontiguousarray(wls[i % K]["Y"].T)).pin_memory() for i in range(NTH)]  # (S, m) row-major == m x S col-major
     Yv = [y.numpy().T for y in Yh]  # Fortran-ordered views of the pinned buffers
     h2d = Yh[0].numel() * 8 + M * 8
@@ -323,33 +323,30 @@ def run_gpu(args, rank, world, local_rank):
     raw_gbps = 8 * Yh[0].numel() * 8 / (time.perf_counter() - t0) / 1e9
     del dst
 
-    def e2e_chunk(slot, nsteps):
-        ps = [W.make_gpu_problem(wls[slot % K], Y=Yv[slot], device=local_rank, ctx_slot=1 + slot) for _ in range(nsteps)]  # H2D per step
-        rs = solver.fit_many(ps) if nsteps > 1 else [solver.fit(ps[0])]
-        out = [(r.nonlinear_parameters(), r.linear_coefficients()) for r in rs]  # D2H per step
-        for p in ps:
-            p.close()
-        return out
-
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(NTH)
+    # The call a user makes for a set of host-resident data sets: LevMarSolver.fit_host_batch (vp_fit_host_batch):
+    # NTH worker threads of the library, one stream each, build -> fit -> read back one problem after the other.
+    model_e2e = (vb.SeparableModelBuilder(["p0", "p1"]).function(["p0"], vb.ExpDecay()).function(["p1"], vb.ExpDecay())
+                 .invariant_function(vb.Constant()).independent_variable(wls[0]["x"]).initial_parameters(alpha0).build())
+    E2E_STEPS = int(os.environ.get("VP_E2E_STEPS", str(max(K, 60))))  # a longer region than K steps: ~40 ms instead of 14
 
     def e2e_run(nsteps):
-        chunks = [min(CH, nsteps - i) for i in range(0, nsteps, CH)]
-        futs = [pool.submit(e2e_chunk, i % NTH, c) for i, c in enumerate(chunks)]
-        return [o for f in futs for o in f.result()]
+        ys = [Yv[i % NTH] for i in range(nsteps)]
+        reports, alpha, Cs = solver.fit_host_batch(model_e2e, ys, device=local_rank, workers=NTH)
+        assert all(r.termination.was_successful() for r in reports)
+        return alpha, Cs
 
-    e2e_run(max(Wm, NTH * CH))
+    e2e_run(max(Wm, 2 * NTH))
     e2e_times = []
     for _ in range(3):
         barrier()
         t0 = time.perf_counter()
-        outs = e2e_run(K)
+        alpha_e, Cs_e = e2e_run(E2E_STEPS)
         torch.cuda.synchronize()
-        e2e_times.append(max_over_ranks(time.perf_counter() - t0))
-        assert len(outs) == K
+        e2e_times.append(max_over_ranks(time.perf_counter() - t0) * K / E2E_STEPS)  # seconds per K steps
+    for i in range(min(NTH, E2E_STEPS)):
+        t = np.sort(np.asarray(wls[i % K]["alpha_true"], dtype=np.float64))
+        assert np.max(np.abs(np.sort(alpha_e[i]) - t) / t) <= 1e-8
     clocks.__exit__(None, None, None)
-    pool.shutdown()
     e2e_dt = _stats(e2e_times)["median"]
     e2e_val = world * K / e2e_dt
 
@@ -420,7 +417,8 @@ def run_gpu(args, rank, world, local_rank):
                        "fit_many_equals_fit": "same evaluation counts as the sequential vp_fit runs (asserted)"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_val, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "host_threads": NTH, "steps_per_chunk": CH, "runs_s": e2e_times,
+                    "host_threads": NTH, "timed_steps": E2E_STEPS, "api": "LevMarSolver.fit_host_batch -> vp_fit_host_batch",
+                    "runs_s_per_K_steps": e2e_times,
                     "h2d_GBps_per_gpu": K * h2d / e2e_dt / 1e9,
                     "h2d_GBps_raw_memcpy_all_ranks_concurrent": raw_gbps,
                     "ceiling": "the PCIe link of each GPU (Gen5 x16): every step moves 33.6 MB host-to-device"},

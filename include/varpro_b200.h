@@ -239,6 +239,16 @@ int vp_best_fit_device(vp_problem *problem, void *out_device);
  * host-driven LM loop. Re-evaluates at the current parameters. */
 enum { VP_JACOBIAN_KAUFMAN = 0, VP_JACOBIAN_FULL = 1 };
 int vp_problem_set_jacobian(vp_problem *problem, int mode);
+/* Which singular values of Phi_w count as zero in the inner solve C = Phi_w^+ Y_w:
+ * VP_RANK_ABSOLUTE (default) = the reference: sigma_i <= svd_eps is truncated (src/solvers/levmar/mod.rs:52-54;
+ * svd_eps = SeparableProblemBuilder::epsilon, default machine epsilon), the residual is formed with that C (:57-59)
+ * and the Jacobian keeps the UNtruncated projector (:123-124).
+ * VP_RANK_RELATIVE = the original MATLAB rule sigma_i <= m * eps_machine * sigma_1 (matlab/varpro.m:642-643), the
+ * robust choice for nearly collinear basis functions (two equal decay times, tau -> infinity next to a constant).
+ * The decision is made on the n x n triangle of the panel's QR factorisation; full-rank panels pay nothing.
+ * Re-evaluates at the current parameters. */
+enum { VP_RANK_ABSOLUTE = 0, VP_RANK_RELATIVE = 1 };
+int vp_problem_set_rank_policy(vp_problem *problem, int policy);
 /* ||r||^2, J^T r and J^T J of the current parameters without materialising r or J */
 int vp_reduce(vp_problem *problem, vp_reduced *out);
 
@@ -285,6 +295,20 @@ int vp_fit(vp_problem *problem, const vp_lm_options *options, vp_fit_report *rep
 int vp_fit_many(vp_problem **problems, int64_t n, const vp_lm_options *options, vp_fit_report *reports,
                 int32_t reserved);
 
+/* Fit n_problems problems of ONE model whose observations live in HOST memory (pinned memory for full PCIe
+ * speed), pipelined: `workers` (<= 0: 3) threads of the library, each with its own stream on ctx's device, build
+ * (vp_problem_create: the host-to-device copy), fit (vp_fit) and read back (vp_params -> alpha_out + i*q,
+ * vp_linear_coefficients -> C_outs[i], n x S in dtype; C_outs or entries of it may be NULL) one problem after the
+ * other, so the copy of one problem overlaps the fit of another. Equivalent to that loop over the reference API
+ * (src/problem/builder.rs:116-324 + src/solvers/levmar/mod.rs:238-254 per data set); results are those of vp_fit.
+ * Y_hosts: n_problems pointers to m x S column-major matrices with leading dimension ldY. alpha0: q shared initial
+ * parameters. Returns the first error. */
+int vp_fit_host_batch(vp_ctx *ctx, int dtype, int64_t m, const void *x_host, int32_t q, int32_t n,
+                      const vp_basis_desc *basis, int64_t n_problems, int64_t S, const void *const *Y_hosts,
+                      int64_t ldY, const void *w_host, double svd_eps, const double *alpha0,
+                      const vp_lm_options *options, int32_t workers, vp_fit_report *reports, double *alpha_out,
+                      void *const *C_outs);
+
 /* ---- fit statistics: replaces FitStatistics::try_calculate (src/statistics/mod.rs:352-441) ----
  * The reference computes statistics for a single right-hand side only
  * (src/solvers/levmar/mod.rs:269-278); here the same calculation is applied to EVERY
@@ -317,6 +341,7 @@ int vp_batch_destroy(vp_batch *batch);
 int vp_batch_fit(vp_batch *batch, const vp_lm_options *options, vp_fit_report *reports);
 int vp_batch_params(vp_batch *batch, double *alpha_out);            /* q x P */
 int vp_batch_set_params(vp_batch *batch, const double *alpha);      /* q x P */
+int vp_batch_set_rank_policy(vp_batch *batch, int policy);          /* VP_RANK_* */
 int vp_batch_linear_coefficients(vp_batch *batch, double *C_out);   /* n x P */
 
 /* ---- diagnostics ---------------------------------------------------------

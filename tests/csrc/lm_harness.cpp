@@ -4,6 +4,7 @@
 // Test infrastructure only.
 #include <cstring>
 #include "../../varpro_b200/csrc/lm_step.cuh"
+#include "../../varpro_b200/csrc/rank_policy.cuh"
 
 using namespace vp;
 
@@ -47,4 +48,17 @@ int lmh_last_accepted(const Harness *h) { return h->st.last_accepted; }
 double lmh_fnorm(const Harness *h) { return h->st.fnorm; }
 double lmh_par(const Harness *h) { return h->st.par; }
 double lmh_delta(const Harness *h) { return h->st.delta; }
+
+// rank policy (rank_policy.cuh): R is n x n upper triangular, column-major with leading dimension n.
+// Returns 1 if the cheap bound proves full rank (then the outputs are untouched), else runs the SVD path:
+// truncated flag, Urot = Ur diag(keep), RinvEff = V diag(keep / sigma), both n x n column-major.
+int rph_policy(int n, const double *R, const double *Rinv, double tol, int *truncated, double *Urot, double *RinvEff)
+{
+    if (rank_surely_full(n, R, n, Rinv, n, tol)) return 1;
+    SmallSvd sv;
+    rank_policy_svd(n, R, n, tol, &sv);
+    *truncated = sv.truncated;
+    for (int i = 0; i < n * n; ++i) { Urot[i] = sv.Urot[i]; RinvEff[i] = sv.RinvEff[i]; }
+    return 0;
+}
 }

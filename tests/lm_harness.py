@@ -9,10 +9,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "lm_harness.cpp")
 LIB = os.path.join(HERE, "csrc", "liblm_harness.so")
 DEP = os.path.join(HERE, "..", "varpro_b200", "csrc", "lm_step.cuh")
+DEP2 = os.path.join(HERE, "..", "varpro_b200", "csrc", "rank_policy.cuh")
 
 
 def build():
-    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(DEP)):
+    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(DEP), os.path.getmtime(DEP2)):
         subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", LIB, SRC],
                        check=True, capture_output=True)
     return LIB
@@ -37,6 +38,8 @@ def lib():
         for n in ("lmh_fnorm", "lmh_par", "lmh_delta"):
             getattr(L, n).argtypes = [C.c_void_p]
             getattr(L, n).restype = C.c_double
+        L.rph_policy.restype = C.c_int
+        L.rph_policy.argtypes = [C.c_int, dp, dp, C.c_double, C.POINTER(C.c_int), dp, dp]
         L.lmh_set_generic.argtypes = [C.c_void_p, C.c_int]
         L.lmh_state_bytes.restype = C.c_int
         L.lmh_state.argtypes = [C.c_void_p, C.c_void_p]
@@ -108,3 +111,16 @@ def fit_with_oracle_evals(op, x0, **kw):
                           delta=h.delta, accepted=h.last_accepted))
         x = h.trial()
     return h, trace
+
+
+def rank_policy(R, tol):
+    """rank_policy.cuh on the host: (surely_full, truncated, Urot, RinvEff) for an upper triangular R."""
+    R = np.asfortranarray(R, dtype=np.float64)
+    n = R.shape[0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Rinv = np.asfortranarray(np.linalg.inv(R) if np.all(np.diag(R) != 0) else np.full((n, n), np.inf))
+    trunc = C.c_int(0)
+    U = np.zeros((n, n), order="F")
+    Ri = np.zeros((n, n), order="F")
+    full = lib().rph_policy(n, _dp(R), _dp(Rinv), float(tol), C.byref(trunc), _dp(U), _dp(Ri))
+    return bool(full), bool(trunc.value), U, Ri

@@ -345,3 +345,109 @@ def test_c4_statistics_full_size_column_sample():
     # column 0 is the reference's lmfit asset (weighted goldens, tests/integration_tests/main.rs:616-688)
     gold = W.lmfit_case(True)
     assert np.max(np.abs(stats[0].covariance_matrix() - gold["covmat"]) / np.sqrt(np.outer(np.diag(gold["covmat"]), np.diag(gold["covmat"])))) <= 0.25
+
+
+# ---------------------------------------------------------------------------------------------------
+# (c) rank-deficient panels: the reference's singular-value rule, MATLAB's relative rule
+# ---------------------------------------------------------------------------------------------------
+def _pinv_solution(wl, alpha, thr_abs=None, thr_rel=None):
+    """C and R of the truncated-SVD solve on the host (numpy), with the given singular-value threshold."""
+    x = wl["x"]
+    w = wl["weights"] if wl.get("weights") is not None else np.ones_like(x)
+    Phi = w[:, None] * np.stack([np.exp(-x / alpha[0]), np.exp(-x / alpha[1]), np.ones_like(x)], axis=1)
+    U, s, Vt = np.linalg.svd(Phi, full_matrices=False)
+    thr = thr_abs if thr_abs is not None else thr_rel * s[0]
+    inv = np.where(s > thr, 1.0 / s, 0.0)
+    Yw = w[:, None] * wl["Y"]
+    Cc = (Vt.T * inv) @ (U.T @ Yw)
+    return Cc, Yw - Phi @ Cc, s
+
+
+@pytest.mark.parametrize("S", [1, 50])
+def test_rank_deficient_panel_absolute_rule_matches_the_oracle(S):
+    """Two EQUAL decay times (Phi has two identical columns) and tau -> 1e9 next to the constant (nearly collinear):
+    with an epsilon well above the rounding level both the oracle (reference rule: sigma <= eps truncated in the
+    solve, src/solvers/levmar/mod.rs:52-54) and the GPU truncate the same singular value: minimum-norm coefficients,
+    residuals and ||r||^2 agree. (The Jacobian of a rank-deficient panel is implementation-defined in the reference
+    itself -- its projector keeps an arbitrary direction for the vanishing singular value -- and is not compared.)"""
+    rng = np.random.default_rng(31)
+    m = 300
+    x = np.linspace(0.0, 10.0, m)
+    Cs = rng.uniform(1.0, 5.0, size=(3, S))
+    Phi = np.stack([np.exp(-x / 1.5), np.exp(-x / 4.0), np.ones_like(x)], axis=1)
+    Y = np.asfortranarray(Phi @ Cs + 1e-3 * rng.standard_normal((m, S)))
+    for alpha, eps in [([2.0, 2.0], 1e-8), ([2.0, 1e9], 1e-6)]:
+        wl = dict(x=x, Y=Y, basis=W.DOUBLE_EXP, q=2, alpha0=alpha, weights=None)
+        import varpro_b200 as vb
+        names = ["p0", "p1"]
+        model = (vb.SeparableModelBuilder(names).function(["p0"], vb.ExpDecay()).function(["p1"], vb.ExpDecay())
+                 .invariant_function(vb.Constant()).independent_variable(x).initial_parameters(alpha).build())
+        pb = vb.SeparableProblemBuilder.new(model) if S == 1 else vb.SeparableProblemBuilder.mrhs(model)
+        gp = pb.observations(Y[:, 0] if S == 1 else Y).epsilon(eps).build()
+        from oracle import varpro_oracle as vo
+        op = vo.OracleProblem(x, W.DOUBLE_EXP, 2, Y, alpha, weights=None, eps=eps)
+        C_o, r_o = op.linear_coefficients(), op.residuals()
+        C_np, R_np, s = _pinv_solution(wl, alpha, thr_abs=eps)
+        assert (s <= eps).sum() == 1 and np.max(np.abs(C_o - C_np)) <= 1e-7 * np.abs(C_np).max()  # the oracle truncates one value
+        C_g = gp.linear_coefficients().reshape(3, S)
+        assert np.isfinite(C_g).all()
+        assert np.max(np.abs(C_g - C_o)) <= 1e-7 * max(1.0, np.abs(C_o).max()), (alpha, C_g[:, 0], C_o[:, 0])
+        r_g = gp.residuals()
+        assert np.max(np.abs(r_g - r_o)) <= 1e-8 * np.linalg.norm(Y)
+        red = gp.reduce()
+        assert abs(red["rnorm2"] - r_o @ r_o) <= 1e-8 * (r_o @ r_o)
+        if alpha[0] == alpha[1]:
+            assert np.max(np.abs(C_g[0] - C_g[1])) <= 1e-7 * np.abs(C_g[0]).max()  # minimum norm: twin columns share the load
+
+
+def test_rank_policy_relative_matlab_rule():
+    """vp_problem_set_rank_policy(VP_RANK_RELATIVE): sigma <= m * eps * sigma_1 (matlab/varpro.m:642-643). With the
+    DEFAULT absolute epsilon (2.2e-16) twin columns are a coin toss -- the vanishing singular value comes out as
+    rounding noise of either side of eps, in nalgebra as much as here -- while the relative rule truncates it
+    reliably; compared with numpy's truncated SVD at the same threshold."""
+    import varpro_b200 as vb
+    rng = np.random.default_rng(32)
+    m, S = 400, 7
+    x = np.linspace(0.0, 10.0, m)
+    Cs = rng.uniform(1.0, 5.0, size=(3, S))
+    Phi = np.stack([np.exp(-x / 1.5), np.exp(-x / 4.0), np.ones_like(x)], axis=1)
+    Y = np.asfortranarray(Phi @ Cs + 1e-3 * rng.standard_normal((m, S)))
+    w = rng.uniform(0.5, 1.5, size=m)
+    alpha = [2.5, 2.5]
+    wl = dict(x=x, Y=Y, basis=W.DOUBLE_EXP, q=2, alpha0=alpha, weights=w)
+    gp = W.make_gpu_problem(wl)
+    gp.set_rank_policy("relative")
+    C_np, R_np, s = _pinv_solution(wl, alpha, thr_rel=m * np.finfo(float).eps)
+    C_g = gp.linear_coefficients().reshape(3, S)
+    assert np.max(np.abs(C_g - C_np)) <= 1e-7 * np.abs(C_np).max()
+    assert np.max(np.abs(gp.residuals().reshape(S, m).T - R_np)) <= 1e-8 * np.linalg.norm(Y)
+    # a full-rank panel is untouched by the policy: bitwise the default result
+    wl2 = dict(wl, alpha0=[1.2, 5.0])
+    a, b = W.make_gpu_problem(wl2), W.make_gpu_problem(wl2)
+    b.set_rank_policy("relative")
+    ra, rb = a.reduce(), b.reduce()
+    assert ra["rnorm2"] == rb["rnorm2"] and np.array_equal(ra["H"], rb["H"]) and np.array_equal(a.linear_coefficients(), b.linear_coefficients())
+    # and a fit that passes through the degenerate starting point (tau1 = tau2) converges under the relative rule
+    res = vb.LevMarSolver.default().fit(gp)
+    assert np.isfinite(res.nonlinear_parameters()).all()
+
+
+def test_fit_host_batch_equals_fit_per_problem():
+    """vp_fit_host_batch (host buffers, pipelined worker threads inside the library) against build + fit + read back
+    per problem: bitwise the same parameters, coefficients and reports."""
+    import varpro_b200 as vb
+    wls = [W.c2(S=300 + 50 * k, seed=700 + k) for k in range(3)]
+    solver = vb.LevMarSolver.default()
+    for wl in wls:
+        names = ["p0", "p1"]
+        model = (vb.SeparableModelBuilder(names).function(["p0"], vb.ExpDecay()).function(["p1"], vb.ExpDecay())
+                 .invariant_function(vb.Constant()).independent_variable(wl["x"]).initial_parameters(list(wl["alpha0"])).build())
+        rng = np.random.default_rng(1)
+        Ys = [np.asfortranarray(wl["Y"] * (1.0 + 0.1 * k) + 1e-3 * k * rng.standard_normal(wl["Y"].shape)) for k in range(7)]
+        reports, alpha, Cs = solver.fit_host_batch(model, Ys, workers=3)
+        for k, Y in enumerate(Ys):
+            one = solver.fit(W.make_gpu_problem(wl, Y=Y))
+            assert np.array_equal(one.nonlinear_parameters(), alpha[k])
+            assert one.minimization_report.number_of_evaluations == reports[k].number_of_evaluations
+            assert one.minimization_report.objective_function == reports[k].objective_function
+            assert np.array_equal(one.linear_coefficients(), Cs[k])

@@ -75,6 +75,7 @@ SYMBOLS = {
     "vp_jacobian_device": (C.c_int, [_vp, _vp]),
     "vp_best_fit_device": (C.c_int, [_vp, _vp]),
     "vp_problem_set_jacobian": (C.c_int, [_vp, C.c_int]),
+    "vp_problem_set_rank_policy": (C.c_int, [_vp, C.c_int]),
     "vp_reduce": (C.c_int, [_vp, C.POINTER(Reduced)]),
     "vp_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, _pp, _vp]),
     "vp_comm_connect": (C.c_int, [_vp, _vp]),
@@ -83,6 +84,9 @@ SYMBOLS = {
     "vp_problem_set_comm": (C.c_int, [_vp, _vp]),
     "vp_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),
     "vp_fit_many": (C.c_int, [_pp, C.c_int64, C.POINTER(LmOptions), C.POINTER(FitReport), C.c_int32]),
+    "vp_fit_host_batch": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, C.c_int32, C.c_int32, C.POINTER(BasisDesc), C.c_int64, C.c_int64,
+                                    _pp, C.c_int64, _vp, C.c_double, _dp, C.POINTER(LmOptions), C.c_int32, C.POINTER(FitReport),
+                                    _dp, _pp]),
     "vp_statistics": (C.c_int, [_vp, _dp, _dp, _dp]),
     "vp_batch_create": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),
     "vp_batch_create_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _dp, _pp]),
@@ -90,6 +94,7 @@ SYMBOLS = {
     "vp_batch_fit": (C.c_int, [_vp, C.POINTER(LmOptions), C.POINTER(FitReport)]),
     "vp_batch_params": (C.c_int, [_vp, _dp]),
     "vp_batch_set_params": (C.c_int, [_vp, _dp]),
+    "vp_batch_set_rank_policy": (C.c_int, [_vp, C.c_int]),
     "vp_batch_linear_coefficients": (C.c_int, [_vp, _dp]),
     "vp_measure_fp64_peaks": (C.c_int, [_vp, _dp, _dp]),
     "vp_debug_timeline": (C.c_int, [_vp, C.POINTER(C.c_longlong), C.c_int64, C.POINTER(C.c_int64)]),

@@ -567,6 +567,12 @@ class SeparableProblem:
         _check(_lib.load().vp_problem_set_jacobian(self._h, code), self._ctx.h)
         return self
 
+    def set_rank_policy(self, policy: str):
+        """"absolute" (default; the reference: singular values <= epsilon are truncated in the solve,
+        src/solvers/levmar/mod.rs:52-54) or "relative" (MATLAB: sigma <= m*eps*sigma_1, matlab/varpro.m:642-643)."""
+        _check(_lib.load().vp_problem_set_rank_policy(self._h, {"absolute": 0, "relative": 1}[policy]), self._ctx.h)
+        return self
+
     def statistics(self, confidence_sigma: bool = False):
         """FitStatistics::try_calculate (src/statistics/mod.rs:352-441) for every right-hand side with the
         shared nonlinear parameters (vp_statistics). Returns a list of FitStatistics (one per column)."""
@@ -814,6 +820,37 @@ class LevMarSolver:
         st = problem.statistics(confidence_sigma=True)
         return result, (st[0] if problem.single_rhs else st)
 
+    def fit_host_batch(self, model: "SeparableModel", observations: Sequence[np.ndarray], weights=None, eps: float = -1.0,
+                       device: int = 0, workers: int = 0):
+        """Build, fit and read back one MRHS problem per entry of `observations` (m x S arrays, Fortran order; pinned
+        host memory gives full PCIe speed) through vp_fit_host_batch: worker threads of the library pipeline the
+        host-to-device copy of one problem with the fit of another. Equivalent to
+        `[LevMarSolver.fit(SeparableProblemBuilder.mrhs(model).observations(Y).build()) for Y in observations]`.
+        Returns (reports, parameters (len x q), coefficients list of n x S arrays)."""
+        lib = _lib.load()
+        ctx = _Ctx.get(device)
+        Ys = [Y if (isinstance(Y, np.ndarray) and Y.flags.f_contiguous and Y.dtype == model.dtype) else np.asfortranarray(Y, dtype=model.dtype)
+              for Y in observations]
+        if not Ys:
+            return [], np.empty((0, model.parameter_count())), []
+        m, S = Ys[0].shape
+        if any(Y.shape != (m, S) for Y in Ys) or m != model.output_len():
+            raise InvalidLengthOfData(f"Vectors x and y must have same lengths. Given x length = {model.output_len()} and y length = {m}")
+        npb, q, n = len(Ys), model.parameter_count(), model.base_function_count()
+        Cs = [np.empty((n, S), dtype=model.dtype, order="F") for _ in range(npb)]
+        alpha = np.empty((npb, q), dtype=np.float64)
+        reps = (_lib.FitReport * npb)()
+        yptrs = (C.c_void_p * npb)(*[Y.ctypes.data for Y in Ys])
+        cptrs = (C.c_void_p * npb)(*[c.ctypes.data for c in Cs])
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=model.dtype)
+        a0 = np.ascontiguousarray(model.params(), dtype=np.float64)
+        _check(lib.vp_fit_host_batch(ctx.h, VP_F32 if model.dtype == np.float32 else VP_F64, m, model.x.ctypes.data_as(C.c_void_p), q, n,
+                                     model._descs(), npb, S, yptrs, m, None if w is None else w.ctypes.data_as(C.c_void_p),
+                                     float(eps), a0.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self._solver._o), int(workers),
+                                     reps, alpha.ctypes.data_as(C.POINTER(C.c_double)), cptrs), ctx.h)
+        reports = [MinimizationReport(TerminationReason(r.termination), r.number_of_evaluations, r.objective_function) for r in reps]
+        return reports, alpha, Cs
+
     def fit_many(self, problems: Sequence[SeparableProblem], max_concurrent: int = 0) -> List[FitResult]:
         """Fit independent problems together (vp_fit_many): the loop a caller of the reference writes around
         LevMarSolver::fit, executed by ONE persistent kernel whose CTAs take (fit, group-of-columns) work items
@@ -896,6 +933,10 @@ class IndependentBatch:
         if a.shape != (self._P, self._q):
             raise InvalidParameterCount("parameters must have shape (P, q)")
         _check(_lib.load().vp_batch_set_params(self._h, a.ctypes.data_as(C.POINTER(C.c_double))), self._ctx.h)
+
+    def set_rank_policy(self, policy: str):
+        _check(_lib.load().vp_batch_set_rank_policy(self._h, {"absolute": 0, "relative": 1}[policy]), self._ctx.h)
+        return self
 
     def fit(self, solver: Optional["LevMarSolver"] = None, reports: bool = True) -> Optional[BatchFitResult]:
         lib = _lib.load()

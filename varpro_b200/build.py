@@ -23,9 +23,9 @@ HEADER = os.path.join(HERE, "..", "include", "varpro_b200.h")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
-LINK_LIBS: list[str] = ["-ldl"]  # NVTX v3 is header-only and dlopens its injection library
+LINK_LIBS: list[str] = ["-ldl", "-lpthread"]  # NVTX v3 is header-only and dlopens its injection library
 # host side of the C ABI (see csrc/vp_internal.h)
-HOST_UNITS = ["vp_ctx", "vp_problem", "vp_fit", "vp_batch", "vp_diag"]
+HOST_UNITS = ["vp_ctx", "vp_problem", "vp_fit", "vp_batch", "vp_hostbatch", "vp_diag"]
 
 
 def _groups():

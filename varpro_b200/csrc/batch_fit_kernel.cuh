@@ -233,7 +233,7 @@ batch_fit_kernel(const BatchArgs a)
                 const double sigma = s[0];
                 const double ajj = tl.top[J][J];
                 const double nrm = sqrt(sigma);
-                const bool keep = isfinite(nrm) && nrm > a.svd_eps;
+                const bool keep = isfinite(nrm) && nrm > 0.0; // near-dependence: rank policy on R1 in the LM phase
                 const double al = (ajj >= 0.0) ? -nrm : nrm;
                 const double vnorm2 = 2.0 * (sigma - ajj * al);
                 const double bt = (keep && vnorm2 > 0.0) ? 2.0 / vnorm2 : 0.0;
@@ -263,7 +263,7 @@ batch_fit_kernel(const BatchArgs a)
                 }
             }
 
-            // 3. tail reduction: rows >= n (plus the rows of dropped columns)
+            // 3. tail reduction: rows >= n (the untruncated projector; truncated directions are added by the rank policy)
             {
                 double tv[KMAX];
 #pragma unroll
@@ -271,7 +271,7 @@ batch_fit_kernel(const BatchArgs a)
 #pragma unroll
                 for (int r = 0; r < RPT; ++r) {
                     const int i = tid + r * THREADS;
-                    const bool tail = (i < m) && (i >= N || ((dropped >> i) & 1));
+                    const bool tail = (i < m) && (i >= N);
                     if (tail) {
                         const double yv = yt[r];
                         tv[0] = fma(yv, yv, tv[0]);
@@ -303,17 +303,53 @@ batch_fit_kernel(const BatchArgs a)
         if ((tid & 31) == 0 && (tid >> 5) < G && prob_s[tid >> 5] >= 0) {
             const int g = tid >> 5;
             const BatchTail<N, P, KMAX> &tl = tail_s[g];
-            const int dropped = tl.dropped;
-            double coef[N];
+            // inner solve c = R1^-1 (Q^T y) under the rank policy (rank_policy.cuh): triangular inverse, cheap
+            // full-rank test, and -- rarely -- the SVD of R1 with the truncated directions moved into the residual
+            double Rm[N * N], Ri[N * N], coef[N];
 #pragma unroll
-            for (int i = N - 1; i >= 0; --i) {
-                double sacc = tl.top[i][NPV];
+            for (int c = 0; c < N; ++c)
 #pragma unroll
-                for (int k = i + 1; k < N; ++k) sacc -= tl.top[i][k] * coef[k];
-                coef[i] = ((dropped >> i) & 1) ? 0.0 : sacc / tl.rdiag[i];
+                for (int i = 0; i < N; ++i) { Rm[c * N + i] = (i < c) ? tl.top[i][c] : ((i == c) ? tl.rdiag[c] : 0.0); Ri[c * N + i] = 0.0; }
+#pragma unroll
+            for (int c = 0; c < N; ++c)
+#pragma unroll
+                for (int i = N - 1; i >= 0; --i) {
+                    if (i > c) continue;
+                    double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k)
+                        if (k > i && k <= c) sacc -= Rm[k * N + i] * Ri[c * N + k];
+                    Ri[c * N + i] = sacc / Rm[i * N + i];
+                }
+            double rn2_extra = 0.0;
+            if (rank_surely_full(N, Rm, N, Ri, N, a.svd_eps)) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int c = i; c < N; ++c) sacc += Ri[c * N + i] * tl.top[c][NPV];
+                    coef[i] = sacc;
+                }
+            } else {
+                SmallSvd sv;
+                rank_policy_svd(N, Rm, N, a.svd_eps, &sv);
+                double bb[N], b2 = 0.0, bb2 = 0.0;
+                for (int c = 0; c < N; ++c) {
+                    double sacc = 0.0;
+                    for (int k = 0; k < N; ++k) sacc += sv.Urot[c * N + k] * tl.top[k][NPV];
+                    bb[c] = sacc;
+                    bb2 += sacc * sacc;
+                    b2 += tl.top[c][NPV] * tl.top[c][NPV];
+                }
+                for (int i = 0; i < N; ++i) {
+                    double sacc = 0.0;
+                    for (int c = 0; c < N; ++c) sacc += sv.RinvEff[c * N + i] * bb[c];
+                    coef[i] = sacc;
+                }
+                rn2_extra = fmax(b2 - bb2, 0.0); // the truncated components of Q^T y stay in the residual
             }
             LmEval ev;
-            ev.rnorm2 = tl.tv[0];
+            ev.rnorm2 = tl.tv[0] + rn2_extra;
             int finite = !tl.bad && isfinite(tl.tv[0]);
             for (int k = 0; k < VP_LM_MAXQ; ++k) ev.g[k] = 0.0;
             for (int k = 0; k < VP_LM_MAXQ * VP_LM_MAXQ; ++k) ev.H[k] = 0.0;

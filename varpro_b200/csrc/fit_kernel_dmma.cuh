@@ -338,6 +338,7 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
     __shared__ double top[N][NPV];
     __shared__ double alpha_s[VP_MAX_Q];
     __shared__ PanelSmall small_s;
+    __shared__ SmallSvd svd_s;
     __shared__ LmEval ev_s;
     __shared__ __align__(8) FitDevice fd_s; // this CTA's copy of the LM state (fit mode)
     __shared__ int is_last, ctrl_more, flag_s;
@@ -424,7 +425,7 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
             double pa[RPT][NPV], pd0[RPT][P > 0 ? P : 1];
             const int bad = panel_eval_staged<N, P, RPT, THREADS>(f.md, xi, wi, alpha_s, pstage, lds, pa, pd0);
             dbg_mark(a.dbg, 9);
-            panel_hh_factor<double, N, P, RPT, THREADS>(f.md, pa, pd0, bad, alpha_s, f.svd_eps, lds, pstage, &small_s, red, top, nullptr);
+            panel_hh_factor<double, N, P, RPT, THREADS>(f.md, pa, pd0, bad, alpha_s, f.svd_eps, lds, pstage, &small_s, red, top, nullptr, &svd_s);
         }
         __syncthreads();
         dbg_mark(a.dbg, 10);

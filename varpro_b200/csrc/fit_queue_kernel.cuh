@@ -124,6 +124,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     __shared__ double red[2][NWARPS * KMAX];
     __shared__ double top[N][NPV];
     __shared__ double alpha_s[VP_MAX_Q];
+    __shared__ SmallSvd svd_s;
     __shared__ LmEval ev_s;
     __shared__ __align__(8) FitDevice fd_s;
     __shared__ __align__(8) QueueFit qf_s; // the claimed fit's descriptor: ONE cooperative L2 read per item instead of chains of dependent loads
@@ -158,7 +159,7 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             const int bad = panel_eval_staged<N, P, RPT, THREADS>(md, xi, wi, alpha_s, staging, lds, pa, pd0);
             if (dbg_on && tid == 0) fin_acc[2] += global_timer_ns() - ts0;
             panel_hh_factor<double, N, P, RPT, THREADS>(md, pa, pd0, bad, alpha_s, qf->svd_eps, qf->ldp, qf->Pq, qf->small, red, top,
-                                                        nullptr);
+                                                        nullptr, &svd_s);
         }
         if (sizeof(TY) != sizeof(double)) {
             // the f64 staging overlaid the float slots: restore the zero pad rows [ld, lds) of every slot

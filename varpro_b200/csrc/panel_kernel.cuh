@@ -15,12 +15,11 @@
 // Orthogonalisation: classical Gram-Schmidt applied twice (CGS2), which gives
 // orthogonality at machine precision for numerically non-singular panels and
 // needs only one multi-value block reduction per pass.
-// Rank policy: a column whose remaining norm is <= svd_eps (the reference's
-// absolute singular-value threshold, src/problem/builder.rs:246-251,282) is
-// dropped: q_j = 0 and its coefficient is 0. The reference truncates sigma_i <=
-// eps in the solve instead (src/solvers/levmar/mod.rs:52-54); the two agree on
-// every full-rank panel; behaviour on exactly rank-deficient panels is not
-// pinned by any reference test (SURVEY.md 8c "unpinned" (v)).
+// Rank policy (rank_policy.cuh): the reference truncates singular values <= eps in the solve
+// (src/solvers/levmar/mod.rs:52-54) and keeps the untruncated U in the projector (:123-124); MATLAB's
+// relative rule is the alternative. Both are decided on the n x n triangle R1 -- a cheap bound proves the
+// full-rank case, otherwise one thread computes the tiny SVD and Q is re-expressed in the singular basis
+// (after E has been formed with the full Q). A column that is EXACTLY zero when it is normalised gives q_j = 0.
 //
 // Implementation note: the kernel runs for microseconds on ONE SM, so its cost
 // is dominated by instruction fetch of straight-line code, not by arithmetic
@@ -31,6 +30,7 @@
 #pragma once
 
 #include "device_common.cuh"
+#include "rank_policy.cuh"
 
 namespace vp {
 
@@ -128,6 +128,8 @@ panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
     __shared__ double Rm_s[VP_MAX_N * VP_MAX_N];
     __shared__ double alpha_s[VP_MAX_Q];
     __shared__ PanelRound rounds[PANEL_MAX_ROUNDS];
+    __shared__ SmallSvd svd_s;
+    __shared__ double Ri_s[VP_MAX_N * VP_MAX_N];
     __shared__ int nrounds_s, dropped_s;
     const int tid = threadIdx.x, nt = blockDim.x;
 
@@ -227,7 +229,7 @@ panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
             if (tid < cnt && tgt < n) Rm_s[tgt * VP_MAX_N + tid] += scratch[((nt + 31) >> 5) * 8 + tid];
         } else if (type == ROUND_NORMALISE) {
             const double nrm = sqrt(d[0]);
-            const bool keep = isfinite(nrm) && nrm > svd_eps;
+            const bool keep = isfinite(nrm) && nrm > 0.0; // near-dependence is the rank policy's business
             double *aj = col + (size_t)tgt * m;
             for (int i = tid; i < m; i += nt) aj[i] = keep ? aj[i] / nrm : 0.0;
             if (tid == 0) {
@@ -246,33 +248,54 @@ panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
     }
 
     dbg_mark(dbg, 2);
-    // 5. R1^-1 restricted to the kept columns (back substitution): thread c
-    //    solves R1 x = e_c; plus bookkeeping
+    // 5. R1^-1 (back substitution; thread c solves R1 x = e_c), then the rank policy on R1
     const int dropped = dropped_s;
+    if (tid < VP_MAX_N * VP_MAX_N) Ri_s[tid] = 0.0;
+    __syncthreads();
     if (tid < n) {
         const int c = tid;
         double xcol[VP_MAX_N];
 #pragma unroll
         for (int i = 0; i < VP_MAX_N; ++i) xcol[i] = 0.0;
-        if (!((dropped >> c) & 1)) {
 #pragma unroll
-            for (int i = VP_MAX_N - 1; i >= 0; --i) {
-                if (i > c || ((dropped >> i) & 1)) continue;
-                double s = (i == c) ? 1.0 : 0.0;
+        for (int i = VP_MAX_N - 1; i >= 0; --i) {
+            if (i > c) continue;
+            double s = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-                for (int k = 0; k < VP_MAX_N; ++k)
-                    if (k > i && k <= c) s -= Rm_s[k * VP_MAX_N + i] * xcol[k];
-                xcol[i] = s / Rm_s[i * VP_MAX_N + i];
-            }
+            for (int k = 0; k < VP_MAX_N; ++k)
+                if (k > i && k <= c) s -= Rm_s[k * VP_MAX_N + i] * xcol[k];
+            xcol[i] = s / Rm_s[i * VP_MAX_N + i];
         }
 #pragma unroll
-        for (int i = 0; i < VP_MAX_N; ++i) small->Rinv[c * VP_MAX_N + i] = xcol[i];
+        for (int i = 0; i < VP_MAX_N; ++i) Ri_s[c * VP_MAX_N + i] = xcol[i];
     }
+    __syncthreads();
+    if (tid == 0) {
+        svd_s.truncated = 0;
+        if (!rank_surely_full(n, Rm_s, VP_MAX_N, Ri_s, VP_MAX_N, svd_eps)) rank_policy_svd(n, Rm_s, VP_MAX_N, svd_eps, &svd_s);
+    }
+    __syncthreads();
+    const int truncated = svd_s.truncated;
+    if (truncated) { // rare: Q'' = Q Ur diag(keep) (E was formed with the full Q), Rinv = V diag(keep / sigma)
+        for (int i = tid; i < m; i += nt) {
+            double qo[VP_MAX_N], qn[VP_MAX_N];
+            for (int k = 0; k < n; ++k) qo[k] = col[(size_t)k * m + i];
+            for (int c = 0; c < n; ++c) {
+                double sacc = 0.0;
+                for (int k = 0; k < n; ++k) sacc = fma(qo[k], svd_s.Urot[c * n + k], sacc);
+                qn[c] = sacc;
+            }
+            for (int c = 0; c < n; ++c) col[(size_t)c * m + i] = qn[c];
+        }
+        if (tid < n * n) Ri_s[(tid / n) * VP_MAX_N + (tid % n)] = svd_s.RinvEff[tid];
+        __syncthreads();
+    }
+    if (tid < VP_MAX_N * VP_MAX_N) small->Rinv[tid] = Ri_s[tid];
     if (tid < VP_MAX_N * VP_MAX_N) small->Rm[tid] = Rm_s[tid];
     if (tid < VP_MAX_Q) small->alpha[tid] = alpha_s[tid];
     if (tid == 0) {
         small->nonfinite = bad ? 1 : 0;
-        small->dropped = dropped;
+        small->dropped = dropped | (truncated ? (1 << 30) : 0);
     }
 
     dbg_mark(dbg, 3);

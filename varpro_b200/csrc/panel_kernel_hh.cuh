@@ -19,11 +19,14 @@
 // Householder QR is unconditionally backward stable; Q is orthonormal to working
 // precision whatever the conditioning of Phi_w.
 //
-// Rank policy (identical to panel_kernel): |R_jj| <= svd_eps drops column j (q_j = 0,
-// coefficient 0).
+// Rank policy (rank_policy.cuh, identical in panel_kernel): the reference's rule -- singular values <= eps are
+// truncated in the solve, the projector stays untruncated -- or MATLAB's relative rule, decided on the n x n
+// triangle R1; a cheap bound proves the common full-rank case without an SVD. A column that is EXACTLY zero
+// when its Householder step starts is skipped (q_j = 0).
 #pragma once
 
 #include "panel_kernel.cuh"
+#include "rank_policy.cuh"
 
 namespace vp {
 
@@ -82,7 +85,7 @@ __device__ __forceinline__ void hh_steps(double (&a)[RPT][N + P], double (&beta)
         const double sigma = s[0];
         const double ajj = top[J][J];
         const double nrm = sqrt(sigma);
-        const bool keep = isfinite(nrm) && nrm > svd_eps;
+        const bool keep = isfinite(nrm) && nrm > 0.0; // near-dependence is the rank policy's business (singular values of R1)
         const double al = (ajj >= 0.0) ? -nrm : nrm;
         const double vnorm2 = 2.0 * (sigma - ajj * al);
         const double bt = (keep && vnorm2 > 0.0) ? 2.0 / vnorm2 : 0.0;
@@ -165,7 +168,7 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
                                                 int bad, const double *alpha_s, const double svd_eps, const int ldp, T *Pq,
                                                 PanelSmall *small,
                                                 double (*red)[(THREADS / 32) * ((N + P > 8) ? N + P : 8)],
-                                                double (*top)[N + P], unsigned long long *dbg)
+                                                double (*top)[N + P], unsigned long long *dbg, SmallSvd *svd_s)
 {
     constexpr int NPV = N + P;
     constexpr int NW = THREADS / 32;
@@ -273,6 +276,28 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
             W[aa][c] = sacc;
         }
 
+    // ---- 4b. rank policy on R1 (thread 0; the others go on with Q and E and meet it at the next barrier) ----
+    if (tid == 0) {
+        double Rm[N * N], Ri[N * N]; // column-major, ld N: R1 and its triangular inverse
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+#pragma unroll
+            for (int i = 0; i < N; ++i) { Rm[c * N + i] = (i < c) ? top[i][c] : ((i == c) ? rdiag[c] : 0.0); Ri[c * N + i] = 0.0; }
+#pragma unroll
+        for (int c = 0; c < N; ++c)
+#pragma unroll
+            for (int i = N - 1; i >= 0; --i) {
+                if (i > c) continue;
+                double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k)
+                    if (k > i && k <= c) sacc -= Rm[k * N + i] * Ri[c * N + k];
+                Ri[c * N + i] = sacc / Rm[i * N + i];
+            }
+        svd_s->truncated = 0;
+        if (!rank_surely_full(N, Rm, N, Ri, N, svd_eps)) rank_policy_svd(N, Rm, N, svd_eps, svd_s);
+    }
+
     // ---- 5. explicit Q and E for my rows -------------------------------------------------------
     // E = D - Q (Q^T D) leaves Q^T E = O(eps) ||D||; a second projection pass (one more
     // reduction, n*p values) brings it down to O(eps) ||E||, which sets the noise floor of the
@@ -292,7 +317,7 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
 #pragma unroll
                 for (int aa = 0; aa < N; ++aa)
                     if (i >= aa) sacc = fma(-a[r][aa], W[aa][c], sacc); // V[i][aa] = a[r][aa] on rows >= aa
-                qrow[r][c] = (((dropped >> c) & 1) || i >= m) ? 0.0 : sacc;
+                qrow[r][c] = (i >= m) ? 0.0 : sacc; // (a skipped step has beta = 0: its column is H_0..H_{c-1} e_c, still orthonormal)
             }
 #pragma unroll
             for (int e = 0; e < P; ++e) {
@@ -330,6 +355,23 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
 #pragma unroll
                 for (int c = 0; c < N; ++c) erow[r][e] = fma(-qrow[r][c], qe[c * P + e], erow[r][e]);
     }
+    if constexpr (N * P == 0) __syncthreads(); // (the Q^T E reduction above has the barrier otherwise)
+    const int truncated = svd_s->truncated;
+    if (truncated) { // rare: Q'' = Q Ur diag(keep); E above was formed with the full Q (untruncated projector)
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            double qn[N];
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) sacc = fma(qrow[r][k], svd_s->Urot[c * N + k], sacc);
+                qn[c] = sacc;
+            }
+#pragma unroll
+            for (int c = 0; c < N; ++c) qrow[r][c] = qn[c];
+        }
+    }
     // publish [Q | E | 0] in the problem dtype
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
@@ -356,7 +398,10 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
         double xcol[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) xcol[i] = 0.0;
-        if (!((dropped >> c) & 1)) {
+        if (truncated) { // V diag(keep / sigma): a full matrix
+#pragma unroll
+            for (int i = 0; i < N; ++i) xcol[i] = svd_s->RinvEff[c * N + i];
+        } else if (!((dropped >> c) & 1)) {
 #pragma unroll
             for (int i = N - 1; i >= 0; --i) {
                 if (i > c || ((dropped >> i) & 1)) continue;
@@ -383,7 +428,7 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
                 ++t;
             }
         small->nonfinite = bad ? 1 : 0;
-        small->dropped = dropped;
+        small->dropped = dropped | (truncated ? (1 << 30) : 0);
     }
     if (tid >= 64 && tid < 64 + VP_MAX_Q) small->alpha[tid - 64] = alpha_s[tid - 64];
     dbg_mark(dbg, 4);
@@ -394,12 +439,12 @@ __device__ __forceinline__ void panel_hh_body(const ModelDesc &md, const double 
                                               const double *alpha_s, const double svd_eps, const int ldp, T *Pq,
                                               PanelSmall *small,
                                               double (*red)[(THREADS / 32) * ((N + P > 8) ? N + P : 8)],
-                                              double (*top)[N + P], unsigned long long *dbg)
+                                              double (*top)[N + P], unsigned long long *dbg, SmallSvd *svd_s)
 {
     double a[RPT][N + P];           // working matrix rows
     double d0[RPT][P > 0 ? P : 1];  // the untouched weighted derivative columns
     const int bad = panel_hh_eval<N, P, RPT, THREADS>(md, xi_r, wi_r, alpha_s, a, d0);
-    panel_hh_factor<T, N, P, RPT, THREADS>(md, a, d0, bad, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg);
+    panel_hh_factor<T, N, P, RPT, THREADS>(md, a, d0, bad, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg, svd_s);
 }
 
 template <typename T, int N, int P, int RPT, int THREADS>
@@ -414,6 +459,7 @@ panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
     __shared__ double red[2][NW * KMAX];
     __shared__ double top[N][NPV];   // rows 0..n-1 of the working matrix (R, Q^T D and v entries)
     __shared__ double alpha_s[VP_MAX_Q];
+    __shared__ SmallSvd svd_s;
     const int tid = threadIdx.x;
     dbg_mark(dbg, 0);
     if (tid < VP_MAX_Q) alpha_s[tid] = tid < md.q ? alpha_dev[tid] : 0.0;
@@ -426,7 +472,7 @@ panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
         wi[r] = in ? (w ? (double)w[i] : 1.0) : 0.0;
     }
     __syncthreads();
-    panel_hh_body<T, N, P, RPT, THREADS>(md, xi, wi, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg);
+    panel_hh_body<T, N, P, RPT, THREADS>(md, xi, wi, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg, &svd_s);
 }
 
 } // namespace vp

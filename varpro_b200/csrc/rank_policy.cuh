@@ -29,6 +29,13 @@
 
 #include "../../include/varpro_b200.h"
 
+#ifndef __CUDACC__ // the CPU test harness (tests/csrc/lm_harness.cpp) compiles this header with g++
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
+#endif
+
 namespace vp {
 
 struct SmallSvd {

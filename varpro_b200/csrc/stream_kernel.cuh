@@ -463,7 +463,7 @@ stream_kernel(const StreamArgs<T> a)
             for (int r = 0; r < N; ++r) {
                 double s = 0.0;
 #pragma unroll
-                for (int c2 = r; c2 < N; ++c2) s += rinv_s[c2 * N + r] * bu[tid * NPV + c2];
+                for (int c2 = 0; c2 < N; ++c2) s += rinv_s[c2 * N + r] * bu[tid * NPV + c2]; // full product: the rank policy may make Rinv non-triangular
                 coef[r] = s;
                 Cout[(size_t)(col0 + tid) * N + r] = (T)s;
             }
@@ -567,7 +567,7 @@ stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m)
             double coef[VP_MAX_N];
             for (int r = 0; r < n; ++r) {
                 double sacc = 0.0;
-                for (int c2 = r; c2 < n; ++c2) sacc += rinv_s[c2 * VP_MAX_N + r] * d[c2];
+                for (int c2 = 0; c2 < n; ++c2) sacc += rinv_s[c2 * VP_MAX_N + r] * d[c2];
                 coef[r] = sacc;
                 Cout[(size_t)s * n + r] = (T)sacc;
             }

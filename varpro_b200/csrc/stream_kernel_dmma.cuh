@@ -207,7 +207,7 @@ stream_kernel_dmma(const StreamArgs<double> a, const int lds)
             for (int r = 0; r < N; ++r) {
                 double s = 0.0;
 #pragma unroll
-                for (int c2 = r; c2 < N; ++c2) s += rinv_s[c2 * N + r] * bu[c2 * 8 + tid];
+                for (int c2 = 0; c2 < N; ++c2) s += rinv_s[c2 * N + r] * bu[c2 * 8 + tid];
                 coef[r] = s;
                 Cout[(size_t)(col0 + tid) * N + r] = s;
             }

@@ -17,6 +17,7 @@ struct vp_batch {
     int *term = nullptr, *nfev = nullptr;
     unsigned long long *next = nullptr;
     double svd_eps = 0.0;
+    int rank_policy = 0;
     int kernel = -1;
     int mpad = 0;
     size_t smem = 0;
@@ -127,7 +128,7 @@ static int batch_fit_launch(vp_batch *b, const vp_lm_options *opt)
     BatchArgs a{};
     a.md = md;
     a.x = (const double *)b->model->x_dev; a.w = b->w_dev; a.Y = b->Y; a.ld = b->ld; a.P = b->P;
-    a.svd_eps = b->svd_eps;
+    a.svd_eps = vp_rank_tol(b->rank_policy, b->svd_eps, md.m, VP_F64);
     vp_lm_config_from_options(VP_F64, md.q, opt, a.cfg);
     // start from the current parameters: alpha -> alpha0 (device copy), results go to alpha
     if (md.q > 0)
@@ -196,6 +197,13 @@ extern "C" int vp_batch_set_params(vp_batch *b, const double *alpha)
     VP_CUDA(ctx, cudaMemcpyAsync(b->alpha, alpha, sizeof(double) * (size_t)q * b->P, cudaMemcpyHostToDevice, ctx->stream));
     VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     b->fitted = false;
+    return VP_OK;
+}
+
+extern "C" int vp_batch_set_rank_policy(vp_batch *b, int policy)
+{
+    if (!b || (policy != VP_RANK_ABSOLUTE && policy != VP_RANK_RELATIVE)) return VP_ERR_INVALID_ARGUMENT;
+    b->rank_policy = policy;
     return VP_OK;
 }
 

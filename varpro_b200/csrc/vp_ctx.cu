@@ -231,6 +231,8 @@ extern "C" int vp_ctx_trim(vp_ctx *ctx)
 extern "C" int vp_ctx_destroy(vp_ctx *ctx)
 {
     if (!ctx) return VP_OK;
+    for (vp_ctx *w : ctx->workers) vp_ctx_destroy(w);
+    ctx->workers.clear();
     cudaSetDevice(ctx->device);
     pool_release(ctx->dev_pool, false);
     pool_release(ctx->host_pool, true);

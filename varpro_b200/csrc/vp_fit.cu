@@ -305,7 +305,7 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
             f.Pq = pr->Pq64; f.ldp = pr->ldp64;
         }
         f.small = pr->small; f.partials = pr->partials; f.ticket = pr->ticket;
-        f.fit = pr->fit_dev; f.svd_eps = pr->svd_eps;
+        f.fit = pr->fit_dev; f.svd_eps = pr->rank_tol;
         f.ld = pr->model->ld; f.S = (int)pr->S; f.red_stride = pr->red_stride;
         f.ntiles = (int)((pr->S + DMMA_CT - 1) / DMMA_CT);
         // the partition vp_fit's persistent kernel uses for this problem (one part per CTA of ITS grid)

@@ -95,6 +95,7 @@ struct vp_ctx {
     size_t smem_optin = 0;
     BufferPool dev_pool, host_pool;
     CtxOptions opt;
+    std::vector<vp_ctx *> workers; // contexts of vp_fit_host_batch's worker threads (same device, own streams)
 };
 
 struct vp_model {
@@ -132,7 +133,9 @@ struct vp_problem {
     int64_t S = 0;
     void *Yw = nullptr;    // ld x S
     void *w_dev = nullptr; // m or null
-    double svd_eps = 0.0;
+    double svd_eps = 0.0;  // the builder's epsilon (absolute threshold)
+    int rank_policy = 0;   // VP_RANK_ABSOLUTE / VP_RANK_RELATIVE
+    double rank_tol = 0.0; // what the kernels get (rank_policy.cuh): >= 0 absolute eps; < 0: -(m * eps_machine), relative
     double alpha[VP_MAX_Q] = {0};
     double *alpha_dev = nullptr; // = &fit_dev->st.x_trial[0]: the parameters the next evaluation is made at
     vp::FitDevice *fit_dev = nullptr;  // device-resident LM state
@@ -186,6 +189,10 @@ int vp_fail(vp_ctx *ctx, int code, const std::string &msg);
                            std::string(#expr) + ": " + cudaGetErrorString(_e));                \
     } while (0)
 
+inline double vp_rank_tol(int policy, double svd_eps, int m, int dtype)
+{
+    return policy == VP_RANK_RELATIVE ? -(double)m * (dtype == VP_F32 ? (double)FLT_EPSILON : DBL_EPSILON) : svd_eps;
+}
 inline size_t vp_esize(int dtype) { return dtype == VP_F32 ? 4 : 8; }
 inline int vp_vec_of(int dtype) { return dtype == VP_F32 ? 4 : 2; }
 

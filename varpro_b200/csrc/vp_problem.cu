@@ -199,7 +199,7 @@ static int launch_panel_t(vp_problem *pr)
             ModelDesc mdc = md;
             const void *xp = mo->x_dev, *wp = pr->w_dev;
             const double *ap = pr->alpha_dev;
-            double eps = pr->svd_eps;
+            double eps = pr->rank_tol;
             int ldp = pr->ldp;
             void *pq = pr->Pq;
             PanelSmall *sm = pr->small;
@@ -217,7 +217,7 @@ static int launch_panel_t(vp_problem *pr)
         return vp_fail(ctx, VP_ERR_MODEL_TOO_LARGE, "m*(n+p) panel does not fit in shared memory");
     if (smem > 48 * 1024) VP_CUDA(ctx, vp_ensure_dynamic_smem(ctx->device, (const void *)panel_kernel<T>, smem));
     panel_kernel<T><<<1, threads, smem, ctx->stream>>>(md, (const T *)mo->x_dev, (const T *)pr->w_dev, pr->alpha_dev,
-                                                       pr->svd_eps, pr->ldp, (T *)pr->Pq, pr->small, dbg,
+                                                       pr->rank_tol, pr->ldp, (T *)pr->Pq, pr->small, dbg,
                                                        mo->hosteval ? mo->pre_dev : nullptr);
     ctx->launches++;
     VP_CUDA(ctx, cudaGetLastError());
@@ -291,7 +291,7 @@ int vp_launch_fused(vp_problem *pr, int cdst, bool fit_mode)
     FitArgs f{};
     f.md = md;
     f.x = (const double *)mo->x_dev; f.w = (const double *)pr->w_dev;
-    f.svd_eps = pr->svd_eps;
+    f.svd_eps = pr->rank_tol;
     f.alpha_dev = pr->alpha_dev;
     f.ctl = pr->fit_ctl;
     f.jac_full = pr->jac_full;
@@ -476,6 +476,8 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     const int ld = model->ld, m = md.m;
     // default epsilon = machine epsilon of the scalar (src/problem/builder.rs:282), |eps| otherwise (:248)
     pr->svd_eps = svd_eps < 0 ? (dtype == VP_F32 ? (double)FLT_EPSILON : DBL_EPSILON) : fabs(svd_eps);
+    pr->rank_policy = VP_RANK_ABSOLUTE;
+    pr->rank_tol = vp_rank_tol(pr->rank_policy, pr->svd_eps, md.m, dtype);
     pr->red_stride = 64;
     pr->max_grid = ctx->sm_count * 8;
 
@@ -608,6 +610,14 @@ extern "C" int vp_problem_set_jacobian(vp_problem *pr, int mode)
     pr->jac_full = mode == VP_JACOBIAN_FULL ? 1 : 0;
     if (!pr->cached) return VP_OK;
     return vp_refresh_cached_evaluation(pr); // its J^T J depends on the mode
+}
+
+extern "C" int vp_problem_set_rank_policy(vp_problem *pr, int policy)
+{
+    if (!pr || (policy != VP_RANK_ABSOLUTE && policy != VP_RANK_RELATIVE)) return VP_ERR_INVALID_ARGUMENT;
+    pr->rank_policy = policy;
+    pr->rank_tol = vp_rank_tol(policy, pr->svd_eps, pr->model->md.m, pr->model->dtype);
+    return vp_refresh_cached_evaluation(pr);
 }
 
 extern "C" int vp_reduce(vp_problem *pr, vp_reduced *out)

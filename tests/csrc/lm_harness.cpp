@@ -31,7 +31,7 @@ int lmh_advance(Harness *h, double rnorm2, const double *g, const double *H /* q
     LmEval ev;
     std::memset(&ev, 0, sizeof(ev));
     const int q = h->st.q;
-    ev.rnorm2 = rnorm2; ev.finite = finite;
+    ev.rnorm2 = rnorm2; ev.finite = finite ? VP_EVAL_ALL_OK : 0; // finite = 0: the evaluation failed (residuals() is None)
     for (int k = 0; k < q; ++k) ev.g[k] = g[k];
     for (int i = 0; i < q * q; ++i) ev.H[i] = H[i];
     return (h->generic ? lm_advance_generic(h->st, h->cfg, ev) : lm_advance(h->st, h->cfg, ev)) ? 1 : 0;

@@ -41,9 +41,11 @@ def test_options_stepbound_patience_and_termination_codes():
     assert h.termination == 8 and h.nfev == 3  # LostPatience
     h, _ = LH.fit_with_oracle_evals(W.make_oracle(wl), wl["alpha0"], stepbound=1.0)
     assert h.termination in (2, 3, 4, 5, 6)
-    # non-finite evaluation at the start -> Numerical
+    # failed evaluation at the start (residuals() is None) -> User, like the crate; a NaN norm of a valid residual -> Numerical
     hh = LH.LmHarness([1.0, 2.0])
-    assert hh.advance(np.nan, np.zeros(2), np.zeros((2, 2)), finite=False) is False and hh.termination == 1
+    assert hh.advance(np.nan, np.zeros(2), np.zeros((2, 2)), finite=False) is False and hh.termination == 0
+    hh = LH.LmHarness([1.0, 2.0])
+    assert hh.advance(np.nan, np.zeros(2), np.eye(2), finite=True) is False and hh.termination == 1
     # exactly zero residual -> ResidualsZero
     hh = LH.LmHarness([1.0, 2.0])
     assert hh.advance(0.0, np.zeros(2), np.eye(2), finite=True) is False and hh.termination == 2

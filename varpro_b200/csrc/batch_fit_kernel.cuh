@@ -194,7 +194,7 @@ batch_fit_kernel(const BatchArgs a)
                         }
                         if (i < m) {
                             const double pv = wi[r] * v, pa = wi[r] * da, pb = wi[r] * db;
-                            bad |= !isfinite(pv) | ((np > 0) & !isfinite(pa)) | ((np > 1) & !isfinite(pb));
+                            bad |= (!isfinite(pv) ? 1 : 0) | (fabs(pv) > RANK_HUGE_ENTRY ? (2 << j) : 0); // flag word of rank_policy.cuh
                             colm[(size_t)j * mpad + i] = pv;
                             if (np > 0) colm[(size_t)(N + e) * mpad + i] = pa;
                             if (np > 1) colm[(size_t)(N + e + 1) * mpad + i] = pb;
@@ -204,6 +204,15 @@ batch_fit_kernel(const BatchArgs a)
                 }
             }
             bad = __syncthreads_or(bad);
+            if (bad >> 1) { // overflowing basis columns: zero them and their derivative columns
+                for (int idx = tid; idx < m * NPV; idx += THREADS) {
+                    const int c = idx / m, i = idx - c * m;
+                    const int j = c < N ? c : a.md.e_basis[c - N];
+                    if ((bad >> (1 + j)) & 1) colm[(size_t)c * mpad + i] = 0.0;
+                }
+                __syncthreads();
+            }
+            bad &= 1;
 
             // 2. Householder steps on [Phi_w | D | y] (y in registers)
             int dropped = 0;
@@ -350,7 +359,8 @@ batch_fit_kernel(const BatchArgs a)
             }
             LmEval ev;
             ev.rnorm2 = tl.tv[0] + rn2_extra;
-            int finite = !tl.bad && isfinite(tl.tv[0]);
+            const int resid_ok = !tl.bad && isfinite(tl.tv[0] + rn2_extra);
+            int finite = 1; // derivatives
             for (int k = 0; k < VP_LM_MAXQ; ++k) ev.g[k] = 0.0;
             for (int k = 0; k < VP_LM_MAXQ * VP_LM_MAXQ; ++k) ev.H[k] = 0.0;
             double Mm[P > 0 ? P : 1][P > 0 ? P : 1];
@@ -378,7 +388,7 @@ batch_fit_kernel(const BatchArgs a)
             }
             for (int k = 0; k < q; ++k) finite = finite && isfinite(ev.g[k]);
             for (int k = 0; k < q * q; ++k) finite = finite && isfinite(ev.H[k]);
-            ev.finite = finite;
+            ev.finite = (resid_ok ? VP_EVAL_RESIDUAL_OK : 0) | (finite ? VP_EVAL_DERIVS_OK : 0);
             LmState &st = st_s[g];
             const bool more = lm_advance(st, a.cfg, ev);
             if (st.last_accepted) {

@@ -189,11 +189,8 @@ __device__ __forceinline__ void fused_assemble(const double *sh, const double *M
 {
     constexpr int NG = N * (N + 1) / 2;
     const int tid = threadIdx.x;
-    int ok = 1;
-    if (tid == 0) {
-        ev->rnorm2 = sh[0];
-        ok = isfinite(sh[0]) && !nonfinite;
-    }
+    int ok = 1; // derivatives finite (every thread votes on its entry)
+    if (tid == 0) ev->rnorm2 = sh[0];
     if (tid >= 32 && tid < 32 + q) {
         const int kk = tid - 32;
         double gk = 0.0;
@@ -227,7 +224,7 @@ __device__ __forceinline__ void fused_assemble(const double *sh, const double *M
         }
     }
     ok = __syncthreads_and(ok);
-    if (tid == 0) ev->finite = ok;
+    if (tid == 0) ev->finite = ((isfinite(sh[0]) && !nonfinite) ? VP_EVAL_RESIDUAL_OK : 0) | (ok ? VP_EVAL_DERIVS_OK : 0);
     __syncthreads();
 }
 
@@ -287,7 +284,7 @@ __device__ __forceinline__ int panel_eval_staged(const ModelDesc &md, const doub
             const int i = tid + r * THREADS;
             const bool in = i < md.m; // wi = 0 there, but 0 * inf must not poison the column
             const double pv = in ? wi[r] * v[r] : 0.0, pa = in ? wi[r] * da[r] : 0.0, pb = in ? wi[r] * db[r] : 0.0;
-            bad |= !isfinite(pv) | ((np > 0) & !isfinite(pa)) | ((np > 1) & !isfinite(pb));
+            bad |= (!isfinite(pv) ? 1 : 0) | (fabs(pv) > RANK_HUGE_ENTRY ? (2 << j) : 0); // flag word of rank_policy.cuh
             if (i < lds) {
                 stg[(size_t)j * lds + i] = pv;
                 if (np > 0) stg[(size_t)(N + e) * lds + i] = pa;

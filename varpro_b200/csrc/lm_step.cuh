@@ -80,8 +80,11 @@ struct LmEval {
     double rnorm2;                     // ||r||^2
     double g[VP_LM_MAXQ];              // J^T r
     double H[VP_LM_MAXQ * VP_LM_MAXQ]; // J^T J, column-major q x q (leading dimension q)
-    int finite;
+    int finite; // bit 0: the residual is valid (Phi_w and ||r||^2 finite: the reference's cache is Some); bit 1: g and H are finite
 };
+#define VP_EVAL_RESIDUAL_OK 1
+#define VP_EVAL_DERIVS_OK 2
+#define VP_EVAL_ALL_OK 3
 
 // The lmder state between two evaluations. NQ = capacity of the arrays; matrices are packed
 // with leading dimension q, so LmStateT<q> is a prefix-compatible view of LmStateT<VP_LM_MAXQ>.
@@ -479,7 +482,9 @@ VP_HD bool lm_advance_core(LmStateT<NQ> &st, const LmConfig &cfg, const double r
         st.last_accepted = 1;
         if (n == 0) { st.termination = TERM_NO_PARAMETERS; return false; }
         const double fn = sqrt(rnorm2);
-        if (!finite || !isfinite(fn)) { st.fnorm = fn; st.termination = TERM_NUMERICAL; return false; }
+        // residuals() is None -> the crate stops with User; a non-finite norm of an existing residual -> Numerical
+        if (!(finite & VP_EVAL_RESIDUAL_OK)) { st.fnorm = fn; st.termination = TERM_USER; return false; }
+        if (!isfinite(fn)) { st.fnorm = fn; st.termination = TERM_NUMERICAL; return false; }
         st.fnorm = fn;
         if (fn == 0.0) { st.termination = TERM_RESIDUALS_ZERO; return false; }
         st.par = 0.0;
@@ -490,7 +495,8 @@ VP_HD bool lm_advance_core(LmStateT<NQ> &st, const LmConfig &cfg, const double r
         // trial evaluation
         st.nfev += 1;
         const double fnorm1 = sqrt(rnorm2);
-        if (!finite || !isfinite(fnorm1)) { st.last_accepted = 0; st.termination = TERM_NUMERICAL; return false; }
+        if (!(finite & VP_EVAL_RESIDUAL_OK)) { st.last_accepted = 0; st.termination = TERM_USER; return false; }
+        if (!isfinite(fnorm1)) { st.last_accepted = 0; st.termination = TERM_NUMERICAL; return false; }
         double actred = -1.0;
         if (0.1 * fnorm1 < st.fnorm) actred = 1.0 - (fnorm1 / st.fnorm) * (fnorm1 / st.fnorm);
         double wa3[NQ];
@@ -542,6 +548,9 @@ VP_HD bool lm_advance_core(LmStateT<NQ> &st, const LmConfig &cfg, const double r
     // one copy of the factorisation / lmpar code for both entry points (the step is straight-line
     // code of tens of KB once unrolled; the instruction cache is cold every time it runs)
     if (prepare) {
+        // the Jacobian of the (new) accepted point is needed now: non-finite derivatives end the fit here, a
+        // rejected trial with a valid residual never looks at them (like lmder, which evaluates J only after acceptance)
+        if (!(finite & VP_EVAL_DERIVS_OK)) { st.termination = TERM_NUMERICAL; return false; }
         if (!lm_outer_prepare<QT, NQ>(st, cfg, Hev, gev)) return false;
     }
     lm_inner_propose<QT, NQ>(st);

@@ -178,7 +178,7 @@ panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
         for (int idx = tid; idx < m * (n + p); idx += nt) {
             const int i = idx % m;
             const double v = (w ? (double)w[i] : 1.0) * pre[idx];
-            bad |= !isfinite(v);
+            if (idx < m * n) bad |= (!isfinite(v) ? 1 : 0) | (fabs(v) > RANK_HUGE_ENTRY ? (2 << (idx / m)) : 0);
             col[idx] = v;
         }
     }
@@ -193,13 +193,22 @@ panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
             const double a1 = np > 1 ? alpha_s[md.pidx[j][1]] : 0.0;
             const BasisVals bv = basis_eval_all(md.kind[j], xi, a0, a1, md.scale[j]);
             const double v = wi * bv.v;
-            bad |= !isfinite(v);
+            bad |= (!isfinite(v) ? 1 : 0) | (fabs(v) > RANK_HUGE_ENTRY ? (2 << j) : 0); // flag word of rank_policy.cuh
             col[(size_t)j * m + i] = v;
-            if (np > 0) { const double d = wi * bv.d0; bad |= !isfinite(d); col[(size_t)(n + e) * m + i] = d; ++e; }
-            if (np > 1) { const double d = wi * bv.d1; bad |= !isfinite(d); col[(size_t)(n + e) * m + i] = d; ++e; }
+            if (np > 0) { col[(size_t)(n + e) * m + i] = wi * bv.d0; ++e; }
+            if (np > 1) { col[(size_t)(n + e) * m + i] = wi * bv.d1; ++e; }
         }
     }
     bad = __syncthreads_or(bad);
+    if (bad >> 1) { // overflowing basis columns: zero them and their derivative columns
+        for (int idx = tid; idx < m * (n + p); idx += nt) {
+            const int c = idx / m;
+            const int j = c < n ? c : md.e_basis[c - n];
+            if ((bad >> (1 + j)) & 1) col[idx] = 0.0;
+        }
+        __syncthreads();
+    }
+    bad &= 1;
     dbg_mark(dbg, 1);
 
     // 2.-4. the rounds

@@ -137,14 +137,13 @@ __device__ __forceinline__ int panel_hh_eval(const ModelDesc &md, const double (
             const double a1 = np > 1 ? alpha_s[md.pidx[j][1]] : 0.0;
             const BasisVals bv = basis_eval_all(md.kind[j], xi, a0, a1, md.scale[j]);
             const double v = in ? wi * bv.v : 0.0;
-            bad |= !isfinite(v);
+            bad |= (!isfinite(v) ? 1 : 0) | (fabs(v) > RANK_HUGE_ENTRY ? (2 << j) : 0); // flag word of rank_policy.cuh
             a[r][j] = v;
             // derivative columns are ordered by (basis function, slot); e is uniform across threads
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (s < np) {
                     const double dv = in ? wi * (s == 0 ? bv.d0 : bv.d1) : 0.0;
-                    bad |= !isfinite(dv);
 #pragma unroll
                     for (int ee = 0; ee < P; ++ee)
                         if (ee == e) { a[r][N + ee] = dv; d0[r][ee] = dv; }
@@ -179,6 +178,18 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
     const int m = md.m;
 
     bad = __syncthreads_or(bad);
+    if (bad >> 1) { // overflowing basis columns (rank_policy.cuh): zero them and their derivative columns
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                if ((bad >> (1 + j)) & 1) a[r][j] = 0.0;
+#pragma unroll
+            for (int e = 0; e < P; ++e)
+                if ((bad >> (1 + md.e_basis[e])) & 1) { a[r][N + e] = 0.0; d0[r][e] = 0.0; }
+        }
+    }
+    bad &= 1;
     dbg_mark(dbg, 1);
 
     // ---- 2. Householder steps ------------------------------------------------------------

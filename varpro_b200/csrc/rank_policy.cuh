@@ -38,6 +38,15 @@
 
 namespace vp {
 
+// A weighted basis column whose sum of squares overflows (entries beyond ~1e154, e.g. exp(-x/tau) at a slightly
+// negative trial tau) cannot be factored; the reference's restatement ends up with a zero singular vector and a
+// zero coefficient for it (sigma = inf => U_j = a_j / inf = 0, c_j = 0) and carries on with a finite residual, which
+// the LM loop then simply rejects. The panel evaluators reproduce that: such a column -- and its derivative
+// columns -- are zeroed before the factorisation (exact zero column => sigma = 0 => truncated), instead of letting
+// inf * 0 poison the evaluation. Bit 0 of the evaluators' flag word = a non-finite entry of Phi_w (cache = None,
+// src/solvers/levmar/mod.rs:43-72); bit 1 + j = column j overflows.
+constexpr double RANK_HUGE_ENTRY = 1e154;
+
 struct SmallSvd {
     int truncated;                      // 1: at least one singular value was truncated
     double Urot[VP_MAX_N * VP_MAX_N];   // Ur diag(keep), column-major, leading dimension n

@@ -174,7 +174,8 @@ __device__ void stream_finalize(const StreamArgs<T> &a, int n, int p, int nparts
         EvalOut *o = a.out;
         const int q = a.q;
         double rn2 = sh[0];
-        int finite = isfinite(rn2) && !nonfinite;
+        const int resid_ok = isfinite(rn2) && !nonfinite;
+        int finite = 1; // derivatives
         for (int kk = 0; kk < q; ++kk) {
             double gk = 0.0;
             for (int e = 0; e < p; ++e)
@@ -199,7 +200,7 @@ __device__ void stream_finalize(const StreamArgs<T> &a, int n, int p, int nparts
                 finite = finite && isfinite(h);
             }
         o->rnorm2 = rn2;
-        o->finite = finite;
+        o->finite = (resid_ok ? VP_EVAL_RESIDUAL_OK : 0) | (finite ? VP_EVAL_DERIVS_OK : 0);
         *a.ticket = 0; // re-arm for the next launch
         dbg_mark(a.dbg, 13);
     }

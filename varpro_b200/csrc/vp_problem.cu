@@ -398,7 +398,8 @@ static int add_full_jacobian_term_t(vp_problem *pr)
     for (int a = 0; a < p; ++a)
         for (int b = 0; b < p; ++b)
             o->H[md.e_param[b] * q + md.e_param[a]] += Wm[md.e_basis[a]][md.e_basis[b]] * U[a][b];
-    for (int i = 0; i < q * q; ++i) o->finite = o->finite && std::isfinite(o->H[i]);
+    for (int i = 0; i < q * q; ++i)
+        if (!std::isfinite(o->H[i])) o->finite &= ~VP_EVAL_DERIVS_OK;
     return VP_OK;
 }
 static int add_full_jacobian_term(vp_problem *pr)
@@ -438,7 +439,7 @@ int vp_refresh_cached_evaluation(vp_problem *pr)
     if (rc != VP_OK) { pr->cached = false; return rc; }
     pr->cur = dst;
     vp_evalout_to_lm(*pr->out_host, pr->model->md.q, pr->eval);
-    pr->cached = pr->eval.finite != 0;
+    pr->cached = (pr->eval.finite & VP_EVAL_RESIDUAL_OK) != 0;
     return VP_OK;
 }
 
@@ -550,7 +551,7 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     }
     if (rc != VP_OK) { vp_problem_destroy(pr); return rc; }
     vp_evalout_to_lm(*pr->out_host, md.q, pr->eval);
-    pr->cached = pr->eval.finite != 0;
+    pr->cached = (pr->eval.finite & VP_EVAL_RESIDUAL_OK) != 0;
     *out = pr;
     return VP_OK;
 }
@@ -626,7 +627,7 @@ extern "C" int vp_reduce(vp_problem *pr, vp_reduced *out)
     const int q = pr->model->md.q;
     memset(out, 0, sizeof(*out));
     out->rnorm2 = pr->eval.rnorm2;
-    out->finite = pr->eval.finite;
+    out->finite = pr->eval.finite == VP_EVAL_ALL_OK ? 1 : 0;
     out->q = q;
     for (int k = 0; k < q; ++k) out->g[k] = pr->eval.g[k];
     for (int i = 0; i < q * q; ++i) out->H[i] = pr->eval.H[i];

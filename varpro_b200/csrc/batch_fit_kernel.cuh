@@ -203,7 +203,7 @@ batch_fit_kernel(const BatchArgs a)
                     e += np;
                 }
             }
-            bad = __syncthreads_or(bad);
+            bad = block_or_flags(bad, 1 + N);
             if (bad >> 1) { // overflowing basis columns: zero them and their derivative columns
                 for (int idx = tid; idx < m * NPV; idx += THREADS) {
                     const int c = idx / m, i = idx - c * m;

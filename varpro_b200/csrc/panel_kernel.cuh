@@ -199,7 +199,7 @@ panel_kernel(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
             if (np > 1) { col[(size_t)(n + e) * m + i] = wi * bv.d1; ++e; }
         }
     }
-    bad = __syncthreads_or(bad);
+    bad = block_or_flags(bad, 1 + n);
     if (bad >> 1) { // overflowing basis columns: zero them and their derivative columns
         for (int idx = tid; idx < m * (n + p); idx += nt) {
             const int c = idx / m;

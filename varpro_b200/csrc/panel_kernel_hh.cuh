@@ -177,7 +177,7 @@ __device__ __forceinline__ void panel_hh_factor(const ModelDesc &md, double (&a)
     const int tid = threadIdx.x;
     const int m = md.m;
 
-    bad = __syncthreads_or(bad);
+    bad = block_or_flags(bad, 1 + N);
     if (bad >> 1) { // overflowing basis columns (rank_policy.cuh): zero them and their derivative columns
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {

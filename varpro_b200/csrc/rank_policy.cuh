@@ -47,6 +47,19 @@ namespace vp {
 // src/solvers/levmar/mod.rs:43-72); bit 1 + j = column j overflows.
 constexpr double RANK_HUGE_ENTRY = 1e154;
 
+#ifdef __CUDACC__
+// Bitwise OR of the evaluators' flag words over the CTA. __syncthreads_or only tells whether ANY thread had a
+// non-zero word, which is the common (all clear) answer after one barrier; the per-bit reductions run only then.
+__device__ __forceinline__ int block_or_flags(int flags, int nbits)
+{
+    if (!__syncthreads_or(flags)) return 0;
+    int out = 0;
+    for (int b = 0; b < nbits; ++b)
+        if (__syncthreads_or((flags >> b) & 1)) out |= 1 << b;
+    return out;
+}
+#endif
+
 struct SmallSvd {
     int truncated;                      // 1: at least one singular value was truncated
     double Urot[VP_MAX_N * VP_MAX_N];   // Ur diag(keep), column-major, leading dimension n

@@ -151,6 +151,13 @@ extern "C" {
     pub fn vp_fit(problem: *mut vp_problem, options: *const vp_lm_options, report: *mut vp_fit_report) -> c_int;
     pub fn vp_fit_many(problems: *mut *mut vp_problem, n: i64, options: *const vp_lm_options,
                        reports: *mut vp_fit_report, reserved: i32) -> c_int;
+    /// Host-resident data sets of one model, pipelined on library worker threads (copy of one problem overlaps the
+    /// fit of another): the loop over SeparableProblemBuilder::build + LevMarSolver::fit per data set.
+    pub fn vp_fit_host_batch(ctx: *mut vp_ctx, dtype: c_int, m: i64, x_host: *const c_void, q: i32, n: i32,
+                             basis: *const vp_basis_desc, n_problems: i64, s: i64, y_hosts: *const *const c_void,
+                             ld_y: i64, w_host: *const c_void, svd_eps: f64, alpha0: *const f64,
+                             options: *const vp_lm_options, workers: i32, reports: *mut vp_fit_report,
+                             alpha_out: *mut f64, c_outs: *const *mut c_void) -> c_int;
 
     // ---- FitStatistics::try_calculate per right-hand side (src/statistics/mod.rs:352-441) ----------
     pub fn vp_statistics(problem: *mut vp_problem, cov_out: *mut f64, reduced_chi2_out: *mut f64,
@@ -165,6 +172,7 @@ extern "C" {
     pub fn vp_batch_fit(batch: *mut vp_batch, options: *const vp_lm_options, reports: *mut vp_fit_report) -> c_int;
     pub fn vp_batch_params(batch: *mut vp_batch, alpha_out: *mut f64) -> c_int;
     pub fn vp_batch_set_params(batch: *mut vp_batch, alpha: *const f64) -> c_int;
+    pub fn vp_batch_set_rank_policy(batch: *mut vp_batch, policy: c_int) -> c_int;
     pub fn vp_batch_linear_coefficients(batch: *mut vp_batch, c_out: *mut f64) -> c_int;
 
     // ---- diagnostics -------------------------------------------------------------------------------------

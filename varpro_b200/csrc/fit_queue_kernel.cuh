@@ -55,10 +55,14 @@ struct QueueFit {
     int pad_;
 };
 
-struct QueueItem {
-    int fit, item;
-    unsigned long long seq; // item index + 1 once the item is valid
-};
+// A queue slot is ONE 64-bit word, written with a single st.release and read with a single ld.acquire:
+// [63:32] sequence = queue index + 1 once the item is valid, [31:12] fit, [11:0] item of the fit's evaluation.
+typedef unsigned long long QueueItem;
+constexpr int QUEUE_ITEM_BITS = 12, QUEUE_FIT_BITS = 20;
+__host__ __device__ inline QueueItem queue_pack(unsigned long long idx, int fit, int item)
+{
+    return ((idx + 1ull) << 32) | ((unsigned long long)(unsigned)fit << QUEUE_ITEM_BITS) | (unsigned long long)(unsigned)item;
+}
 
 struct QueueCtl {
     unsigned long long head; // next item index to claim
@@ -191,19 +195,12 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         if (tid == 0) push_base = atomicAdd(&ctl->tail, (unsigned long long)push_n);
         __syncthreads();
         const int nitems = push_n;
-        // publish the items: all threads fill slots, one fence, then the sequence flags (a slot is
-        // valid once its flag holds item index + 1; consumers read it with ld.acquire)
+        // publish the items: one st.release per slot (the fence + barrier above ordered everything the consumers
+        // will read before these stores)
         {
             const unsigned long long base = push_base;
-            for (int j = tid; j < nitems; j += THREADS) {
-                QueueItem *it = &ctl->items[(base + j) % ctl->cap];
-                it->fit = k;
-                it->item = j;
-            }
-            __threadfence();
-            __syncthreads();
             for (int j = tid; j < nitems; j += THREADS)
-                st_release_gpu_u64(&ctl->items[(base + j) % ctl->cap].seq, base + j + 1ull);
+                st_release_gpu_u64(&ctl->items[(base + j) % ctl->cap], queue_pack(base + j, k, j));
         }
         __syncthreads();
         if (dbg_on && tid == 0) { fin_acc[4] += global_timer_ns() - ts1; fin_acc[5] += 1; }
@@ -228,16 +225,29 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         const unsigned long long tf0 = dbg_on ? global_timer_ns() : 0ull;
         // everything the LM step and the next panel need that does not depend on the fold is requested
         // first, so that its L2 latency overlaps the fold: the LM state, M, x and w
+        // (into REGISTERS: a store to shared memory would stall the warp until the load has returned, before the
+        // fold's own loads are even issued)
         unsigned long long *fw = reinterpret_cast<unsigned long long *>(qf->fit);
         unsigned long long *lw = reinterpret_cast<unsigned long long *>(&fd_s);
-        for (int i = tid; i < FIT_WORDS; i += THREADS) lw[i] = __ldcg(fw + i);
-        if (tid < P * P) Msh[tid] = __ldcg(&qf->small->M[(tid / P) * VP_MAX_P + (tid % P)]);
-        if (tid == 0) nonfinite_s = __ldcg(&qf->small->nonfinite);
+        constexpr int FWPT = (FIT_WORDS + THREADS - 1) / THREADS;
+        unsigned long long fwreg[FWPT];
+#pragma unroll
+        for (int t = 0; t < FWPT; ++t) fwreg[t] = (tid + t * THREADS < FIT_WORDS) ? __ldcg(fw + tid + t * THREADS) : 0ull;
+        const double m_reg = (tid < P * P) ? __ldcg(&qf->small->M[(tid / (P > 0 ? P : 1)) * VP_MAX_P + (tid % (P > 0 ? P : 1))]) : 0.0;
+        const int nonfinite_reg = (tid == 0) ? __ldcg(&qf->small->nonfinite) : 0;
         double xi[RPT], wi[RPT];
         load_xw(qf, xi, wi);
         // rinv_s still holds Rinv of this fit's current panel (loaded with the item's fragments)
         fold_rows(qf->partials, qf->red_stride, qf->part.nparts, NVF, sums_s, fold_scratch);
-        if (tid == 0) *qf->ticket = 0u; // re-arm: the next evaluation of this problem may be a single-evaluation launch (vp_set_params)
+#pragma unroll
+        for (int t = 0; t < FWPT; ++t)
+            if (tid + t * THREADS < FIT_WORDS) lw[tid + t * THREADS] = fwreg[t];
+        if (tid < P * P) Msh[tid] = m_reg;
+        if (tid == 0) {
+            nonfinite_s = nonfinite_reg;
+            *qf->ticket = 0u; // re-arm: the next evaluation of this problem may be a single-evaluation launch (vp_set_params)
+        }
+        __syncthreads();
         fused_assemble<N, P>(sums_s, Msh, P, rinv_s, qf->md.e_basis, qf->md.e_param, q, qf->jac_full, nonfinite_s, &ev_s);
         const unsigned long long tf1 = dbg_on ? global_timer_ns() : 0ull;
         if (tid == 0) {
@@ -299,16 +309,18 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         const unsigned long long t_a = dbg_on ? global_timer_ns() : 0ull;
         if (tid == 0) {
             const unsigned long long idx = atomicAdd(&ctl->head, 1ull);
-            QueueItem *it = &ctl->items[idx % ctl->cap];
+            const QueueItem *it = &ctl->items[idx % ctl->cap];
             const unsigned long long t0 = global_timer_ns();
+            unsigned long long word = 0ull;
             int got = 0;
             for (;;) {
-                if (ld_acquire_gpu_u64(&it->seq) == idx + 1ull) { got = 1; break; }
+                word = ld_acquire_gpu_u64(it);
+                if ((word >> 32) == ((idx + 1ull) & 0xffffffffull)) { got = 1; break; }
                 if (ld_acquire_gpu_s32(&ctl->fits_left) <= 0 && idx >= ld_acquire_gpu_u64(&ctl->tail)) break;
                 if (global_timer_ns() - t0 > SPIN_TIMEOUT_NS) { ctl->error = 1; break; }
             }
-            item_fit = got ? it->fit : -1;
-            item_idx = got ? it->item : 0;
+            item_fit = got ? (int)((word >> QUEUE_ITEM_BITS) & ((1u << QUEUE_FIT_BITS) - 1u)) : -1;
+            item_idx = got ? (int)(word & ((1u << QUEUE_ITEM_BITS) - 1u)) : 0;
         }
         __syncthreads();
         const int k = item_fit, item = item_idx;

@@ -246,6 +246,7 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
                            const std::vector<LmConfig> &cfgs)
 {
     const int K = (int)prs.size();
+    if (K >= (1 << QUEUE_FIT_BITS)) return VP_ERR_UNSUPPORTED_BASIS; // does not fit a queue slot: per-fit drivers
     vp_problem *p0 = prs[0];
     int lds = 0;
     const int qidx = queue_kernel_for(p0, &lds);
@@ -311,6 +312,7 @@ static int fit_queue_group(vp_ctx *ctx, const std::vector<vp_problem *> &prs, st
         // the partition vp_fit's persistent kernel uses for this problem (one part per CTA of ITS grid)
         int nparts = pr->plan_fit >= 0 ? pr->fit_grid : (f.ntiles < ctx->sm_count ? f.ntiles : ctx->sm_count);
         if (nparts > pr->max_grid) nparts = pr->max_grid;
+        if (nparts >= (1 << QUEUE_ITEM_BITS)) nparts = (1 << QUEUE_ITEM_BITS) - 1;
         f.part = make_partition(f.ntiles, nparts);
         // the kernel sizes the work items of every evaluation itself (negative: fixed number of parts per item)
         f.items_per_cta = ctx->opt.queue_parts_per_item > 0 ? -ctx->opt.queue_parts_per_item : ctx->opt.queue_items_per_cta;

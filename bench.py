@@ -380,7 +380,7 @@ def run_gpu(args, rank, world, local_rank):
         single_cold = BYTES_EVAL / (cold_us * 1e-6) / 1e9
         traffic_static = None
         try:
-            traffic_static = json.load(open(os.path.join(ROOT, "profiles", "r03_queue_traffic.json")))
+            traffic_static = json.load(open(os.path.join(ROOT, "profiles", "round2_queue_traffic.json")))
         except Exception:
             pass
         extras = {}

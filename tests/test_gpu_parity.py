@@ -345,6 +345,24 @@ def test_fit_many_is_bitwise_vp_fit(ctx_options, items_per_cta):
         vb.set_option("queue_items_per_cta", 2)
 
 
+def test_fp32_fit_many_is_bitwise_vp_fit_on_the_persistent_fp32_kernel():
+    """fp32 problems (BASELINE config 4 shape, weighted): vp_fit runs the persistent whole-fit kernel instantiated for
+    float storage, vp_fit_many the work-queue kernel: same parts, same tile code => bitwise equal."""
+    import varpro_b200 as vb
+    solver = vb.LevMarSolver.default()
+    wls = []
+    for k in range(4):
+        wl = W.c4(S=600 + 200 * k, seed=40 + k)
+        wls.append(wl)
+    seq = [solver.fit(W.make_gpu_problem(wl, dtype=np.float32)) for wl in wls]
+    many = solver.fit_many([W.make_gpu_problem(wl, dtype=np.float32) for wl in wls])
+    for a, b in zip(seq, many):
+        assert a.was_successful() and b.was_successful()
+        assert np.array_equal(a.nonlinear_parameters(), b.nonlinear_parameters())
+        assert a.minimization_report.number_of_evaluations == b.minimization_report.number_of_evaluations
+        assert np.array_equal(a.linear_coefficients(), b.linear_coefficients())
+
+
 def test_problems_are_reusable_after_fit_many():
     """vp_fit_many leaves every problem ready for the next call: set_params back to the start gives bitwise the
     evaluation of a fresh problem (the per-problem ticket is re-armed), and a second fit_many repeats the first."""

@@ -173,13 +173,14 @@ batch_fit_kernel(const BatchArgs a)
                     const double a0 = np > 0 ? alpha_s[a.md.pidx[j][0]] : 0.0;
                     const double a1 = np > 1 ? alpha_s[a.md.pidx[j][1]] : 0.0;
                     const double scale = a.md.scale[j];
+                    const double inv0 = (kind == VP_BASIS_EXP_DECAY) ? 1.0 / a0 : 0.0;
 #pragma unroll
                     for (int r = 0; r < RPT; ++r) {
                         const int i = tid + r * THREADS;
                         double v, da = 0.0, db = 0.0;
                         if (kind == VP_BASIS_EXP_DECAY) {
-                            const double ex = exp(-xi[r] / a0);
-                            v = ex; da = ex * xi[r] / (a0 * a0);
+                            const double t = xi[r] * inv0, ex = exp(-t); // one division per basis function, see basis_eval_all
+                            v = ex; da = ex * t * inv0;
                         } else if (kind == VP_BASIS_EXP_RATE_COS) {
                             const double ex = exp(-a0 * xi[r]);
                             double sn, cs;

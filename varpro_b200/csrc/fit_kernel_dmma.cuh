@@ -61,8 +61,8 @@ struct CommArgs {
 
 struct FitArgs {
     ModelDesc md;
-    const double *x; // m values of the independent variable
-    const double *w; // m weights or nullptr
+    const void *x; // m values of the independent variable, in the problem dtype
+    const void *w; // m weights or nullptr, in the problem dtype
     double svd_eps;
     const double *alpha_dev; // parameters of the first evaluation
     FitCtl *ctl;             // fit mode only
@@ -252,10 +252,11 @@ __device__ __forceinline__ int panel_eval_staged(const ModelDesc &md, const doub
         const double scale = md.scale[j];
         double v[RPT], da[RPT], db[RPT];
         if (kind == VP_BASIS_EXP_DECAY) { // exp(-x/tau); exp(-x/tau)*x/(tau*tau)
+            const double inv0 = 1.0 / a0;
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
-                const double ex = exp(-xi[r] / a0);
-                v[r] = ex; da[r] = ex * xi[r] / (a0 * a0); db[r] = 0.0;
+                const double t = xi[r] * inv0, ex = exp(-t); // one division per basis function, see basis_eval_all
+                v[r] = ex; da[r] = ex * t * inv0; db[r] = 0.0;
             }
         } else if (kind == VP_BASIS_EXP_RATE_COS) {
 #pragma unroll
@@ -305,9 +306,11 @@ __device__ __forceinline__ int panel_eval_staged(const ModelDesc &md, const doub
     return bad;
 }
 
-template <int N, int P, int KSTEPS, int NWARPS, bool EXACT>
+// TY: element type of the observations / coefficients in HBM (double or float); all arithmetic is fp64 (fp32
+// problems stream half the bytes and are converted when the tile fragments are loaded, see fit_queue_kernel.cuh).
+template <typename TY, int N, int P, int KSTEPS, int NWARPS, bool EXACT>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
-fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
+fit_kernel_dmma(const StreamArgs<TY> a, const int lds, const FitArgs f)
 {
     constexpr int NPV = N + P;
     constexpr int THREADS = NWARPS * 32;
@@ -344,7 +347,10 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
     const int grp = lane >> 2, tig = lane & 3; // mma "groupID" and "threadID_in_group"
     const int ld = a.ld, S = a.S, nst = a.nstages, q = a.q;
     const size_t stage_elems = (size_t)CT * lds;
-    double *tiles = reinterpret_cast<double *>(smem_raw);
+    TY *tiles = reinterpret_cast<TY *>(smem_raw);
+    // the panel is staged (fp64, column stride lds) in the LAST pst stages of the ring: one for double tiles, two for
+    // float tiles (n + p columns of lds doubles must fit)
+    const int pst = (int)(((size_t)(NPV + 1) * lds * sizeof(double) + stage_elems * sizeof(TY) - 1) / (stage_elems * sizeof(TY)));
     const bool fit_mode = a.fit != nullptr;
     const int grid = (int)gridDim.x;
 
@@ -361,15 +367,15 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
     // zero the pad rows [ld, lds) of every column slot (never written by the copies)
     if (lds > ld)
         for (int slot = tid; slot < nst * CT; slot += THREADS)
-            for (int r = ld; r < lds; ++r) tiles[(size_t)slot * lds + r] = 0.0;
+            for (int r = ld; r < lds; ++r) tiles[(size_t)slot * lds + r] = (TY)0;
     // this thread's rows of x and w stay in registers for the whole fit
     double xi[RPT], wi[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const int i = tid + r * THREADS;
         const bool in = i < f.md.m;
-        xi[r] = in ? f.x[i] : 0.0;
-        wi[r] = in ? (f.w ? f.w[i] : 1.0) : 0.0;
+        xi[r] = in ? (double)static_cast<const TY *>(f.x)[i] : 0.0;
+        wi[r] = in ? (f.w ? (double)static_cast<const TY *>(f.w)[i] : 1.0) : 0.0;
     }
     // every CTA keeps its own copy of the LM state
     if (fit_mode) {
@@ -386,14 +392,14 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
 
     // Producer (see stream_kernel_dmma): column c of a tile is fetched by warp c % NWARPS, lane 0.
     int next_i = 0, next_st = 0;
-    const uint32_t col_bytes = (uint32_t)(ld * sizeof(double));
+    const uint32_t col_bytes = (uint32_t)(ld * sizeof(TY));
     auto issue = [&]() {
         const int col0 = (tile0 + next_i) * CT;
         const int nc = min(CT, S - col0);
         if (lane == 0) {
             if (warp == 0) mbar_arrive_expect_tx(&full_bar[next_st], col_bytes * nc);
-            double *dst = tiles + (size_t)next_st * stage_elems;
-            const double *src = a.Y + (size_t)col0 * ld;
+            TY *dst = tiles + (size_t)next_st * stage_elems;
+            const TY *src = a.Y + (size_t)col0 * ld;
 #pragma unroll 1
             for (int c = warp; c < nc; c += NWARPS)
                 bulk_copy_g2s(dst + (size_t)c * lds, src + (size_t)c * ld, col_bytes, &full_bar[next_st]);
@@ -401,11 +407,11 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
         ++next_i;
         if (++next_st == nst) next_st = 0;
     };
-    // the observations do not depend on the parameters: start fetching immediately. The last
-    // stage is where the panel is staged for the fragment loads, so it is filled afterwards.
-    for (int i = 0; i < nst - 1 && i < my; ++i) issue();
+    // the observations do not depend on the parameters: start fetching immediately. The last pst
+    // stages are where the panel is staged for the fragment loads, so they are filled afterwards.
+    for (int i = 0; i < nst - pst && i < my; ++i) issue();
 
-    double *pstage = tiles + (size_t)(nst - 1) * stage_elems;
+    double *pstage = reinterpret_cast<double *>(tiles + (size_t)(nst - pst) * stage_elems);
     uint32_t phase_bits = 0; // bit st: parity of the next completion to wait for on stage st
 
     for (unsigned int e = 0;; ++e) {
@@ -414,7 +420,7 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
             alpha_s[tid] = tid < q ? ((e == 0 || !fit_mode) ? __ldcg(&f.alpha_dev[tid]) : fd_s.st.x_trial[tid]) : 0.0;
         __syncthreads();
         const int cdst = fit_mode ? (fd_s.cur ^ 1) : a.cdst;
-        double *Cout = cdst ? a.C1 : a.C0;
+        TY *Cout = cdst ? a.C1 : a.C0;
 
         // ---- K1: the panel, in this CTA ---------------------------------------------------
         dbg_mark(a.dbg, 8);
@@ -443,9 +449,16 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
                 a2[rs] = ok ? src2[8 * rs] : 0.0;
             }
         }
-        fence_proxy_async_smem(); // generic accesses to the panel stage before the bulk copy overwrites it
+        if (sizeof(TY) != sizeof(double)) {
+            // the f64 staging overlaid float slots: restore the zero pad rows [ld, lds) of the staging stages
+            __syncthreads();
+            if (lds > ld)
+                for (int slot = (nst - pst) * CT + tid; slot < nst * CT; slot += THREADS)
+                    for (int r = ld; r < lds; ++r) tiles[(size_t)slot * lds + r] = (TY)0;
+        }
+        fence_proxy_async_smem(); // generic accesses to the panel stages before the bulk copies overwrite them
         __syncthreads();
-        if (next_i < my) issue();
+        for (int k = 0; k < pst && next_i < my; ++k) issue();
         dbg_mark(a.dbg, 1);
 
         // ---- K2: stream this CTA's part -----------------------------------------------------
@@ -455,12 +468,12 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
         for (int i = 0; i < my; ++i) {
             const int col0 = (tile0 + i) * CT;
             const int nc = min(CT, S - col0);
-            const double *tp = tiles + (size_t)st * stage_elems;
+            const TY *tp = tiles + (size_t)st * stage_elems;
             mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
             phase_bits ^= 1u << st;
             if (i == 0) dbg_mark(a.dbg, 2);
             if (++st == nst) st = 0;
-            dmma_tile<double, N, P, KSTEPS, NWARPS, EXACT>(tp, lds, nc, col0, a1, a2, rinv_s, part, bu, Cout, ebasis, acc, [&]() {
+            dmma_tile<TY, N, P, KSTEPS, NWARPS, EXACT>(tp, lds, nc, col0, a1, a2, rinv_s, part, bu, Cout, ebasis, acc, [&]() {
                 if (i >= 1 && next_i < my) issue(); // refill the stage tile i-1 used
             });
         }
@@ -471,7 +484,7 @@ fit_kernel_dmma(const StreamArgs<double> a, const int lds, const FitArgs f)
         next_i = 0;
         next_st = 0;
         if (fit_mode)
-            for (int i = 0; i < nst - 1 && i < my; ++i) issue();
+            for (int i = 0; i < nst - pst && i < my; ++i) issue();
 
         // ---- part row -> global (double-buffered by evaluation parity), count this CTA in ------------
         double *rows = a.partials + (size_t)(fit_mode ? (e & 1u) : 0u) * grid * a.red_stride;

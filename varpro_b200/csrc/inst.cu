@@ -28,7 +28,7 @@ static const KernelGroup group = {simt_tab, (int)(sizeof(simt_tab) / sizeof(simt
 static const DmmaKernelEntry dmma_tab[] = {VP_DK(8, 4, 0), VP_DK(16, 8, 0), VP_DK(32, 8, 0), VP_DK(32, 8, 1), VP_DK(32, 16, 0)};
 static const KernelGroup group = {nullptr, 0, dmma_tab, (int)(sizeof(dmma_tab) / sizeof(dmma_tab[0])), nullptr, 0, nullptr, 0};
 #elif VP_INST_PART == 3
-#define VP_FK(KS, NW, EX) {N_, P_, KS, NW, EX, (const void *)&fit_kernel_dmma<N_, P_, KS, NW, (EX) != 0>}
+#define VP_FK(KS, NW, EX) {VP_INST_DT, N_, P_, KS, NW, EX, (const void *)&fit_kernel_dmma<T_, N_, P_, KS, NW, (EX) != 0>}
 #if VP_INST_VARIANT == 0
 static const FitKernelEntry fit_tab[] = {VP_FK(8, 4, 0), VP_FK(16, 8, 0)};
 #elif VP_INST_VARIANT == 1

@@ -19,7 +19,7 @@ struct PanelHHEntry {
     const void *fn;
 };
 struct FitKernelEntry { // fit_kernel_dmma: fused panel + streaming reduce (+ whole LM loop)
-    int n, p, ksteps, nwarps, exact;
+    int dtype, n, p, ksteps, nwarps, exact;
     const void *fn;
 };
 struct QueueKernelEntry { // fit_queue_kernel: many fits on one persistent grid with a device-side work queue
@@ -58,6 +58,9 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_3_2_queue2, double, VP_F64, 3, 2, 5) \
     X(f32_3_2_simt, float, VP_F32, 3, 2, 0)  /* the same in fp32 (C4) */ \
     X(f32_3_2_panel, float, VP_F32, 3, 2, 2) \
+    X(f32_3_2_fit0, float, VP_F32, 3, 2, 3) \
+    X(f32_3_2_fit1, float, VP_F32, 3, 2, 3) \
+    X(f32_3_2_fit2, float, VP_F32, 3, 2, 3) \
     X(f32_3_2_queue0, float, VP_F32, 3, 2, 5) \
     X(f32_3_2_queue1, float, VP_F32, 3, 2, 5) \
     X(f32_3_2_queue2, float, VP_F32, 3, 2, 5) \

@@ -169,7 +169,7 @@ struct vp_problem {
     size_t plan_smem = 0;
     // fused evaluation / persistent fit kernel (fit_kernel_dmma), -1 = not available
     int plan_fit = -1;
-    int fit_grid = 0, fit_nst = 0;
+    int fit_grid = 0, fit_nst = 0, fit_lds = 0;
     size_t fit_smem = 0;
     vp::FitCtl *fit_ctl = nullptr;
     int jac_full = 0;       // 1: full Golub-Pereyra Jacobian (vp_problem_set_jacobian); 0: Kaufman (the reference)

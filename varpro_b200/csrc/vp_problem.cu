@@ -6,55 +6,61 @@
 
 using namespace vp;
 
-// the fused evaluation / persistent fit kernel matching a DMMA plan (same tiling), if instantiated
-static int plan_fit_kernel(vp_problem *pr, const DmmaKernelEntry &dk, int lds)
+// the fused evaluation / persistent fit kernel (fit_kernel_dmma<TY>) for this problem, if instantiated for its shape
+static int plan_fit_kernel(vp_problem *pr)
 {
     vp_ctx *ctx = pr->ctx;
+    const vp_model *mo = pr->model;
+    const ModelDesc &md = mo->md;
     pr->plan_fit = -1;
     if (ctx->opt.eval_split) return VP_OK;  // K1 + K2 requested
-    if (pr->model->hosteval) return VP_OK; // the fused kernels evaluate the built-in device basis functions
+    if (mo->hosteval) return VP_OK; // the fused kernels evaluate the built-in device basis functions
+    if (ctx->opt.stream_kernel != VP_STREAMK_AUTO) return VP_OK;
+    const size_t es = vp_esize(mo->dtype);
+    int lds = mo->ld; // conflict-free fragment loads: 4 (mod 16) doubles / 8 (mod 32) floats (see stream_kernel_dmma.cuh)
+    if (mo->dtype == VP_F64) { while (lds % 16 != 4) lds += 2; }
+    else { while (lds % 32 != 8) lds += 4; }
     const KernelTables &KT = vp_kernel_tables();
-    // the best row tiling among the fused instantiations of this shape (independent of the split kernels' choice)
+    // the best row tiling among the fused instantiations of this shape
     int pick = -1;
     for (size_t i = 0; i < KT.fit.size(); ++i) {
         const FitKernelEntry &k = KT.fit[i];
-        if (k.n != dk.n || k.p != dk.p) continue;
+        if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p) continue;
         const int rows = 4 * k.ksteps * k.nwarps;
-        if (rows < pr->model->ld || (k.exact && rows > lds)) continue;
+        if (rows < mo->ld || (k.exact && rows > lds)) continue;
         if (pick < 0 || vp_better_tiling(k.ksteps, k.nwarps, k.exact, KT.fit[(size_t)pick].ksteps, KT.fit[(size_t)pick].nwarps,
                                          KT.fit[(size_t)pick].exact, ctx->opt.fit_warps))
             pick = (int)i;
     }
-    for (size_t i = 0; i < KT.fit.size(); ++i) {
-        if ((int)i != pick) continue;
-        const FitKernelEntry &k = KT.fit[i];
-        const size_t stage_bytes = (size_t)DMMA_CT * lds * sizeof(double);
-        cudaFuncAttributes fa{};
-        VP_CUDA(ctx, cudaFuncGetAttributes(&fa, k.fn));
-        if (fa.sharedSizeBytes + 1024 + 2 * stage_bytes > 227 * 1024) return VP_OK;
-        const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
-        int nst = (int)(budget / stage_bytes);
-        if (nst > STREAM_MAX_STAGES) nst = STREAM_MAX_STAGES;
-        const int max_st = ctx->opt.stream_stages;
-        if (max_st >= 2 && nst > max_st) nst = max_st;
-        if (nst < 2) return VP_OK;
-        const size_t smem = (size_t)nst * stage_bytes;
-        VP_CUDA(ctx, vp_ensure_dynamic_smem(ctx->device, k.fn, smem));
-        int occ = 0;
-        VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.nwarps * 32, smem));
-        if (occ < 1) return VP_OK;
-        const long long ntiles = (pr->S + DMMA_CT - 1) / DMMA_CT;
-        long long grid = (long long)ctx->sm_count * occ; // co-resident by construction (cooperative launch checks it)
-        if (ctx->opt.max_ctas > 0 && grid > ctx->opt.max_ctas) grid = ctx->opt.max_ctas;
-        if (grid > ntiles) grid = ntiles;
-        if (grid > pr->max_grid) grid = pr->max_grid;
-        pr->plan_fit = (int)i;
-        if (4 * k.ksteps * k.nwarps > pr->plan_rows) pr->plan_rows = 4 * k.ksteps * k.nwarps;
-        pr->fit_grid = (int)grid;
-        pr->fit_nst = nst;
-        pr->fit_smem = smem;
-        return VP_OK;
-    }
+    if (pick < 0) return VP_OK;
+    const FitKernelEntry &k = KT.fit[(size_t)pick];
+    const size_t stage_bytes = (size_t)DMMA_CT * lds * es;
+    const int pst = (int)(((size_t)(md.n + md.p + 1) * lds * sizeof(double) + stage_bytes - 1) / stage_bytes); // panel staging stages
+    cudaFuncAttributes fa{};
+    VP_CUDA(ctx, cudaFuncGetAttributes(&fa, k.fn));
+    if (fa.sharedSizeBytes + 1024 + (size_t)(pst + 1) * stage_bytes > 227 * 1024) return VP_OK;
+    const size_t budget = 227 * 1024 - fa.sharedSizeBytes - 1024;
+    int nst = (int)(budget / stage_bytes);
+    if (nst > STREAM_MAX_STAGES) nst = STREAM_MAX_STAGES;
+    const int max_st = ctx->opt.stream_stages;
+    if (max_st >= 2 && nst > max_st) nst = max_st;
+    if (nst < pst + 1) return VP_OK;
+    const size_t smem = (size_t)nst * stage_bytes;
+    VP_CUDA(ctx, vp_ensure_dynamic_smem(ctx->device, k.fn, smem));
+    int occ = 0;
+    VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.nwarps * 32, smem));
+    if (occ < 1) return VP_OK;
+    const long long ntiles = (pr->S + DMMA_CT - 1) / DMMA_CT;
+    long long grid = (long long)ctx->sm_count * occ; // co-resident by construction (cooperative launch checks it)
+    if (ctx->opt.max_ctas > 0 && grid > ctx->opt.max_ctas) grid = ctx->opt.max_ctas;
+    if (grid > ntiles) grid = ntiles;
+    if (grid > pr->max_grid / 2) grid = pr->max_grid / 2; // two row buffers (evaluation parity)
+    pr->plan_fit = pick;
+    if (4 * k.ksteps * k.nwarps > pr->plan_rows) pr->plan_rows = 4 * k.ksteps * k.nwarps;
+    pr->fit_lds = lds;
+    pr->fit_grid = (int)grid;
+    pr->fit_nst = nst;
+    pr->fit_smem = smem;
     return VP_OK;
 }
 
@@ -113,7 +119,7 @@ static int plan_stream(vp_problem *pr)
                     pr->plan_grid = (int)grid;
                     pr->plan_nst = nst;
                     pr->plan_smem = smem;
-                    return plan_fit_kernel(pr, k, lds);
+                    return plan_fit_kernel(pr);
                 }
             }
         }
@@ -168,7 +174,7 @@ static int plan_stream(vp_problem *pr)
                     pr->plan_grid = (int)grid;
                     pr->plan_nst = nst;
                     pr->plan_smem = smem;
-                    return VP_OK;
+                    return plan_fit_kernel(pr);
                 }
             }
         }
@@ -266,7 +272,8 @@ static int launch_stream_t(vp_problem *pr, int cdst, bool graph_mode)
 // One launch of fit_kernel_dmma: a single fused evaluation (fit_mode = false; result in out_dev,
 // coefficients into buffer cdst) or a whole fit (fit_mode = true; cooperative launch, state in fit_dev).
 // Either way CTA b works on part b of the canonical partition (dmma_tile.cuh).
-int vp_launch_fused(vp_problem *pr, int cdst, bool fit_mode)
+template <typename T>
+static int launch_fused_t(vp_problem *pr, int cdst, bool fit_mode)
 {
     vp_ctx *ctx = pr->ctx;
     vp_model *mo = pr->model;
@@ -274,15 +281,15 @@ int vp_launch_fused(vp_problem *pr, int cdst, bool fit_mode)
     const FitKernelEntry &k = vp_kernel_tables().fit[pr->plan_fit];
     cudaStream_t stream = ctx->stream;
     const int grid = pr->fit_grid;
-    StreamArgs<double> a{};
-    a.Y = (const double *)pr->Yw; a.ld = mo->ld; a.S = (int)pr->S;
+    StreamArgs<T> a{};
+    a.Y = (const T *)pr->Yw; a.ld = mo->ld; a.S = (int)pr->S;
     a.Pq = nullptr; a.Pe = nullptr; a.ldp = pr->ldp; a.small = nullptr;
     {
         const TilePartition tp = make_partition((int)((pr->S + DMMA_CT - 1) / DMMA_CT), grid);
         a.tiles_base = tp.base;
         a.tiles_rem = tp.rem;
     }
-    a.C0 = (double *)pr->C[0]; a.C1 = (double *)pr->C[1]; a.cdst = cdst;
+    a.C0 = (T *)pr->C[0]; a.C1 = (T *)pr->C[1]; a.cdst = cdst;
     a.fit = fit_mode ? pr->fit_dev : nullptr;
     a.cond = 0ull;
     a.partials = pr->partials; a.red_stride = pr->red_stride; a.ticket = pr->ticket; a.out = pr->out_dev;
@@ -290,13 +297,13 @@ int vp_launch_fused(vp_problem *pr, int cdst, bool fit_mode)
     for (int e = 0; e < VP_MAX_P; ++e) { a.e_basis[e] = md.e_basis[e]; a.e_param[e] = md.e_param[e]; }
     FitArgs f{};
     f.md = md;
-    f.x = (const double *)mo->x_dev; f.w = (const double *)pr->w_dev;
+    f.x = mo->x_dev; f.w = pr->w_dev;
     f.svd_eps = pr->rank_tol;
     f.alpha_dev = pr->alpha_dev;
     f.ctl = pr->fit_ctl;
     f.jac_full = pr->jac_full;
     if (pr->comm) f.comm = pr->comm->args;
-    int lds = pr->plan_lds;
+    int lds = pr->fit_lds;
     void *args[] = {(void *)&a, (void *)&lds, (void *)&f};
     if (fit_mode) {
         VP_CUDA(ctx, cudaMemsetAsync(pr->fit_ctl, 0, sizeof(FitCtl), stream));
@@ -306,6 +313,11 @@ int vp_launch_fused(vp_problem *pr, int cdst, bool fit_mode)
     }
     ctx->launches++;
     return VP_OK;
+}
+
+int vp_launch_fused(vp_problem *pr, int cdst, bool fit_mode)
+{
+    return pr->model->dtype == VP_F32 ? launch_fused_t<float>(pr, cdst, fit_mode) : launch_fused_t<double>(pr, cdst, fit_mode);
 }
 
 int vp_launch_panel(vp_problem *pr)
@@ -537,6 +549,7 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     {
         int ldp = pr->plan_rows > ld ? pr->plan_rows : ld;
         if (pr->plan_lds > ldp) ldp = pr->plan_lds;
+        if (pr->fit_lds > ldp) ldp = pr->fit_lds;
         pr->ldp = (ldp + 3) / 4 * 4;
         cudaError_t e = DEV_ALLOC(ctx, &pr->Pq, es * (size_t)pr->ldp * (md.n + md.p + 1));
         if (e != cudaSuccess) { vp_problem_destroy(pr); return vp_fail(ctx, VP_ERR_OUT_OF_MEMORY, cudaGetErrorString(e)); }

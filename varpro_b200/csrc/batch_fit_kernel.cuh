@@ -7,20 +7,28 @@
 // (src/problem/builder.rs:116-324, src/solvers/levmar/mod.rs:238-254 per problem).
 //
 // One CTA fits one problem at a time, start to finish, and then takes the next one from a global
-// counter (fits need different numbers of evaluations): y_p is read from HBM ONCE per fit and stays
-// in registers; per evaluation the CTA
+// counter (fits need different numbers of evaluations): y_p is read from HBM ONCE per fit (then L2);
+// per evaluation the CTA
 //   1. regenerates Phi_w(alpha_p), D(alpha_p) from x into a shared-memory working matrix (m x (n+p))
 //      -- materialising Phi for 65 536 problems would take 6.4 GB --
-//   2. runs n Householder steps on [Phi_w | D | y] (y carried along in registers): one fused block
-//      reduction per step (panel_kernel_hh.cuh explains the identities),
-//   3. one more reduction over the rows >= n of the rotated system gives everything the LM step
-//      needs:  ||r||^2 = sum y~_i^2,  u_e = D~_e . y~,  M_ef = D~_e . D~_f   and the top rows give
+//   2. runs n Householder steps on [Phi_w | D | y] (y carried along in registers). EVERY ROW OF THE
+//      WORKING SYSTEM BELONGS TO ONE THREAD, so the only thing that crosses threads is the reduction
+//      of the reflector's dot products: the sweep that applies reflector J also accumulates the dots
+//      reflector J + 1 needs, a finished row is saved and then zeroed in place and the padding rows
+//      hold zeros, so the sweeps carry no row predicates at all,
+//   3. the last sweep accumulates everything the LM step needs over the rows >= n of the rotated
+//      system:  ||r||^2 = sum y~_i^2,  u_e = D~_e . y~,  M_ef = D~_e . D~_f   and the saved top rows give
 //      c = R1^-1 y~[0:n];  then  g_k = -sum_{e in k} c_j(e) u_e,  H_kl = sum M_ef c_j(e) c_j(f)
 //      (the S = 1 case of the formulas in stream_kernel.cuh; no explicit Q or E is formed),
-//   4. thread 0 advances the lmder state machine (lm_step.cuh) in shared memory.
+//   4. lane 0 of a warp advances the lmder state machine (lm_step.cuh) in shared memory.
+// n + 1 block reductions per evaluation (warp level: recursive halving, ~K instead of 5 K shuffles
+// for K values; the reflector scalars are formed once, by warp 0, between the two barriers).
 // Bound: fp64 ALU / exp and block-reduction latency, not HBM (32 KB of y per fit against ~15
 // evaluations of ~0.5 MFLOP each).
 #pragma once
+
+#include <type_traits>
+#include <utility>
 
 #include "device_common.cuh"
 #include "lm_step.cuh"
@@ -28,32 +36,71 @@
 
 namespace vp {
 
-// Sum K per-thread values over the CTA; every thread gets the totals. Two-level: per-warp shuffle
-// fold -> shared, warp 0 folds the NW per-warp partials (one lane per value), everybody reads the K
-// totals back (with 16 warps and K ~ 10 the one-level version makes every thread read NW*K values).
-// buf: NW*K + K doubles; two __syncthreads; buf must not be reused by the next call.
-template <int K, int NW>
-__device__ __forceinline__ void block_sum_two_level(double (&v)[K], double *buf)
+__host__ __device__ constexpr int pow2_ceil(int k) { int p = 1; while (p < k) p <<= 1; return p; }
+__host__ __device__ constexpr int log2_int(int k) { int l = 0; while ((1 << l) < k) ++l; return l; }
+
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, Is...>)
 {
-    static_assert(K <= 32, "one lane of warp 0 per value");
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+// f(integral_constant<int, 0>) ... f(integral_constant<int, N - 1>): a loop whose index is a constant expression
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    static_for_impl(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
+}
+
+// Warp-level sum of KP (a power of two <= 32) values per lane by recursive halving: at the level with lane
+// offset o a lane keeps one half of its values and hands the other half to its partner. Afterwards every lane
+// holds the warp total of value index (lane >> (5 - log2 KP)). KP - 1 + (5 - log2 KP) 64-bit shuffles instead
+// of 5 KP.
+template <int KP>
+__device__ __forceinline__ double warp_sum_scatter(double (&v)[KP])
+{
+    static_assert(KP >= 1 && KP <= 32 && (KP & (KP - 1)) == 0, "power of two");
+    const int lane = threadIdx.x & 31;
+    int o = 16;
+#pragma unroll
+    for (int h = KP / 2; h >= 1; h >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const double keep = up ? v[i + h] : v[i];
+            const double send = up ? v[i] : v[i + h];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    double t = v[0];
+#pragma unroll
+    for (int oo = 16 / KP; oo > 0; oo >>= 1) t += __shfl_xor_sync(0xffffffffu, t, oo);
+    return t;
+}
+
+// First half of a block sum of K values: per-warp partials to buf[warp * KP + k] and ONE barrier, which also
+// ORs `flags` over the CTA (the return value). Second half: warp 0, lane k < K, adds the NW partials.
+template <int K>
+__device__ __forceinline__ int block_sum_begin(const double *s, double *buf, int flags)
+{
+    constexpr int KP = pow2_ceil(K), SH = 5 - log2_int(KP);
+    double v[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) v[k] = k < K ? s[k] : 0.0;
+    const double t = warp_sum_scatter<KP>(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((lane & ((1 << SH) - 1)) == 0) buf[warp * KP + (lane >> SH)] = t;
+    return __syncthreads_or(flags);
+}
+template <int K, int NW>
+__device__ __forceinline__ double block_sum_total(const double *buf, int lane)
+{
+    constexpr int KP = pow2_ceil(K);
+    double t = 0.0;
+    if (lane < KP) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        double t = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) buf[warp * K + k] = t;
+        for (int w = 0; w < NW; ++w) t += buf[w * KP + lane];
     }
-    __syncthreads();
-    if (warp == 0 && lane < K) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) t += buf[w * K + lane];
-        buf[NW * K + lane] = t;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = buf[NW * K + k];
+    return t;
 }
 
 struct BatchArgs {
@@ -72,7 +119,6 @@ struct BatchArgs {
     int *term_out;        // P: Termination
     int *nfev_out;        // P
     unsigned long long *next; // work counter (zeroed by the host)
-    int mpad;             // rows of the shared-memory working matrix (>= m, multiple of 2)
 };
 
 // What one evaluation leaves behind for the LM phase (per problem slot, shared memory).
@@ -84,32 +130,47 @@ struct BatchTail {
     int dropped, bad;
 };
 
+// The per-function part of the model descriptor, in shared memory (run-time indexing of kernel parameters would
+// put the whole descriptor on the stack).
+struct BatchModelS {
+    int kind[VP_MAX_N], npar[VP_MAX_N], p0[VP_MAX_N], p1[VP_MAX_N];
+    int e_basis[VP_MAX_P];
+    double scale[VP_MAX_N];
+};
+
 // G problems are in flight per CTA ("slots"). The serial LM step of a problem costs about as much as
 // its evaluation (ncu: 47 % of all samples were the other 511 threads waiting for thread 0), so the
 // CTA evaluates its G problems one after the other with all threads and then runs the G LM steps
 // CONCURRENTLY, each on lane 0 of a different warp: the LM latency is paid once per G evaluations.
 // y_p is re-read from global memory for every evaluation (first touch from HBM, then L2): keeping
 // G columns in registers is not possible at 128 registers per thread.
+// Working matrix: NPV columns of MP = RPT * THREADS doubles (dynamic shared memory); the rows >= m are zero.
 template <int N, int P, int RPT, int THREADS, int G = 4>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_fit_kernel(const BatchArgs a)
 {
     constexpr int NPV = N + P;
     constexpr int NW = THREADS / 32;
+    constexpr int MP = RPT * THREADS;
     constexpr int NTAIL = 1 + P + P * (P + 1) / 2; // ||r||^2, u_e, M_ef (upper)
     constexpr int KMAX = (NTAIL > NPV + 1) ? NTAIL : NPV + 1;
+    constexpr int HUGE_HI = 0x5ff00000; // high word of 2^512 = 1.34e154: an entry this large overflows the column norm (cf. RANK_HUGE_ENTRY)
     static_assert(G <= NW, "one warp per slot in the LM phase");
-    extern __shared__ __align__(16) double colm[]; // NPV columns of mpad doubles
-    __shared__ double red[2][NW * KMAX + KMAX];
+    static_assert(KMAX <= 32, "one lane of warp 0 per reduced value");
+    extern __shared__ __align__(16) double colm[]; // NPV columns of MP doubles
+    __shared__ double red[NW * pow2_ceil(KMAX)];   // per-warp partial sums of the running block reduction
+    __shared__ double bc[NPV + 2];                 // reflector scalars from warp 0: v_JJ, tau_k, tau_y
+    __shared__ double rowpre[NPV + 1];             // row J of the working system before reflector J is applied
     __shared__ double alpha_s[VP_MAX_Q];
+    __shared__ BatchModelS ms;
     __shared__ LmState st_s[G];
     __shared__ BatchTail<N, P, KMAX> tail_s[G];
     __shared__ double coef_acc[G][N];
     __shared__ long long prob_s[G]; // problem in the slot, -1 = empty
     __shared__ int exhausted_s, nactive_s;
 
-    const int tid = threadIdx.x;
-    const int m = a.md.m, mpad = a.mpad, q = a.md.q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = a.md.m, q = a.md.q;
 
     // the thread's rows of x and w (shared by all problems)
     double xi[RPT], wi[RPT];
@@ -121,7 +182,16 @@ batch_fit_kernel(const BatchArgs a)
         wi[r] = in ? (a.w ? a.w[i] : 1.0) : 0.0;
     }
     if (tid < G) prob_s[tid] = -1;
-    if (tid == 0) exhausted_s = 0;
+    if (tid == 0) {
+        exhausted_s = 0;
+#pragma unroll
+        for (int j = 0; j < VP_MAX_N; ++j) {
+            ms.kind[j] = a.md.kind[j]; ms.npar[j] = a.md.npar[j]; ms.p0[j] = a.md.pidx[j][0]; ms.p1[j] = a.md.pidx[j][1];
+            ms.scale[j] = a.md.scale[j];
+        }
+#pragma unroll
+        for (int e = 0; e < VP_MAX_P; ++e) ms.e_basis[e] = a.md.e_basis[e];
+    }
     __syncthreads();
 
     for (;;) {
@@ -163,150 +233,186 @@ batch_fit_kernel(const BatchArgs a)
             }
             __syncthreads();
 
-            // 1. Phi_w, D into the working matrix (rolled over basis functions, rows unrolled)
-            int bad = 0;
+            // 1. Phi_w, D into the working matrix (rolled over basis functions, rows unrolled). The rows
+            //    r < RPT / 2 are always inside the problem (the host picks the smallest RPT covering m); the others
+            //    may be padding, which is stored as zero whatever the basis function returns at x = 0.
+            int bad_local = 0;
             {
                 int e = 0;
 #pragma unroll 1
                 for (int j = 0; j < N; ++j) {
-                    const int kind = a.md.kind[j], np = a.md.npar[j];
-                    const double a0 = np > 0 ? alpha_s[a.md.pidx[j][0]] : 0.0;
-                    const double a1 = np > 1 ? alpha_s[a.md.pidx[j][1]] : 0.0;
-                    const double scale = a.md.scale[j];
-                    const double inv0 = (kind == VP_BASIS_EXP_DECAY) ? 1.0 / a0 : 0.0;
+                    const int kind = ms.kind[j], np = ms.npar[j];
+                    const double a0 = np > 0 ? alpha_s[ms.p0[j]] : 0.0;
+                    const double a1 = np > 1 ? alpha_s[ms.p1[j]] : 0.0;
+                    double *cv = colm + (size_t)j * MP + tid, *ca = colm + (size_t)(N + e) * MP + tid, *cb = ca + MP;
+                    int mx = 0; // max over the thread's rows of the high word of |Phi_w[i][j]| (NaN / Inf are the largest)
+                    if (kind == VP_BASIS_EXP_DECAY) {
+                        const double inv0 = 1.0 / a0; // one division per basis function, see basis_eval_all
 #pragma unroll
-                    for (int r = 0; r < RPT; ++r) {
-                        const int i = tid + r * THREADS;
-                        double v, da = 0.0, db = 0.0;
-                        if (kind == VP_BASIS_EXP_DECAY) {
-                            const double t = xi[r] * inv0, ex = exp(-t); // one division per basis function, see basis_eval_all
-                            v = ex; da = ex * t * inv0;
-                        } else if (kind == VP_BASIS_EXP_RATE_COS) {
-                            const double ex = exp(-a0 * xi[r]);
-                            double sn, cs;
-                            sincos(a1 * xi[r], &sn, &cs);
-                            v = ex * cs; da = -xi[r] * (ex * cs); db = -xi[r] * ex * sn;
-                        } else if (kind == VP_BASIS_SIN_PHASE) {
-                            double sn, cs;
-                            sincos(a0 * xi[r] + a1, &sn, &cs);
-                            v = sn; da = xi[r] * cs; db = cs;
-                        } else {
-                            v = kind == VP_BASIS_CONSTANT ? 1.0 : (kind == VP_BASIS_LINEAR_X ? scale * xi[r] : nan(""));
+                        for (int r = 0; r < RPT; ++r) {
+                            const double t = xi[r] * inv0, ex = vp_exp(-t);
+                            double pv = wi[r] * ex, pa = wi[r] * (ex * t * inv0);
+                            if (RPT == 1 || r >= RPT / 2) {
+                                const bool in = tid + r * THREADS < m;
+                                pv = in ? pv : 0.0; pa = in ? pa : 0.0;
+                            }
+                            mx = max(mx, __double2hiint(pv) & 0x7fffffff);
+                            cv[r * THREADS] = pv;
+                            ca[r * THREADS] = pa;
                         }
-                        if (i < m) {
-                            const double pv = wi[r] * v, pa = wi[r] * da, pb = wi[r] * db;
-                            bad |= (!isfinite(pv) ? 1 : 0) | (fabs(pv) > RANK_HUGE_ENTRY ? (2 << j) : 0); // flag word of rank_policy.cuh
-                            colm[(size_t)j * mpad + i] = pv;
-                            if (np > 0) colm[(size_t)(N + e) * mpad + i] = pa;
-                            if (np > 1) colm[(size_t)(N + e + 1) * mpad + i] = pb;
+                    } else {
+                        const double scale = ms.scale[j];
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) {
+                            double v, da = 0.0, db = 0.0;
+                            if (kind == VP_BASIS_EXP_RATE_COS) {
+                                const double ex = exp(-a0 * xi[r]);
+                                double sn, cs;
+                                sincos(a1 * xi[r], &sn, &cs);
+                                v = ex * cs; da = -xi[r] * (ex * cs); db = -xi[r] * ex * sn;
+                            } else if (kind == VP_BASIS_SIN_PHASE) {
+                                double sn, cs;
+                                sincos(a0 * xi[r] + a1, &sn, &cs);
+                                v = sn; da = xi[r] * cs; db = cs;
+                            } else {
+                                v = kind == VP_BASIS_CONSTANT ? 1.0 : (kind == VP_BASIS_LINEAR_X ? scale * xi[r] : nan(""));
+                            }
+                            const bool in = tid + r * THREADS < m;
+                            const double pv = in ? wi[r] * v : 0.0;
+                            mx = max(mx, __double2hiint(pv) & 0x7fffffff);
+                            cv[r * THREADS] = pv;
+                            if (np > 0) ca[r * THREADS] = in ? wi[r] * da : 0.0;
+                            if (np > 1) cb[r * THREADS] = in ? wi[r] * db : 0.0;
                         }
                     }
+                    bad_local |= (mx >= 0x7ff00000 ? 1 : 0) | (mx >= HUGE_HI ? (2 << j) : 0); // flag word of rank_policy.cuh
                     e += np;
                 }
             }
-            bad = block_or_flags(bad, 1 + N);
-            if (bad >> 1) { // overflowing basis columns: zero them and their derivative columns
-                for (int idx = tid; idx < m * NPV; idx += THREADS) {
-                    const int c = idx / m, i = idx - c * m;
-                    const int j = c < N ? c : a.md.e_basis[c - N];
-                    if ((bad >> (1 + j)) & 1) colm[(size_t)c * mpad + i] = 0.0;
+
+            // 2. sweep 0: sigma_0 and the dots of column 0 with every column and y. The barrier of the reduction
+            //    also ORs the flag words; overflowing basis columns (rare) are zeroed together with their derivative
+            //    columns -- every thread in its own rows -- and the sweep is repeated.
+            double s[KMAX];
+            int bad = 0;
+            {
+                int flags = bad_local;
+                bool redo;
+                do {
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) s[k] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        const double *rowp = colm + tid + r * THREADS;
+                        const double aj = rowp[0];
+#pragma unroll
+                        for (int k = 0; k < NPV; ++k) s[k] = fma(aj, rowp[(size_t)k * MP], s[k]);
+                        s[NPV] = fma(aj, yt[r], s[NPV]);
+                    }
+                    if (tid == 0) { // row 0 before its reflector is applied (thread 0 owns it, r = 0)
+#pragma unroll
+                        for (int k = 0; k < NPV; ++k) rowpre[k] = colm[(size_t)k * MP];
+                        rowpre[NPV] = yt[0];
+                    }
+                    redo = false;
+                    if (block_sum_begin<NPV + 1>(s, red, flags)) {
+                        bad = block_or_flags(bad_local, 1 + N);
+                        flags = 0;
+                        if (bad >> 1) {
+#pragma unroll
+                            for (int c = 0; c < NPV; ++c) {
+                                const int jb = c < N ? c : ms.e_basis[c - N];
+                                if ((bad >> (1 + jb)) & 1) {
+#pragma unroll
+                                    for (int r = 0; r < RPT; ++r) colm[(size_t)c * MP + tid + r * THREADS] = 0.0;
+                                }
+                            }
+                            redo = true;
+                        }
+                        bad &= 1;
+                    }
+                } while (redo);
+            }
+
+            // 3. Householder steps. Iteration J: warp 0 finishes the pending reduction (dots of column J over the rows
+            //    >= J) and forms the reflector; everybody applies it in one sweep that also accumulates what comes next.
+            int dropped = 0;
+            static_for<N>([&](auto Jc) {
+                constexpr int J = decltype(Jc)::value;
+                constexpr int K = NPV - J + 1; // sigma_J, dots with the NPV - J - 1 columns to the right, dot with y
+                if (warp == 0) {
+                    const double tot = block_sum_total<K, NW>(red, lane);
+                    const double sigma = __shfl_sync(0xffffffffu, tot, 0);
+                    const double ajj = rowpre[J];
+                    const double nrm = sqrt(sigma);
+                    const bool keep = isfinite(nrm) && nrm > 0.0; // near-dependence: rank policy on R1 in the LM phase
+                    const double al = (ajj >= 0.0) ? -nrm : nrm;
+                    const double vnorm2 = 2.0 * (sigma - ajj * al);
+                    const double bt = (keep && vnorm2 > 0.0) ? 2.0 / vnorm2 : 0.0;
+                    if (!keep) dropped |= 1 << J;
+                    if (lane >= 1 && lane < K) bc[lane] = bt * (tot - al * rowpre[J + lane]); // tau_k; lane K - 1: tau_y
+                    if (lane == 0) { bc[0] = ajj - al; tl.rdiag[J] = keep ? al : 0.0; }
                 }
                 __syncthreads();
-            }
-            bad &= 1;
-
-            // 2. Householder steps on [Phi_w | D | y] (y in registers)
-            int dropped = 0;
+                const double vjj = bc[0];
+                double tau[K];
 #pragma unroll
-            for (int J = 0; J < N; ++J) {
-                const int K = NPV - J + 1; // sigma, dots with the columns to the right, dot with y
-                double s[KMAX];
+                for (int k = 1; k < K; ++k) tau[k] = bc[k];
+                const double tau_y = tau[K - 1];
 #pragma unroll
                 for (int k = 0; k < KMAX; ++k) s[k] = 0.0;
 #pragma unroll
                 for (int r = 0; r < RPT; ++r) {
-                    const int i = tid + r * THREADS;
-                    if (i >= J && i < m) {
-                        const double aj = colm[(size_t)J * mpad + i];
+                    double *rowp = colm + tid + r * THREADS;
+                    double vi = rowp[(size_t)J * MP]; // zero in the finished rows < J
+                    if (r == 0) vi = (tid == J) ? vjj : vi;
+                    double row[NPV]; // the updated entries of the columns > J of this row
 #pragma unroll
-                        for (int k = 0; k < NPV - J; ++k) s[k] = fma(aj, colm[(size_t)(J + k) * mpad + i], s[k]);
-                        s[NPV - J] = fma(aj, yt[r], s[NPV - J]);
-                    }
-                }
-                if (tid == J) { // row J is owned by thread J (r = 0): publish it
+                    for (int k = J + 1; k < NPV; ++k) row[k] = fma(-tau[k - J], vi, rowp[(size_t)k * MP]);
+                    double yv = fma(-tau_y, vi, yt[r]);
+                    if (r == 0) {
+                        if (tid == J) { // the final row J: R[J][k > J], (Q^T D)[J][:], (Q^T y)[J]; then out of the system
 #pragma unroll
-                    for (int k = 0; k < NPV; ++k) tl.top[J][k] = colm[(size_t)k * mpad + J];
-                    tl.top[J][NPV] = yt[0];
-                }
-                (void)K;
-                block_sum_two_level<KMAX, NW>(s, red[J & 1]);
-                const double sigma = s[0];
-                const double ajj = tl.top[J][J];
-                const double nrm = sqrt(sigma);
-                const bool keep = isfinite(nrm) && nrm > 0.0; // near-dependence: rank policy on R1 in the LM phase
-                const double al = (ajj >= 0.0) ? -nrm : nrm;
-                const double vnorm2 = 2.0 * (sigma - ajj * al);
-                const double bt = (keep && vnorm2 > 0.0) ? 2.0 / vnorm2 : 0.0;
-                if (tid == 0) tl.rdiag[J] = keep ? al : 0.0;
-                if (!keep) dropped |= 1 << J;
-                const double vjj = ajj - al;
-                double tau[NPV + 1];
-#pragma unroll
-                for (int k = 1; k < NPV - J; ++k) tau[k] = bt * (s[k] - al * tl.top[J][J + k]);
-                const double tau_y = bt * (s[NPV - J] - al * tl.top[J][NPV]);
-#pragma unroll
-                for (int r = 0; r < RPT; ++r) {
-                    const int i = tid + r * THREADS;
-                    if (i >= J && i < m) {
-                        const double vi = (i > J) ? colm[(size_t)J * mpad + i] : vjj;
-#pragma unroll
-                        for (int k = 1; k < NPV - J; ++k)
-                            colm[(size_t)(J + k) * mpad + i] = fma(-tau[k], vi, colm[(size_t)(J + k) * mpad + i]);
-                        yt[r] = fma(-tau_y, vi, yt[r]);
-                    }
-                }
-                __syncthreads(); // everyone has read top[J]; its owner rewrites it with the final row
-                if (tid == J) {
-#pragma unroll
-                    for (int k = J + 1; k < NPV; ++k) tl.top[J][k] = colm[(size_t)k * mpad + J]; // R[J][k], (Q^T D)[J][:]
-                    tl.top[J][NPV] = yt[0];                                                        // (Q^T y)[J]
-                }
-            }
-
-            // 3. tail reduction: rows >= n (the untruncated projector; truncated directions are added by the rank policy)
-            {
-                double tv[KMAX];
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) tv[k] = 0.0;
-#pragma unroll
-                for (int r = 0; r < RPT; ++r) {
-                    const int i = tid + r * THREADS;
-                    const bool tail = (i < m) && (i >= N);
-                    if (tail) {
-                        const double yv = yt[r];
-                        tv[0] = fma(yv, yv, tv[0]);
-                        double de[P > 0 ? P : 1];
-#pragma unroll
-                        for (int e = 0; e < P; ++e) {
-                            de[e] = colm[(size_t)(N + e) * mpad + i];
-                            tv[1 + e] = fma(de[e], yv, tv[1 + e]);
+                            for (int k = J + 1; k < NPV; ++k) { tl.top[J][k] = row[k]; row[k] = 0.0; }
+                            tl.top[J][NPV] = yv;
+                            yv = 0.0;
                         }
+                    }
+                    yt[r] = yv;
+                    if constexpr (J + 1 < N) {
+#pragma unroll
+                        for (int k = J + 1; k < NPV; ++k) rowp[(size_t)k * MP] = row[k];
+                        const double aj = row[J + 1]; // dots of the updated column J + 1 for the next reflector
+#pragma unroll
+                        for (int k = 0; k < NPV - J - 1; ++k) s[k] = fma(aj, row[J + 1 + k], s[k]);
+                        s[NPV - J - 1] = fma(aj, yv, s[NPV - J - 1]);
+                        if (r == 0) {
+                            if (tid == J + 1) { // row J + 1 before ITS reflector
+#pragma unroll
+                                for (int k = J + 1; k < NPV; ++k) rowpre[k] = row[k];
+                                rowpre[NPV] = yv;
+                            }
+                        }
+                    } else { // tail sums over the rows >= n (the untruncated projector); the finished rows are zero
+                        s[0] = fma(yv, yv, s[0]);
+#pragma unroll
+                        for (int e = 0; e < P; ++e) s[1 + e] = fma(row[N + e], yv, s[1 + e]);
                         int t = 1 + P;
 #pragma unroll
                         for (int e = 0; e < P; ++e)
 #pragma unroll
-                            for (int f2 = e; f2 < P; ++f2) { tv[t] = fma(de[e], de[f2], tv[t]); ++t; }
+                            for (int f2 = e; f2 < P; ++f2) { s[t] = fma(row[N + e], row[N + f2], s[t]); ++t; }
                     }
                 }
-                block_sum_two_level<KMAX, NW>(tv, red[N & 1]);
-                if (tid == 0) {
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) tl.tv[k] = tv[k];
-                    tl.dropped = dropped;
-                    tl.bad = bad;
-                }
+                if constexpr (J + 1 < N) block_sum_begin<K - 1>(s, red, 0);
+                else block_sum_begin<NTAIL>(s, red, 0);
+            });
+            if (warp == 0) {
+                const double tot = block_sum_total<NTAIL, NW>(red, lane);
+                if (lane < NTAIL) tl.tv[lane] = tot;
+                if (lane == 0) { tl.dropped = dropped; tl.bad = bad; }
             }
-            __syncthreads(); // the working matrix and the reduction buffers are free for the next slot
+            __syncthreads(); // the tail is complete; the reduction buffers are free for the next slot
         }
 
         // ---- LM phase: lane 0 of warp g advances slot g; the G steps run concurrently ----------------

@@ -53,7 +53,7 @@ static int batch_create_common(vp_ctx *ctx, vp_model *model, int64_t P, const vo
     }
     if (pick < 0)
         return vp_fail(ctx, VP_ERR_MODEL_TOO_LARGE, "vp_batch: no independent-batch kernel instantiated for this model shape / m > 4096");
-    const int mpad = (md.m + 1) / 2 * 2;
+    const int mpad = KT.batch[pick].rpt * KT.batch[pick].threads; // rows of the shared-memory working matrix (rows >= m are zero)
     const size_t smem = sizeof(double) * (size_t)(md.n + md.p) * mpad;
     cudaFuncAttributes fa{};
     VP_CUDA(ctx, cudaFuncGetAttributes(&fa, KT.batch[pick].fn));
@@ -134,7 +134,7 @@ static int batch_fit_launch(vp_batch *b, const vp_lm_options *opt)
     if (md.q > 0)
         VP_CUDA(ctx, cudaMemcpyAsync(b->alpha0, b->alpha, sizeof(double) * (size_t)md.q * b->P, cudaMemcpyDeviceToDevice, ctx->stream));
     a.alpha0 = b->alpha0; a.alpha_out = b->alpha; a.C_out = b->C; a.obj_out = b->obj; a.term_out = b->term; a.nfev_out = b->nfev;
-    a.next = b->next; a.mpad = b->mpad;
+    a.next = b->next;
     VP_CUDA(ctx, cudaMemsetAsync(b->next, 0, sizeof(unsigned long long), ctx->stream));
     int occ = 0;
     VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads, b->smem));

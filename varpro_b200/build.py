@@ -48,13 +48,51 @@ def _units():
     return units
 
 
-def _stamp(src=None, flags=()):
-    """Hash of everything an object (src given) or the whole library (src None) depends on: every
-    header, the unit's own source (all sources for the library) and the flags."""
-    h = hashlib.sha256()
-    for d in sorted(_deps()):
-        if d.endswith(".cu") and src is not None and os.path.abspath(d) != os.path.abspath(src):
+def _includes(path, part=None, seen=None):
+    """Transitive closure of the local #include "..." of `path`. Only the `#if VP_INST_PART == k` ladder of
+    csrc/inst.cu is interpreted (with `part`); every other conditional is taken as true."""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    active = [True]  # stack for the VP_INST_PART ladder
+    taken = [True]
+    for line in open(path):
+        ls = line.strip()
+        mi = re.match(r"#\s*(if|elif)\s+VP_INST_PART\s*==\s*(\d+)", ls)
+        if mi and part is not None:
+            hit = int(mi.group(2)) == int(part)
+            if mi.group(1) == "if":
+                active.append(hit)
+                taken.append(hit)
+            else:
+                active[-1] = hit and not taken[-1]
+                taken[-1] = taken[-1] or hit
             continue
+        if part is not None and len(active) > 1 and re.match(r"#\s*else\b", ls):
+            active[-1] = not taken[-1]
+            continue
+        if part is not None and len(active) > 1 and re.match(r"#\s*endif\b", ls):
+            active.pop()
+            taken.pop()
+            continue
+        m = re.match(r'#\s*include\s+"([^"]+)"', ls)
+        if m and all(active):
+            _includes(os.path.join(os.path.dirname(path), m.group(1)), None, seen)
+    return seen
+
+
+def _stamp(src=None, flags=()):
+    """Hash of everything an object (src given: its source and the headers it includes) or the whole
+    library (src None: every source and header) depends on, plus the flags."""
+    h = hashlib.sha256()
+    if src is None:
+        deps = _deps()
+    else:
+        part = next((f.split("=")[1] for f in flags if f.startswith("-DVP_INST_PART=")), None)
+        deps = _includes(src, part)
+    for d in sorted(deps):
         h.update(os.path.basename(d).encode())
         h.update(open(d, "rb").read())
     h.update(" ".join(list(NVCC_FLAGS) + list(LINK_LIBS) + list(flags)).encode())

@@ -20,7 +20,7 @@
 //      system:  ||r||^2 = sum y~_i^2,  u_e = D~_e . y~,  M_ef = D~_e . D~_f   and the saved top rows give
 //      c = R1^-1 y~[0:n];  then  g_k = -sum_{e in k} c_j(e) u_e,  H_kl = sum M_ef c_j(e) c_j(f)
 //      (the S = 1 case of the formulas in stream_kernel.cuh; no explicit Q or E is formed),
-//   4. lane 0 of a warp advances the lmder state machine (lm_step.cuh) in shared memory.
+//   4. a lane of the LM warp advances the lmder state machine (lm_step.cuh) in shared memory.
 // n + 1 block reductions per evaluation (warp level: recursive halving, ~K instead of 5 K shuffles
 // for K values; the reflector scalars are formed once, by warp 0, between the two barriers).
 // Bound: fp64 ALU / exp and block-reduction latency, not HBM (32 KB of y per fit against ~15
@@ -51,6 +51,31 @@ __device__ __forceinline__ void static_for(F &&f)
     static_for_impl(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
 }
 
+// ---- named barriers for the compute warps (the LM warps of the CTA never join them) -----------------------
+__device__ __forceinline__ void bar_sync_n(const int id, const int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ int bar_or_n(const int id, const int count, const int pred)
+{
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %3, 0;\n\t"
+        "bar.red.or.pred q, %1, %2, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"(id), "r"(count), "r"(pred)
+        : "memory");
+    return r;
+}
+__device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
+__device__ __forceinline__ void st_flag(int *p, const int v)
+{
+    __threadfence_block();
+    *(volatile int *)p = v;
+}
+
 // Warp-level sum of KP (a power of two <= 32) values per lane by recursive halving: at the level with lane
 // offset o a lane keeps one half of its values and hands the other half to its partner. Afterwards every lane
 // holds the warp total of value index (lane >> (5 - log2 KP)). KP - 1 + (5 - log2 KP) 64-bit shuffles instead
@@ -77,9 +102,10 @@ __device__ __forceinline__ double warp_sum_scatter(double (&v)[KP])
     return t;
 }
 
-// First half of a block sum of K values: per-warp partials to buf[warp * KP + k] and ONE barrier, which also
+// First half of a block sum of K values over the NTHREADS compute threads (named barrier 1): per-warp partials
+// to buf[warp * KP + k] and ONE barrier, which also
 // ORs `flags` over the CTA (the return value). Second half: warp 0, lane k < K, adds the NW partials.
-template <int K>
+template <int K, int NTHREADS>
 __device__ __forceinline__ int block_sum_begin(const double *s, double *buf, int flags)
 {
     constexpr int KP = pow2_ceil(K), SH = 5 - log2_int(KP);
@@ -89,7 +115,7 @@ __device__ __forceinline__ int block_sum_begin(const double *s, double *buf, int
     const double t = warp_sum_scatter<KP>(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if ((lane & ((1 << SH) - 1)) == 0) buf[warp * KP + (lane >> SH)] = t;
-    return __syncthreads_or(flags);
+    return bar_or_n(1, NTHREADS, flags);
 }
 template <int K, int NW>
 __device__ __forceinline__ double block_sum_total(const double *buf, int lane)
@@ -119,6 +145,8 @@ struct BatchArgs {
     int *term_out;        // P: Termination
     int *nfev_out;        // P
     unsigned long long *next; // work counter (zeroed by the host)
+    ExpTable expc;            // vp_exp_table(): the exp coefficients as direct constant-bank operands
+    unsigned long long *dbg;  // optional per-CTA accumulators: [0] evaluation ns, [1] LM ns, [2] ns waiting for LM, [3] evaluations, [5] basis ns, [6] sweep 0 ns, [7] LM steps
 };
 
 // What one evaluation leaves behind for the LM phase (per problem slot, shared memory).
@@ -138,15 +166,21 @@ struct BatchModelS {
     double scale[VP_MAX_N];
 };
 
-// G problems are in flight per CTA ("slots"). The serial LM step of a problem costs about as much as
-// its evaluation (ncu: 47 % of all samples were the other 511 threads waiting for thread 0), so the
-// CTA evaluates its G problems one after the other with all threads and then runs the G LM steps
-// CONCURRENTLY, each on lane 0 of a different warp: the LM latency is paid once per G evaluations.
-// y_p is re-read from global memory for every evaluation (first touch from HBM, then L2): keeping
-// G columns in registers is not possible at 128 registers per thread.
+// G problems are in flight per CTA ("slots", two groups of G / 2) and the CTA is WARP-SPECIALISED: THREADS compute
+// threads evaluate the slots round-robin with all their lanes; ONE extra warp runs the lmder steps, lane l serving
+// slot l of the current group, the lanes in lockstep (SIMT: the warp pays for the slowest step, the others cost
+// nothing). The serial LM step of a q = 3 problem is ~3 500 dependent instructions = 30 us, against 11.7 us for an
+// evaluation at m = 4096; while the LM warp steps the slots of one group the compute warps evaluate the other
+// group, so the step latency disappears behind G / 2 evaluations. Hand-off through shared-memory sequence
+// numbers per group: ev_seq = rounds evaluated, lm_seq = rounds stepped (DEAD when the group has no problem left).
+// The compute warps only wait when a group's steps are slower than the other group's evaluations (small m) or in
+// the drain at the end of the batch. No CTA-wide barrier after the prologue: the compute warps synchronise on
+// named barrier 1, and the reduction buffers alternate with the evaluation parity so that warp 0 can finish the
+// tail of one evaluation while the other warps are already generating the next basis.
 // Working matrix: NPV columns of MP = RPT * THREADS doubles (dynamic shared memory); the rows >= m are zero.
-template <int N, int P, int RPT, int THREADS, int G = 4>
-__global__ void __launch_bounds__(THREADS, 1)
+// (The block has THREADS + 32 threads; registers are allocated in units of 4 warps, hence 96 per thread.)
+template <int N, int P, int RPT, int THREADS, int G = 16>
+__global__ void __launch_bounds__(THREADS + 32, 1)
 batch_fit_kernel(const BatchArgs a)
 {
     constexpr int NPV = N + P;
@@ -154,34 +188,29 @@ batch_fit_kernel(const BatchArgs a)
     constexpr int MP = RPT * THREADS;
     constexpr int NTAIL = 1 + P + P * (P + 1) / 2; // ||r||^2, u_e, M_ef (upper)
     constexpr int KMAX = (NTAIL > NPV + 1) ? NTAIL : NPV + 1;
+    constexpr int KRED = NW * pow2_ceil(KMAX);
     constexpr int HUGE_HI = 0x5ff00000; // high word of 2^512 = 1.34e154: an entry this large overflows the column norm (cf. RANK_HUGE_ENTRY)
-    static_assert(G <= NW, "one warp per slot in the LM phase");
+    constexpr int DEAD = 0x7fffffff;
+    constexpr int GH = G / 2; // slots per group
+    static_assert(G % 2 == 0 && GH <= 32, "one lane of the LM warp per slot of a group");
     static_assert(KMAX <= 32, "one lane of warp 0 per reduced value");
     extern __shared__ __align__(16) double colm[]; // NPV columns of MP doubles
-    __shared__ double red[NW * pow2_ceil(KMAX)];   // per-warp partial sums of the running block reduction
+    __shared__ double red2[2][KRED];               // per-warp partial sums of the running block reduction (by evaluation parity)
     __shared__ double bc[NPV + 2];                 // reflector scalars from warp 0: v_JJ, tau_k, tau_y
     __shared__ double rowpre[NPV + 1];             // row J of the working system before reflector J is applied
-    __shared__ double alpha_s[VP_MAX_Q];
     __shared__ BatchModelS ms;
     __shared__ LmState st_s[G];
     __shared__ BatchTail<N, P, KMAX> tail_s[G];
     __shared__ double coef_acc[G][N];
-    __shared__ long long prob_s[G]; // problem in the slot, -1 = empty
-    __shared__ int exhausted_s, nactive_s;
+    __shared__ long long prob_s[G]; // problem in the slot
+    __shared__ int ev_seq[2], lm_seq[2], live_s[G];
+    __shared__ int exhausted_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = a.md.m, q = a.md.q;
 
-    // the thread's rows of x and w (shared by all problems)
-    double xi[RPT], wi[RPT];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int i = tid + r * THREADS;
-        const bool in = i < m;
-        xi[r] = in ? a.x[i] : 0.0;
-        wi[r] = in ? (a.w ? a.w[i] : 1.0) : 0.0;
-    }
-    if (tid < G) prob_s[tid] = -1;
+    if (tid < G) { live_s[tid] = 0; prob_s[tid] = -1; }
+    if (tid < 2) { ev_seq[tid] = 0; lm_seq[tid] = 0; }
     if (tid == 0) {
         exhausted_s = 0;
 #pragma unroll
@@ -192,47 +221,193 @@ batch_fit_kernel(const BatchArgs a)
 #pragma unroll
         for (int e = 0; e < VP_MAX_P; ++e) ms.e_basis[e] = a.md.e_basis[e];
     }
-    __syncthreads();
+    __syncthreads(); // the only CTA-wide barrier
 
-    for (;;) {
-        // ---- refill empty slots from the global work counter -------------------------------------
-        if (tid == 0) {
-            int nact = 0;
-            for (int g = 0; g < G; ++g) {
-                if (prob_s[g] < 0 && !exhausted_s) {
-                    const long long pnew = (long long)atomicAdd(a.next, 1ull);
-                    if (pnew < a.P) {
-                        double x0[VP_MAX_Q];
-                        for (int k = 0; k < VP_MAX_Q; ++k) x0[k] = k < q ? a.alpha0[(size_t)pnew * q + k] : 0.0;
-                        lm_init(st_s[g], q, x0);
-                        prob_s[g] = pnew;
+    // =============================== the LM warp =======================================================
+    if (tid >= THREADS) {
+        unsigned long long t_lm = 0, n_lm = 0; // (dbg, lane 0)
+        const bool mine = lane < GH;
+        // take a problem from the global counter into slot g, or mark the slot dead
+        auto refill = [&](const int g) {
+            long long pnew = -1;
+            if (!ld_flag(&exhausted_s)) {
+                pnew = (long long)atomicAdd(a.next, 1ull);
+                if (pnew >= a.P) { pnew = -1; *(volatile int *)&exhausted_s = 1; }
+            }
+            if (pnew >= 0) {
+                double x0[VP_MAX_Q];
+                for (int k = 0; k < VP_MAX_Q; ++k) x0[k] = k < q ? a.alpha0[(size_t)pnew * q + k] : 0.0;
+                lm_init(st_s[g], q, x0);
+                prob_s[g] = pnew;
+            }
+            live_s[g] = pnew >= 0;
+        };
+        unsigned alive[2];
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {
+            if (mine) refill(grp * GH + lane);
+            alive[grp] = __ballot_sync(0xffffffffu, mine && live_s[grp * GH + lane]);
+            if (lane == 0) st_flag(&lm_seq[grp], alive[grp] ? 1 : DEAD);
+        }
+        for (int round = 1; alive[0] | alive[1]; ++round) {
+#pragma unroll 1
+            for (int grp = 0; grp < 2; ++grp) {
+                if (!alive[grp]) continue; // warp-uniform
+                if (lane == 0)
+                    while (ld_flag(&ev_seq[grp]) < round) __nanosleep(200);
+                __syncwarp();
+                __threadfence_block();
+                unsigned long long t0 = 0;
+                if (a.dbg && lane == 0) t0 = global_timer_ns();
+                const int g = grp * GH + lane;
+                if (mine && live_s[g]) {
+                    const BatchTail<N, P, KMAX> &tl = tail_s[g];
+                    // inner solve c = R1^-1 (Q^T y) under the rank policy (rank_policy.cuh): triangular inverse, cheap
+                    // full-rank test, and -- rarely -- the SVD of R1 with the truncated directions moved into the residual
+                    double Rm[N * N], Ri[N * N], coef[N];
+#pragma unroll
+                    for (int c = 0; c < N; ++c)
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { Rm[c * N + i] = (i < c) ? tl.top[i][c] : ((i == c) ? tl.rdiag[c] : 0.0); Ri[c * N + i] = 0.0; }
+#pragma unroll
+                    for (int c = 0; c < N; ++c)
+#pragma unroll
+                        for (int i = N - 1; i >= 0; --i) {
+                            if (i > c) continue;
+                            double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                            for (int k = 0; k < N; ++k)
+                                if (k > i && k <= c) sacc -= Rm[k * N + i] * Ri[c * N + k];
+                            Ri[c * N + i] = sacc / Rm[i * N + i];
+                        }
+                    double rn2_extra = 0.0;
+                    if (rank_surely_full(N, Rm, N, Ri, N, a.svd_eps)) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int c = i; c < N; ++c) sacc += Ri[c * N + i] * tl.top[c][NPV];
+                            coef[i] = sacc;
+                        }
                     } else {
-                        exhausted_s = 1;
+                        SmallSvd sv;
+                        rank_policy_svd(N, Rm, N, a.svd_eps, &sv);
+                        double bb[N], b2 = 0.0, bb2 = 0.0;
+                        for (int c = 0; c < N; ++c) {
+                            double sacc = 0.0;
+                            for (int k = 0; k < N; ++k) sacc += sv.Urot[c * N + k] * tl.top[k][NPV];
+                            bb[c] = sacc;
+                            bb2 += sacc * sacc;
+                            b2 += tl.top[c][NPV] * tl.top[c][NPV];
+                        }
+                        for (int i = 0; i < N; ++i) {
+                            double sacc = 0.0;
+                            for (int c = 0; c < N; ++c) sacc += sv.RinvEff[c * N + i] * bb[c];
+                            coef[i] = sacc;
+                        }
+                        rn2_extra = fmax(b2 - bb2, 0.0); // the truncated components of Q^T y stay in the residual
+                    }
+                    LmEval ev;
+                    ev.rnorm2 = tl.tv[0] + rn2_extra;
+                    const int resid_ok = !tl.bad && isfinite(tl.tv[0] + rn2_extra);
+                    int finite = 1; // derivatives
+                    for (int k = 0; k < VP_LM_MAXQ; ++k) ev.g[k] = 0.0;
+                    for (int k = 0; k < VP_LM_MAXQ * VP_LM_MAXQ; ++k) ev.H[k] = 0.0;
+                    double Mm[P > 0 ? P : 1][P > 0 ? P : 1];
+                    {
+                        int t = 1 + P;
+#pragma unroll
+                        for (int e = 0; e < P; ++e)
+#pragma unroll
+                            for (int f2 = e; f2 < P; ++f2) { Mm[e][f2] = tl.tv[t]; Mm[f2][e] = tl.tv[t]; ++t; }
+                    }
+#pragma unroll
+                    for (int e = 0; e < P; ++e) {
+                        double ce = 0.0;
+#pragma unroll
+                        for (int r = 0; r < N; ++r) ce = (a.md.e_basis[e] == r) ? coef[r] : ce;
+                        const int ke = a.md.e_param[e];
+                        ev.g[ke] -= ce * tl.tv[1 + e];
+#pragma unroll
+                        for (int f2 = 0; f2 < P; ++f2) {
+                            double cf = 0.0;
+#pragma unroll
+                            for (int r = 0; r < N; ++r) cf = (a.md.e_basis[f2] == r) ? coef[r] : cf;
+                            ev.H[a.md.e_param[f2] * q + ke] += Mm[e][f2] * ce * cf;
+                        }
+                    }
+                    for (int k = 0; k < q; ++k) finite = finite && isfinite(ev.g[k]);
+                    for (int k = 0; k < q * q; ++k) finite = finite && isfinite(ev.H[k]);
+                    ev.finite = (resid_ok ? VP_EVAL_RESIDUAL_OK : 0) | (finite ? VP_EVAL_DERIVS_OK : 0);
+                    LmState &st = st_s[g];
+                    const bool more = lm_advance(st, a.cfg, ev);
+                    if (st.last_accepted) {
+#pragma unroll
+                        for (int r = 0; r < N; ++r) coef_acc[g][r] = coef[r];
+                    }
+                    if (!more) { // results of this problem; the slot takes the next problem (or dies)
+                        const long long prob = prob_s[g];
+                        for (int k = 0; k < q; ++k) a.alpha_out[(size_t)prob * q + k] = st.x[k];
+                        for (int r = 0; r < N; ++r) a.C_out[(size_t)prob * N + r] = coef_acc[g][r];
+                        a.obj_out[prob] = 0.5 * st.fnorm * st.fnorm;
+                        a.term_out[prob] = st.termination;
+                        a.nfev_out[prob] = st.nfev;
+                        refill(g);
                     }
                 }
-                nact += prob_s[g] >= 0;
+                __syncwarp();
+                alive[grp] = __ballot_sync(0xffffffffu, mine && live_s[g]);
+                if (lane == 0) {
+                    if (a.dbg) { t_lm += global_timer_ns() - t0; n_lm++; }
+                    st_flag(&lm_seq[grp], alive[grp] ? round + 1 : DEAD);
+                }
             }
-            nactive_s = nact;
         }
-        __syncthreads();
-        if (nactive_s == 0) break;
+        if (a.dbg && lane == 0) {
+            a.dbg[(size_t)blockIdx.x * 8 + 1] = t_lm;
+            a.dbg[(size_t)blockIdx.x * 8 + 7] = n_lm;
+        }
+        return;
+    }
 
-        // ---- evaluation phase: the active slots one after the other, all threads -----------------
+    // =============================== compute warps =====================================================
+    unsigned long long t_eval = 0, t_wait = 0, n_evals = 0, t_basis = 0, t_sw0 = 0, te = 0, tw = 0, tb = 0; // (thread 0, dbg only)
+    // the thread's rows of x and w (shared by all problems)
+    double xi[RPT], wi[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = tid + r * THREADS;
+        const bool in = i < m;
+        xi[r] = in ? a.x[i] : 0.0;
+        wi[r] = in ? (a.w ? a.w[i] : 1.0) : 0.0;
+    }
+    int parity = 0;
+    for (int round = 1;; ++round) {
+        int nlive = 0;
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
+            const int grp = g >= GH;
+            if (g == 0 || g == GH) { // the group's previous LM steps (or its first fill) must be complete
+                if (a.dbg && tid == 0) tw = global_timer_ns();
+                while (ld_flag(&lm_seq[grp]) < round) { }
+                __threadfence_block();
+                if (a.dbg && tid == 0) t_wait += global_timer_ns() - tw;
+            }
+            if (live_s[g]) { // uniform: written before lm_seq
+            ++nlive;
+            parity ^= 1;
+            double *const red = red2[parity];
             const long long prob = prob_s[g];
-            if (prob < 0) continue; // uniform
             BatchTail<N, P, KMAX> &tl = tail_s[g];
-            if (tid < VP_MAX_Q) alpha_s[tid] = tid < q ? st_s[g].x_trial[tid] : 0.0;
+            if (a.dbg && tid == 0) te = global_timer_ns();
+            const double *alpha_s = st_s[g].x_trial;
             // y_p (weighted like builder.rs:307): issued first, consumed after the basis evaluation
             double yt[RPT];
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
                 const int i = tid + r * THREADS;
-                yt[r] = (i < m) ? wi[r] * __ldg(&a.Y[(size_t)prob * a.ld + i]) : 0.0;
+                yt[r] = (i < m) ? wi[r] * __ldcg(&a.Y[(size_t)prob * a.ld + i]) : 0.0;
             }
-            __syncthreads();
-
             // 1. Phi_w, D into the working matrix (rolled over basis functions, rows unrolled). The rows
             //    r < RPT / 2 are always inside the problem (the host picks the smallest RPT covering m); the others
             //    may be padding, which is stored as zero whatever the basis function returns at x = 0.
@@ -248,10 +423,15 @@ batch_fit_kernel(const BatchArgs a)
                     int mx = 0; // max over the thread's rows of the high word of |Phi_w[i][j]| (NaN / Inf are the largest)
                     if (kind == VP_BASIS_EXP_DECAY) {
                         const double inv0 = 1.0 / a0; // one division per basis function, see basis_eval_all
+                        double done[RPT]; // (scheduling only: row r + 4 starts after row r is finished -- 4 exp chains in flight
+                                          //  per thread are enough and 8 do not fit in 96 registers)
 #pragma unroll
                         for (int r = 0; r < RPT; ++r) {
-                            const double t = xi[r] * inv0, ex = vp_exp(-t);
+                            double xr = xi[r];
+                            if (r >= 4) asm volatile("" : "+d"(xr) : "d"(done[r - 4]));
+                            const double t = xr * inv0, ex = vp_exp_with(-t, a.expc.c);
                             double pv = wi[r] * ex, pa = wi[r] * (ex * t * inv0);
+                            done[r] = pa;
                             if (RPT == 1 || r >= RPT / 2) {
                                 const bool in = tid + r * THREADS < m;
                                 pv = in ? pv : 0.0; pa = in ? pa : 0.0;
@@ -266,7 +446,7 @@ batch_fit_kernel(const BatchArgs a)
                         for (int r = 0; r < RPT; ++r) {
                             double v, da = 0.0, db = 0.0;
                             if (kind == VP_BASIS_EXP_RATE_COS) {
-                                const double ex = exp(-a0 * xi[r]);
+                                const double ex = vp_exp(-a0 * xi[r]);
                                 double sn, cs;
                                 sincos(a1 * xi[r], &sn, &cs);
                                 v = ex * cs; da = -xi[r] * (ex * cs); db = -xi[r] * ex * sn;
@@ -290,6 +470,7 @@ batch_fit_kernel(const BatchArgs a)
                 }
             }
 
+            if (a.dbg && tid == 0) { tb = global_timer_ns(); t_basis += tb - te; }
             // 2. sweep 0: sigma_0 and the dots of column 0 with every column and y. The barrier of the reduction
             //    also ORs the flag words; overflowing basis columns (rare) are zeroed together with their derivative
             //    columns -- every thread in its own rows -- and the sweep is repeated.
@@ -315,8 +496,10 @@ batch_fit_kernel(const BatchArgs a)
                         rowpre[NPV] = yt[0];
                     }
                     redo = false;
-                    if (block_sum_begin<NPV + 1>(s, red, flags)) {
-                        bad = block_or_flags(bad_local, 1 + N);
+                    if (block_sum_begin<NPV + 1, THREADS>(s, red, flags)) {
+                        bad = 0; // (rare) the whole flag word, bit by bit
+                        for (int b = 0; b < 1 + N; ++b)
+                            if (bar_or_n(1, THREADS, (bad_local >> b) & 1)) bad |= 1 << b;
                         flags = 0;
                         if (bad >> 1) {
 #pragma unroll
@@ -334,6 +517,7 @@ batch_fit_kernel(const BatchArgs a)
                 } while (redo);
             }
 
+            if (a.dbg && tid == 0) t_sw0 += global_timer_ns() - tb;
             // 3. Householder steps. Iteration J: warp 0 finishes the pending reduction (dots of column J over the rows
             //    >= J) and forms the reflector; everybody applies it in one sweep that also accumulates what comes next.
             int dropped = 0;
@@ -353,7 +537,7 @@ batch_fit_kernel(const BatchArgs a)
                     if (lane >= 1 && lane < K) bc[lane] = bt * (tot - al * rowpre[J + lane]); // tau_k; lane K - 1: tau_y
                     if (lane == 0) { bc[0] = ajj - al; tl.rdiag[J] = keep ? al : 0.0; }
                 }
-                __syncthreads();
+                bar_sync_n(1, THREADS);
                 const double vjj = bc[0];
                 double tau[K];
 #pragma unroll
@@ -404,116 +588,28 @@ batch_fit_kernel(const BatchArgs a)
                             for (int f2 = e; f2 < P; ++f2) { s[t] = fma(row[N + e], row[N + f2], s[t]); ++t; }
                     }
                 }
-                if constexpr (J + 1 < N) block_sum_begin<K - 1>(s, red, 0);
-                else block_sum_begin<NTAIL>(s, red, 0);
+                if constexpr (J + 1 < N) block_sum_begin<K - 1, THREADS>(s, red, 0);
+                else block_sum_begin<NTAIL, THREADS>(s, red, 0);
             });
             if (warp == 0) {
                 const double tot = block_sum_total<NTAIL, NW>(red, lane);
                 if (lane < NTAIL) tl.tv[lane] = tot;
                 if (lane == 0) { tl.dropped = dropped; tl.bad = bad; }
             }
-            __syncthreads(); // the tail is complete; the reduction buffers are free for the next slot
-        }
-
-        // ---- LM phase: lane 0 of warp g advances slot g; the G steps run concurrently ----------------
-        if ((tid & 31) == 0 && (tid >> 5) < G && prob_s[tid >> 5] >= 0) {
-            const int g = tid >> 5;
-            const BatchTail<N, P, KMAX> &tl = tail_s[g];
-            // inner solve c = R1^-1 (Q^T y) under the rank policy (rank_policy.cuh): triangular inverse, cheap
-            // full-rank test, and -- rarely -- the SVD of R1 with the truncated directions moved into the residual
-            double Rm[N * N], Ri[N * N], coef[N];
-#pragma unroll
-            for (int c = 0; c < N; ++c)
-#pragma unroll
-                for (int i = 0; i < N; ++i) { Rm[c * N + i] = (i < c) ? tl.top[i][c] : ((i == c) ? tl.rdiag[c] : 0.0); Ri[c * N + i] = 0.0; }
-#pragma unroll
-            for (int c = 0; c < N; ++c)
-#pragma unroll
-                for (int i = N - 1; i >= 0; --i) {
-                    if (i > c) continue;
-                    double sacc = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int k = 0; k < N; ++k)
-                        if (k > i && k <= c) sacc -= Rm[k * N + i] * Ri[c * N + k];
-                    Ri[c * N + i] = sacc / Rm[i * N + i];
-                }
-            double rn2_extra = 0.0;
-            if (rank_surely_full(N, Rm, N, Ri, N, a.svd_eps)) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int c = i; c < N; ++c) sacc += Ri[c * N + i] * tl.top[c][NPV];
-                    coef[i] = sacc;
-                }
-            } else {
-                SmallSvd sv;
-                rank_policy_svd(N, Rm, N, a.svd_eps, &sv);
-                double bb[N], b2 = 0.0, bb2 = 0.0;
-                for (int c = 0; c < N; ++c) {
-                    double sacc = 0.0;
-                    for (int k = 0; k < N; ++k) sacc += sv.Urot[c * N + k] * tl.top[k][NPV];
-                    bb[c] = sacc;
-                    bb2 += sacc * sacc;
-                    b2 += tl.top[c][NPV] * tl.top[c][NPV];
-                }
-                for (int i = 0; i < N; ++i) {
-                    double sacc = 0.0;
-                    for (int c = 0; c < N; ++c) sacc += sv.RinvEff[c * N + i] * bb[c];
-                    coef[i] = sacc;
-                }
-                rn2_extra = fmax(b2 - bb2, 0.0); // the truncated components of Q^T y stay in the residual
-            }
-            LmEval ev;
-            ev.rnorm2 = tl.tv[0] + rn2_extra;
-            const int resid_ok = !tl.bad && isfinite(tl.tv[0] + rn2_extra);
-            int finite = 1; // derivatives
-            for (int k = 0; k < VP_LM_MAXQ; ++k) ev.g[k] = 0.0;
-            for (int k = 0; k < VP_LM_MAXQ * VP_LM_MAXQ; ++k) ev.H[k] = 0.0;
-            double Mm[P > 0 ? P : 1][P > 0 ? P : 1];
-            {
-                int t = 1 + P;
-#pragma unroll
-                for (int e = 0; e < P; ++e)
-#pragma unroll
-                    for (int f2 = e; f2 < P; ++f2) { Mm[e][f2] = tl.tv[t]; Mm[f2][e] = tl.tv[t]; ++t; }
-            }
-#pragma unroll
-            for (int e = 0; e < P; ++e) {
-                double ce = 0.0;
-#pragma unroll
-                for (int r = 0; r < N; ++r) ce = (a.md.e_basis[e] == r) ? coef[r] : ce;
-                const int ke = a.md.e_param[e];
-                ev.g[ke] -= ce * tl.tv[1 + e];
-#pragma unroll
-                for (int f2 = 0; f2 < P; ++f2) {
-                    double cf = 0.0;
-#pragma unroll
-                    for (int r = 0; r < N; ++r) cf = (a.md.e_basis[f2] == r) ? coef[r] : cf;
-                    ev.H[a.md.e_param[f2] * q + ke] += Mm[e][f2] * ce * cf;
-                }
-            }
-            for (int k = 0; k < q; ++k) finite = finite && isfinite(ev.g[k]);
-            for (int k = 0; k < q * q; ++k) finite = finite && isfinite(ev.H[k]);
-            ev.finite = (resid_ok ? VP_EVAL_RESIDUAL_OK : 0) | (finite ? VP_EVAL_DERIVS_OK : 0);
-            LmState &st = st_s[g];
-            const bool more = lm_advance(st, a.cfg, ev);
-            if (st.last_accepted) {
-#pragma unroll
-                for (int r = 0; r < N; ++r) coef_acc[g][r] = coef[r];
-            }
-            if (!more) { // results of this problem; the slot is refilled in the next round
-                const long long prob = prob_s[g];
-                for (int k = 0; k < q; ++k) a.alpha_out[(size_t)prob * q + k] = st.x[k];
-                for (int r = 0; r < N; ++r) a.C_out[(size_t)prob * N + r] = coef_acc[g][r];
-                a.obj_out[prob] = 0.5 * st.fnorm * st.fnorm;
-                a.term_out[prob] = st.termination;
-                a.nfev_out[prob] = st.nfev;
-                prob_s[g] = -1;
+            if (a.dbg && tid == 0) { t_eval += global_timer_ns() - te; ++n_evals; }
+            } // live slot
+            if ((g == GH - 1 || g == G - 1) && warp == 0) { // warp 0 completes every tail: hand the group to the LM warp
+                __syncwarp();
+                if (lane == 0) st_flag(&ev_seq[grp], round);
             }
         }
-        __syncthreads();
+        if (nlive == 0) break;
+    }
+    if (a.dbg && tid == 0) {
+        unsigned long long *d = a.dbg + (size_t)blockIdx.x * 8;
+        d[0] = t_eval; d[2] = t_wait; d[3] = n_evals; d[5] = t_basis; d[6] = t_sw0;
     }
 }
 
 } // namespace vp
+

@@ -42,30 +42,42 @@ __host__ __device__ inline int g_index(int n, int i, int j)
 // is an operand from the constant bank: the library version re-materialises its 13 constants with ~25 moves
 // per call once registers are tight (49 instructions per exp in batch_fit_kernel, 17 of them fp64; this
 // one is ~20). Arguments outside |a| < 700 (overflow, underflow to denormals, NaN) take the library path.
-static __constant__ double VP_EXP_C[14] = {
-    1.4426950408889634,      // 0: 1 / ln 2
-    6755399441055744.0,      // 1: 1.5 * 2^52 (round-to-nearest-integer shifter)
-    -0.6931471805599453,     // 2: -ln 2 (high)
-    -2.3190468138462996e-17, // 3: -ln 2 (low)
-    2.5100424157005067e-08,  // 4: P9 coefficients, highest degree first
-    2.7620138719733994e-07, 2.7557268378684192e-06, 2.480152119021773e-05, 0.00019841269863105968,
-    0.0013888888917281794, 0.008333333333330051, 0.04166666666662399, 0.16666666666666669,
-    0.5000000000000001};
-__device__ __forceinline__ double vp_exp(double a)
+#define VP_EXP_CONSTANTS                                                                              \
+    1.4426950408889634,          /* 0: 1 / ln 2 */                                                     \
+        6755399441055744.0,      /* 1: 1.5 * 2^52 (round-to-nearest-integer shifter) */                \
+        -0.6931471805599453,     /* 2: -ln 2 (high) */                                                 \
+        -2.3190468138462996e-17, /* 3: -ln 2 (low) */                                                  \
+        2.5100424157005067e-08,  /* 4: P9 coefficients, highest degree first */                       \
+        2.7620138719733994e-07, 2.7557268378684192e-06, 2.480152119021773e-05, 0.00019841269863105968, \
+        0.0013888888917281794, 0.008333333333330051, 0.04166666666662399, 0.16666666666666669,         \
+        0.5000000000000001
+static __constant__ double VP_EXP_C[14] = {VP_EXP_CONSTANTS};
+// The same table as a kernel parameter (constant bank 0): there every coefficient is a direct operand of its
+// DFMA, with no load at all (a __constant__ array lives in bank 3 and costs one LDC per coefficient and exp
+// once the registers are too few to keep the table resident). Filled by the host with vp_exp_table().
+struct ExpTable { double c[14]; };
+inline ExpTable vp_exp_table()
 {
-    const double kd = fma(a, VP_EXP_C[0], VP_EXP_C[1]);
-    const double kf = kd - VP_EXP_C[1];
-    double r = fma(kf, VP_EXP_C[2], a);
-    r = fma(kf, VP_EXP_C[3], r);
-    double p = VP_EXP_C[4];
+    const ExpTable t = {{VP_EXP_CONSTANTS}};
+    return t;
+}
+template <typename TAB>
+__device__ __forceinline__ double vp_exp_with(const double a, const TAB &C)
+{
+    const double kd = fma(a, C[0], C[1]);
+    const double kf = kd - C[1];
+    double r = fma(kf, C[2], a);
+    r = fma(kf, C[3], r);
+    double p = C[4];
 #pragma unroll
-    for (int i = 5; i < 14; ++i) p = fma(p, r, VP_EXP_C[i]);
+    for (int i = 5; i < 14; ++i) p = fma(p, r, C[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const double res = __hiloint2double(__double2hiint(p) + (__double2loint(kd) << 20), __double2loint(p));
     if (!(fabs(a) < 700.0)) return exp(a);
     return res;
 }
+__device__ __forceinline__ double vp_exp(const double a) { return vp_exp_with(a, VP_EXP_C); }
 
 // --- mbarrier + bulk async copy (TMA, SASS: UBLKCP / SYNCS) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

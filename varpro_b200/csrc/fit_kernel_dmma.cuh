@@ -255,13 +255,13 @@ __device__ __forceinline__ int panel_eval_staged(const ModelDesc &md, const doub
             const double inv0 = 1.0 / a0;
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
-                const double t = xi[r] * inv0, ex = exp(-t); // one division per basis function, see basis_eval_all
+                const double t = xi[r] * inv0, ex = vp_exp(-t); // one division per basis function, see basis_eval_all
                 v[r] = ex; da[r] = ex * t * inv0; db[r] = 0.0;
             }
         } else if (kind == VP_BASIS_EXP_RATE_COS) {
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
-                const double ex = exp(-a0 * xi[r]);
+                const double ex = vp_exp(-a0 * xi[r]);
                 double sn, cs;
                 sincos(a1 * xi[r], &sn, &cs);
                 v[r] = ex * cs; da[r] = -xi[r] * (ex * cs); db[r] = -xi[r] * ex * sn;

@@ -1,12 +1,21 @@
 // inst.cu -- one group of kernel instantiations; compiled once per entry of VP_KERNEL_GROUPS with
 //   -DVP_INST_TAG=<tag> -DVP_INST_T=<double|float> -DVP_INST_DT=<VP_F64|VP_F32> -DVP_INST_N=n -DVP_INST_P=p -DVP_INST_PART=<0|1|2>
+// Each part includes only the kernel header it instantiates (build.py follows these conditionals when it decides
+// which objects a header edit invalidates).
 #include "kernel_tables.h"
-#include "batch_fit_kernel.cuh"
-#include "fit_kernel_dmma.cuh"
-#include "fit_queue_kernel.cuh"
-#include "panel_kernel_hh.cuh"
+#if VP_INST_PART == 0
 #include "stream_kernel.cuh"
+#elif VP_INST_PART == 1
 #include "stream_kernel_dmma.cuh"
+#elif VP_INST_PART == 3
+#include "fit_kernel_dmma.cuh"
+#elif VP_INST_PART == 4
+#include "batch_fit_kernel.cuh"
+#elif VP_INST_PART == 5
+#include "fit_queue_kernel.cuh"
+#else
+#include "panel_kernel_hh.cuh"
+#endif
 
 using namespace vp;
 
@@ -49,8 +58,9 @@ static const QueueKernelEntry queue_tab[] = {VP_QK(32, 16, 0)};
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, queue_tab, (int)(sizeof(queue_tab) / sizeof(queue_tab[0]))};
 #elif VP_INST_PART == 4
 constexpr int BATCH_THREADS = 512;
-#define VP_BK(RPT, G) {N_, P_, RPT, BATCH_THREADS, G, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS, G>}
-static const BatchKernelEntry batch_tab[] = {VP_BK(1, 4), VP_BK(2, 4), VP_BK(4, 4), VP_BK(8, 4), VP_BK(8, 8)};
+#define VP_BK(RPT, G) {N_, P_, RPT, BATCH_THREADS, G, 1, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS, G>}
+// slots: two groups of G / 2; one group's LM steps (lockstep in the LM warp, ~40 us) must fit into the other group's evaluations
+static const BatchKernelEntry batch_tab[] = {VP_BK(1, 32), VP_BK(2, 32), VP_BK(4, 32), VP_BK(8, 16)};
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, batch_tab, (int)(sizeof(batch_tab) / sizeof(batch_tab[0]))};
 #else
 constexpr int PANEL_HH_THREADS = 512;

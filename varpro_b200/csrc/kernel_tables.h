@@ -26,8 +26,8 @@ struct QueueKernelEntry { // fit_queue_kernel: many fits on one persistent grid 
     int dtype, n, p, ksteps, nwarps, exact;
     const void *fn;
 };
-struct BatchKernelEntry { // batch_fit_kernel: one CTA fits `slots` independent problems at a time
-    int n, p, rpt, threads, slots;
+struct BatchKernelEntry { // batch_fit_kernel: `threads` compute threads + `lm_warps` LM warps; `slots` problems in flight per CTA
+    int n, p, rpt, threads, slots, lm_warps;
     const void *fn;
 };
 struct KernelGroup {

@@ -68,7 +68,7 @@ static __device__ __noinline__ BasisVals basis_eval_all(int kind, double x, doub
     else if (kind == VP_BASIS_EXP_RATE_COS) { earg = -a0 * x; targ = a1 * x; }
     else if (kind == VP_BASIS_SIN_PHASE) targ = a0 * x + a1;
     double e = 1.0, sn = 0.0, cs = 1.0;
-    if (kind == VP_BASIS_EXP_DECAY || kind == VP_BASIS_EXP_RATE_COS) e = exp(earg);
+    if (kind == VP_BASIS_EXP_DECAY || kind == VP_BASIS_EXP_RATE_COS) e = vp_exp(earg);
     if (kind == VP_BASIS_EXP_RATE_COS || kind == VP_BASIS_SIN_PHASE) sincos(targ, &sn, &cs);
     BasisVals r;
     switch (kind) {

@@ -135,15 +135,33 @@ static int batch_fit_launch(vp_batch *b, const vp_lm_options *opt)
         VP_CUDA(ctx, cudaMemcpyAsync(b->alpha0, b->alpha, sizeof(double) * (size_t)md.q * b->P, cudaMemcpyDeviceToDevice, ctx->stream));
     a.alpha0 = b->alpha0; a.alpha_out = b->alpha; a.C_out = b->C; a.obj_out = b->obj; a.term_out = b->term; a.nfev_out = b->nfev;
     a.next = b->next;
+    a.expc = vp_exp_table();
     VP_CUDA(ctx, cudaMemsetAsync(b->next, 0, sizeof(unsigned long long), ctx->stream));
     int occ = 0;
-    VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads, b->smem));
+    VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads + 32 * k.lm_warps, b->smem));
     if (occ < 1) return vp_fail(ctx, VP_ERR_MODEL_TOO_LARGE, "vp_batch: kernel does not fit on an SM");
     long long grid = (long long)ctx->sm_count * occ;
     if (grid > b->P) grid = b->P;
+    unsigned long long *ddbg = nullptr;
+    if (ctx->opt.batch_dbg && DEV_ALLOC(ctx, &ddbg, sizeof(unsigned long long) * 8 * (size_t)grid) == cudaSuccess)
+        cudaMemsetAsync(ddbg, 0, sizeof(unsigned long long) * 8 * (size_t)grid, ctx->stream);
+    a.dbg = ddbg;
     void *args[] = {(void *)&a};
-    VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3((unsigned)grid), dim3(k.threads), args, b->smem, ctx->stream));
+    VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3((unsigned)grid), dim3(k.threads + 32 * k.lm_warps), args, b->smem, ctx->stream));
     ctx->launches++;
+    if (ddbg) { // diagnostics: per-CTA phase accumulators on stderr
+        std::vector<unsigned long long> hd((size_t)grid * 8);
+        if (cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+            cudaMemcpy(hd.data(), ddbg, sizeof(unsigned long long) * hd.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            double ev = 0, lm = 0, wait = 0, evals = 0, basis = 0, sw0 = 0, nlm = 0;
+            for (long long c = 0; c < grid; ++c) {
+                ev += hd[c * 8]; lm += hd[c * 8 + 1]; wait += hd[c * 8 + 2]; evals += hd[c * 8 + 3]; basis += hd[c * 8 + 5]; sw0 += hd[c * 8 + 6]; nlm += hd[c * 8 + 7];
+            }
+            fprintf(stderr, "[vp batch dbg] CTAs %lld evaluations %.0f | per evaluation %.2f us (y + basis %.2f, sweep 0 + reduction %.2f) + %.2f us waiting for the LM warps | LM step %.2f us (on the LM warps, overlapped) | busy per CTA %.2f ms\n",
+                    grid, evals, 1e-3 * ev / evals, 1e-3 * basis / evals, 1e-3 * sw0 / evals, 1e-3 * wait / evals, 1e-3 * lm / (nlm > 0 ? nlm : 1), 1e-6 * (ev + wait) / grid);
+        }
+        DEV_FREE(ctx, ddbg);
+    }
     b->fitted = true;
     return VP_OK;
 }

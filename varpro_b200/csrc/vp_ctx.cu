@@ -151,6 +151,7 @@ static int parse_option(CtxOptions &o, const char *key, const char *value)
     if (k == "stream_occ") return as_int(o.stream_occ);
     if (k == "queue_items_per_cta") { as_int(o.queue_items_per_cta); if (o.queue_items_per_cta < 1) o.queue_items_per_cta = 1; return VP_OK; }
     if (k == "queue_dbg") return as_int(o.queue_dbg);
+    if (k == "batch_dbg") return as_int(o.batch_dbg);
     if (k == "queue_parts_per_item") return as_int(o.queue_parts_per_item);
     if (k == "trace") return as_int(o.trace);
     if (k == "dbg_fit") return as_int(o.dbg_fit);
@@ -167,7 +168,7 @@ static void options_from_env(CtxOptions &o)
     static const char *const map[][2] = {
         {"VP_FIT_MODE", "fit_mode"}, {"VP_EVAL_KERNEL", "eval_kernel"}, {"VP_STREAM_KERNEL", "stream_kernel"},
         {"VP_PANEL_GENERIC", "panel_generic"}, {"VP_STREAM_STAGES", "stream_stages"}, {"VP_STREAM_CT", "stream_ct"},
-        {"VP_STREAM_OCC", "stream_occ"}, {"VP_QUEUE_ITEMS_PER_CTA", "queue_items_per_cta"}, {"VP_QUEUE_DBG", "queue_dbg"}, {"VP_QUEUE_PARTS_PER_ITEM", "queue_parts_per_item"},
+        {"VP_STREAM_OCC", "stream_occ"}, {"VP_QUEUE_ITEMS_PER_CTA", "queue_items_per_cta"}, {"VP_QUEUE_DBG", "queue_dbg"}, {"VP_BATCH_DBG", "batch_dbg"}, {"VP_QUEUE_PARTS_PER_ITEM", "queue_parts_per_item"},
         {"VP_TRACE", "trace"}, {"VP_DBG_FIT", "dbg_fit"}, {"VP_BATCH_SLOTS", "batch_slots"}, {"VP_POOL_MB", "pool_mb"}, {"VP_MAX_CTAS", "max_ctas"},
         {"VP_FIT_WARPS", "fit_warps"}};
     for (const auto &m : map) {

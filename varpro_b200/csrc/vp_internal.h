@@ -76,6 +76,7 @@ struct CtxOptions {
     int stream_ct = 4, stream_occ = 2; // SIMT streaming kernel: preferred columns per tile, CTAs per SM
     int queue_items_per_cta = 2;      // work-queue kernel: items per CTA and evaluation round the item size aims at
     int queue_parts_per_item = 0;     // > 0: fixed work-item size in parts (diagnostics); 0: sized per evaluation by the kernel
+    int batch_dbg = 0;                // 1: per-phase accumulators of the independent-batch kernel on stderr
     int queue_dbg = 0;                // 1: per-phase accumulators of the work-queue kernel on stderr
     int trace = 0;                    // 1: per-evaluation LM trace on stderr
     int dbg_fit = 0;                  // 1: in-kernel timeline of the persistent fit (vp_debug_timeline reads it)

@@ -15,7 +15,7 @@ import tempfile
 
 rep, obj, key = sys.argv[1:4]
 min_s = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + key.split("ILi")[0][-16:]],
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + (sys.argv[5] if len(sys.argv) > 5 else key.split("ILi")[0][-16:])],
                      capture_output=True, text=True).stdout
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)

@@ -451,3 +451,36 @@ def test_fit_host_batch_equals_fit_per_problem():
             assert one.minimization_report.number_of_evaluations == reports[k].number_of_evaluations
             assert one.minimization_report.objective_function == reports[k].objective_function
             assert np.array_equal(one.linear_coefficients(), Cs[k])
+
+
+# ---------------------------------------------------------------------------------------------------
+# independent-batch kernel: slot refill / drain of the warp-specialised pipeline
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,P,distinct", [(256, 1, 1), (200, 3, 3), (256, 6000, 24), (1000, 2500, 10)])
+def test_batch_slots_refill_and_drain_are_deterministic(m, P, distinct):
+    """P problems of which only `distinct` are different (the others are copies): whatever CTA, slot and round a copy
+    lands in -- first fill, refill from the work counter, the drain with dying slot groups -- it must reproduce the
+    result of its original bit for bit, and the originals must agree with their own oracle fits. P = 1 and P = 3
+    leave whole groups of slots empty from the start; P = 6000 > CTAs x slots exercises the refill."""
+    import varpro_b200 as vb
+    from test_gpu_parity import _batch_model
+    base = W.triple_exp_batch(P=distinct, m=m, seed=4242)
+    reps = (P + distinct - 1) // distinct
+    Y = np.asfortranarray(np.tile(base["Y"], (1, reps))[:, :P])
+    a0 = np.tile(base["alpha0"], (reps, 1))[:P]
+    batch = vb.IndependentBatch(_batch_model(base, m), Y, a0)
+    res = batch.fit()
+    for p in range(distinct, P):
+        o = p % distinct
+        assert np.array_equal(res.nonlinear_parameters[p], res.nonlinear_parameters[o]), p
+        assert np.array_equal(res.linear_coefficients[:, p], res.linear_coefficients[:, o]), p
+        assert res.objective_function[p] == res.objective_function[o] and res.number_of_evaluations[p] == res.number_of_evaluations[o]
+    for p in range(min(distinct, 4)):
+        one = dict(x=base["x"], Y=np.asfortranarray(base["Y"][:, p:p + 1]), basis=base["basis"], q=3,
+                   alpha0=list(base["alpha0"][p]), weights=None)
+        op = W.make_oracle(one)
+        rep = op.fit()
+        assert bool(res.successful[p]) == bool(rep["successful"])
+        rn_g, rn_o = np.sqrt(2 * res.objective_function[p]), np.sqrt(2 * rep["objective_function"])
+        assert abs(rn_g - rn_o) <= 1e-10 * np.linalg.norm(one["Y"]), p
+    batch.close()

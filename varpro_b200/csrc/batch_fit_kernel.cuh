@@ -36,6 +36,7 @@
 
 namespace vp {
 
+constexpr unsigned long long BATCH_SPIN_TIMEOUT_NS = 4000000000ull; // a lost partner must not hang the GPU
 __host__ __device__ constexpr int pow2_ceil(int k) { int p = 1; while (p < k) p <<= 1; return p; }
 __host__ __device__ constexpr int log2_int(int k) { int l = 0; while ((1 << l) < k) ++l; return l; }
 
@@ -145,6 +146,7 @@ struct BatchArgs {
     int *term_out;        // P: Termination
     int *nfev_out;        // P
     unsigned long long *next; // work counter (zeroed by the host)
+    unsigned int *error;      // set to 1 when a hand-off between the compute warps and the LM warp timed out
     ExpTable expc;            // vp_exp_table(): the exp coefficients as direct constant-bank operands
     unsigned long long *dbg;  // optional per-CTA accumulators: [0] evaluation ns, [1] LM ns, [2] ns waiting for LM, [3] evaluations, [5] basis ns, [6] sweep 0 ns, [7] LM steps
 };
@@ -204,7 +206,7 @@ batch_fit_kernel(const BatchArgs a)
     __shared__ double coef_acc[G][N];
     __shared__ long long prob_s[G]; // problem in the slot
     __shared__ int ev_seq[2], lm_seq[2], live_s[G];
-    __shared__ int exhausted_s;
+    __shared__ int exhausted_s, abort_s, go_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = a.md.m, q = a.md.q;
@@ -212,7 +214,7 @@ batch_fit_kernel(const BatchArgs a)
     if (tid < G) { live_s[tid] = 0; prob_s[tid] = -1; }
     if (tid < 2) { ev_seq[tid] = 0; lm_seq[tid] = 0; }
     if (tid == 0) {
-        exhausted_s = 0;
+        exhausted_s = 0; abort_s = 0; go_s = 1;
 #pragma unroll
         for (int j = 0; j < VP_MAX_N; ++j) {
             ms.kind[j] = a.md.kind[j]; ms.npar[j] = a.md.npar[j]; ms.p0[j] = a.md.pidx[j][0]; ms.p1[j] = a.md.pidx[j][1];
@@ -253,9 +255,18 @@ batch_fit_kernel(const BatchArgs a)
 #pragma unroll 1
             for (int grp = 0; grp < 2; ++grp) {
                 if (!alive[grp]) continue; // warp-uniform
-                if (lane == 0)
-                    while (ld_flag(&ev_seq[grp]) < round) __nanosleep(200);
-                __syncwarp();
+                int lost = 0;
+                if (lane == 0) {
+                    const unsigned long long ts = global_timer_ns();
+                    while (ld_flag(&ev_seq[grp]) < round) {
+                        __nanosleep(200);
+                        if (ld_flag(&abort_s) || global_timer_ns() - ts > BATCH_SPIN_TIMEOUT_NS) { lost = 1; break; }
+                    }
+                }
+                if (__shfl_sync(0xffffffffu, lost, 0)) { // the compute warps are gone (bounded spin: never hang the GPU)
+                    if (lane == 0) { *a.error = 1u; *(volatile int *)&abort_s = 1; }
+                    return;
+                }
                 __threadfence_block();
                 unsigned long long t0 = 0;
                 if (a.dbg && lane == 0) t0 = global_timer_ns();
@@ -371,7 +382,7 @@ batch_fit_kernel(const BatchArgs a)
     }
 
     // =============================== compute warps =====================================================
-    unsigned long long t_eval = 0, t_wait = 0, n_evals = 0, t_basis = 0, t_sw0 = 0, te = 0, tw = 0, tb = 0; // (thread 0, dbg only)
+    unsigned long long t_eval = 0, t_wait = 0, n_evals = 0, t_basis = 0, t_sw0 = 0, te = 0, tb = 0; // (thread 0, dbg only)
     // the thread's rows of x and w (shared by all problems)
     double xi[RPT], wi[RPT];
 #pragma unroll
@@ -388,10 +399,17 @@ batch_fit_kernel(const BatchArgs a)
         for (int g = 0; g < G; ++g) {
             const int grp = g >= GH;
             if (g == 0 || g == GH) { // the group's previous LM steps (or its first fill) must be complete
-                if (a.dbg && tid == 0) tw = global_timer_ns();
-                while (ld_flag(&lm_seq[grp]) < round) { }
-                __threadfence_block();
-                if (a.dbg && tid == 0) t_wait += global_timer_ns() - tw;
+                if (tid == 0) { // (one thread decides, so that a timeout leaves the barriers of the others balanced)
+                    const unsigned long long ts = global_timer_ns();
+                    int ok = 1;
+                    while (ld_flag(&lm_seq[grp]) < round)
+                        if (ld_flag(&abort_s) || global_timer_ns() - ts > BATCH_SPIN_TIMEOUT_NS) { ok = 0; break; }
+                    go_s = ok;
+                    if (!ok) { *a.error = 1u; *(volatile int *)&abort_s = 1; }
+                    if (a.dbg) t_wait += global_timer_ns() - ts;
+                }
+                bar_sync_n(1, THREADS);
+                if (!go_s) return; // uniform
             }
             if (live_s[g]) { // uniform: written before lm_seq
             ++nlive;

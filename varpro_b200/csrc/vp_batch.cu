@@ -72,7 +72,7 @@ static int batch_create_common(vp_ctx *ctx, vp_model *model, int64_t P, const vo
     if (e == cudaSuccess) e = DEV_ALLOC(ctx, &b->obj, sizeof(double) * (size_t)P);
     if (e == cudaSuccess) e = DEV_ALLOC(ctx, &b->term, sizeof(int) * (size_t)P);
     if (e == cudaSuccess) e = DEV_ALLOC(ctx, &b->nfev, sizeof(int) * (size_t)P);
-    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &b->next, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = DEV_ALLOC(ctx, &b->next, 2 * sizeof(unsigned long long)); // [0] work counter, [1] error word
     if (e == cudaSuccess && w_host) {
         e = DEV_ALLOC(ctx, &b->w_dev, sizeof(double) * (size_t)m);
         if (e == cudaSuccess) e = cudaMemcpyAsync(b->w_dev, w_host, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream);
@@ -135,8 +135,9 @@ static int batch_fit_launch(vp_batch *b, const vp_lm_options *opt)
         VP_CUDA(ctx, cudaMemcpyAsync(b->alpha0, b->alpha, sizeof(double) * (size_t)md.q * b->P, cudaMemcpyDeviceToDevice, ctx->stream));
     a.alpha0 = b->alpha0; a.alpha_out = b->alpha; a.C_out = b->C; a.obj_out = b->obj; a.term_out = b->term; a.nfev_out = b->nfev;
     a.next = b->next;
+    a.error = reinterpret_cast<unsigned int *>(b->next + 1);
     a.expc = vp_exp_table();
-    VP_CUDA(ctx, cudaMemsetAsync(b->next, 0, sizeof(unsigned long long), ctx->stream));
+    VP_CUDA(ctx, cudaMemsetAsync(b->next, 0, 2 * sizeof(unsigned long long), ctx->stream));
     int occ = 0;
     VP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads + 32 * k.lm_warps, b->smem));
     if (occ < 1) return vp_fail(ctx, VP_ERR_MODEL_TOO_LARGE, "vp_batch: kernel does not fit on an SM");
@@ -173,8 +174,11 @@ extern "C" int vp_batch_fit(vp_batch *b, const vp_lm_options *opt, vp_fit_report
     cudaSetDevice(ctx->device);
     int rc = batch_fit_launch(b, opt);
     if (rc != VP_OK) return rc;
+    unsigned int kerr = 0;
+    VP_CUDA(ctx, cudaMemcpyAsync(&kerr, b->next + 1, sizeof(kerr), cudaMemcpyDeviceToHost, ctx->stream));
     if (!reports) {
         VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (kerr) return vp_fail(ctx, VP_ERR_CUDA, "vp_batch_fit: a hand-off inside the batch kernel timed out (GPU shared with another long-running kernel?)");
         return VP_OK;
     }
     std::vector<double> obj((size_t)b->P);
@@ -183,6 +187,7 @@ extern "C" int vp_batch_fit(vp_batch *b, const vp_lm_options *opt, vp_fit_report
     VP_CUDA(ctx, cudaMemcpyAsync(term.data(), b->term, sizeof(int) * (size_t)b->P, cudaMemcpyDeviceToHost, ctx->stream));
     VP_CUDA(ctx, cudaMemcpyAsync(nfev.data(), b->nfev, sizeof(int) * (size_t)b->P, cudaMemcpyDeviceToHost, ctx->stream));
     VP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (kerr) return vp_fail(ctx, VP_ERR_CUDA, "vp_batch_fit: a hand-off inside the batch kernel timed out (GPU shared with another long-running kernel?)");
     for (int64_t p = 0; p < b->P; ++p) {
         reports[p].termination = term[(size_t)p];
         reports[p].number_of_evaluations = nfev[(size_t)p];

@@ -441,22 +441,33 @@ batch_fit_kernel(const BatchArgs a)
                     int mx = 0; // max over the thread's rows of the high word of |Phi_w[i][j]| (NaN / Inf are the largest)
                     if (kind == VP_BASIS_EXP_DECAY) {
                         const double inv0 = 1.0 / a0; // one division per basis function, see basis_eval_all
-                        double done[RPT]; // (scheduling only: row r + 4 starts after row r is finished -- 4 exp chains in flight
-                                          //  per thread are enough and 8 do not fit in 96 registers)
+                        constexpr int RB = RPT < 4 ? RPT : 4; // rows per block: RB exp chains in flight per thread
+                        double done = 0.0;                    // (scheduling only: a block starts after the previous one is
+                                                              //  finished -- 8 chains do not fit in 96 registers)
 #pragma unroll
-                        for (int r = 0; r < RPT; ++r) {
-                            double xr = xi[r];
-                            if (r >= 4) asm volatile("" : "+d"(xr) : "d"(done[r - 4]));
-                            const double t = xr * inv0, ex = vp_exp_with(-t, a.expc.c);
-                            double pv = wi[r] * ex, pa = wi[r] * (ex * t * inv0);
-                            done[r] = pa;
-                            if (RPT == 1 || r >= RPT / 2) {
-                                const bool in = tid + r * THREADS < m;
-                                pv = in ? pv : 0.0; pa = in ? pa : 0.0;
+                        for (int r0 = 0; r0 < RPT; r0 += RB) {
+                            double t[RB], arg[RB], ex[RB];
+#pragma unroll
+                            for (int v = 0; v < RB; ++v) {
+                                double xr = xi[r0 + v];
+                                if (r0 > 0) asm volatile("" : "+d"(xr) : "d"(done));
+                                t[v] = xr * inv0;
+                                arg[v] = -t[v];
                             }
-                            mx = max(mx, __double2hiint(pv) & 0x7fffffff);
-                            cv[r * THREADS] = pv;
-                            ca[r * THREADS] = pa;
+                            vp_exp_vec<RB>(arg, ex, a.expc.c);
+#pragma unroll
+                            for (int v = 0; v < RB; ++v) {
+                                const int r = r0 + v;
+                                double pv = wi[r] * ex[v], pa = wi[r] * (ex[v] * t[v] * inv0);
+                                if (RPT == 1 || r >= RPT / 2) {
+                                    const bool in = tid + r * THREADS < m;
+                                    pv = in ? pv : 0.0; pa = in ? pa : 0.0;
+                                }
+                                mx = max(mx, __double2hiint(pv) & 0x7fffffff);
+                                cv[r * THREADS] = pv;
+                                ca[r * THREADS] = pa;
+                                done = pa;
+                            }
                         }
                     } else {
                         const double scale = ms.scale[j];

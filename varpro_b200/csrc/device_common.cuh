@@ -78,6 +78,44 @@ __device__ __forceinline__ double vp_exp_with(const double a, const TAB &C)
     return res;
 }
 __device__ __forceinline__ double vp_exp(const double a) { return vp_exp_with(a, VP_EXP_C); }
+// NV independent arguments, written coefficient by coefficient: every constant is fetched once and feeds NV
+// DFMAs of NV independent Horner chains (the row-by-row form reloads the table for every exp when registers
+// are tight). Bitwise the same results as vp_exp_with.
+template <int NV, typename TAB>
+__device__ __forceinline__ void vp_exp_vec(const double (&a)[NV], double (&res)[NV], const TAB &C)
+{
+    double kd[NV], r[NV], p[NV];
+    {
+        const double c0 = C[0], c1 = C[1], c2 = C[2], c3 = C[3];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) kd[v] = fma(a[v], c0, c1);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double kf = kd[v] - c1;
+            r[v] = fma(kf, c3, fma(kf, c2, a[v]));
+        }
+    }
+    {
+        const double c4 = C[4];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) p[v] = c4;
+    }
+#pragma unroll
+    for (int i = 5; i < 14; ++i) {
+        const double ci = C[i];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) p[v] = fma(p[v], r[v], ci);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        double pp = fma(p[v], r[v], 1.0);
+        pp = fma(pp, r[v], 1.0);
+        res[v] = __hiloint2double(__double2hiint(pp) + (__double2loint(kd[v]) << 20), __double2loint(pp));
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+        if (!(fabs(a[v]) < 700.0)) res[v] = exp(a[v]);
+}
 
 // --- mbarrier + bulk async copy (TMA, SASS: UBLKCP / SYNCS) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

@@ -484,3 +484,85 @@ def test_batch_slots_refill_and_drain_are_deterministic(m, P, distinct):
         rn_g, rn_o = np.sqrt(2 * res.objective_function[p]), np.sqrt(2 * rep["objective_function"])
         assert abs(rn_g - rn_o) <= 1e-10 * np.linalg.norm(one["Y"]), p
     batch.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# further model shapes with compiled fast paths: (n, p) = (2, 1), (2, 2), (4, 3)
+# ---------------------------------------------------------------------------------------------------
+_SHAPES = {
+    "exp+offset (2,1)": dict(basis=[(0, [0]), (1, [])], tau=[2.0], start=[1.5]),
+    "double exp (2,2)": dict(basis=[(0, [0]), (0, [1])], tau=[1.0, 4.0], start=[1.3, 3.4]),
+    "triple exp+offset (4,3)": dict(basis=[(0, [0]), (0, [1]), (0, [2]), (1, [])], tau=[0.8, 3.0, 11.0], start=[0.9, 2.6, 12.5]),
+}
+
+
+@pytest.mark.parametrize("shape", sorted(_SHAPES))
+@pytest.mark.parametrize("S", [1, 37])
+def test_further_fast_path_shapes_state_fit_and_fit_many(shape, S):
+    """One exponential + offset, two exponentials, three exponentials + offset: state and fit parity with the oracle
+    on the persistent kernel, vp_fit_many bitwise equal to vp_fit on the work-queue kernel, and the launch counter
+    shows ONE launch per fit (the generic path would need one graph replay per evaluation)."""
+    import varpro_b200 as vb
+    sp = _SHAPES[shape]
+    rng = np.random.default_rng(len(shape) + S)
+    m = 600
+    x = np.linspace(0.0, 25.0, m)
+    n = len(sp["basis"])
+    cols = [np.exp(-x / t) for t in sp["tau"]] + ([np.ones_like(x)] if n > len(sp["tau"]) else [])
+    Cs = rng.uniform(1.0, 5.0, size=(n, S))
+    Y = np.asfortranarray(np.stack(cols, axis=1) @ Cs + 1e-4 * rng.standard_normal((m, S)))
+    wl = dict(x=x, Y=Y, basis=sp["basis"], q=len(sp["tau"]), alpha0=list(sp["start"]), weights=None)
+    gp, op = _make_gpu(wl), W.make_oracle(wl)
+    Yn = np.linalg.norm(Y)
+    _state_parity(gp, op, Yn, shape + " at alpha0")
+    solver = vb.LevMarSolver.default()
+    l0 = gp._ctx.kernel_launches()
+    res = solver.fit(gp)
+    assert gp._ctx.kernel_launches() - l0 == 1, "the whole fit must be ONE launch of the persistent kernel"
+    rep = op.fit()
+    assert rep["successful"] and res.was_successful()
+    assert abs(np.sqrt(2 * res.minimization_report.objective_function) - np.sqrt(2 * rep["objective_function"])) <= REL_RNORM * Yn
+    tol = 1e-5 if n == 4 else REL_PARAM  # three exponentials + offset: ill-conditioned, like the four-exponential test
+    assert np.max(np.abs(res.nonlinear_parameters() - op.params()) / np.abs(op.params())) <= tol
+    a_fit, c_fit = res.nonlinear_parameters().copy(), res.linear_coefficients().copy()
+    nfev = res.minimization_report.number_of_evaluations
+    # the same problem three times through the work queue: bitwise the persistent kernel's result
+    gps = [_make_gpu(wl) for _ in range(3)]
+    many = solver.fit_many(gps)
+    for r in many:
+        assert np.array_equal(r.nonlinear_parameters(), a_fit) and np.array_equal(r.linear_coefficients(), c_fit)
+        assert r.minimization_report.number_of_evaluations == nfev
+    for g in gps + [gp]:
+        g.close()
+
+
+@pytest.mark.parametrize("shape", sorted(_SHAPES))
+def test_further_fast_path_shapes_independent_batch(shape):
+    """The same three shapes through vp_batch: every problem of a small batch against its own single-problem fit."""
+    import varpro_b200 as vb
+    from test_gpu_parity import _batch_model
+    sp = _SHAPES[shape]
+    rng = np.random.default_rng(7 + len(shape))
+    m, P = 500, 9
+    x = np.linspace(0.0, 25.0, m)
+    n, q = len(sp["basis"]), len(sp["tau"])
+    tau = np.array(sp["tau"]) * rng.uniform(0.9, 1.1, size=(P, q))
+    Y = np.empty((m, P))
+    for p in range(P):
+        cols = [np.exp(-x / t) for t in tau[p]] + ([np.ones_like(x)] if n > q else [])
+        Y[:, p] = np.stack(cols, axis=1) @ rng.uniform(1.0, 5.0, size=n) + 1e-4 * rng.standard_normal(m)
+    Y = np.asfortranarray(Y)
+    a0 = np.tile(np.array(sp["start"]), (P, 1))
+    wl = dict(x=x, basis=sp["basis"], q=q)
+    batch = vb.IndependentBatch(_batch_model(wl, m), Y, a0)
+    res = batch.fit()
+    assert res.successful.all(), res.terminations
+    for p in range(P):
+        one = dict(x=x, Y=np.asfortranarray(Y[:, p:p + 1]), basis=sp["basis"], q=q, alpha0=list(sp["start"]), weights=None)
+        gp = _make_gpu(one)
+        r1 = vb.LevMarSolver.default().fit(gp)
+        tol = 1e-5 if n == 4 else 1e-7
+        assert np.max(np.abs(res.nonlinear_parameters[p] - r1.nonlinear_parameters()) / np.abs(r1.nonlinear_parameters())) <= tol, p
+        assert abs(np.sqrt(2 * res.objective_function[p]) - np.sqrt(2 * r1.minimization_report.objective_function)) <= REL_RNORM * np.linalg.norm(Y[:, p]), p
+        gp.close()
+    batch.close()

@@ -60,7 +60,8 @@ static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0
 constexpr int BATCH_THREADS = 512;
 #define VP_BK(RPT, G) {N_, P_, RPT, BATCH_THREADS, G, 1, (const void *)&batch_fit_kernel<N_, P_, RPT, BATCH_THREADS, G>}
 // slots: two groups of G / 2; one group's LM steps (lockstep in the LM warp, ~40 us) must fit into the other group's evaluations
-static const BatchKernelEntry batch_tab[] = {VP_BK(1, 32), VP_BK(2, 32), VP_BK(4, 32), VP_BK(8, 16)};
+constexpr int G_SMALL = (N_ + P_ <= 6) ? 32 : 16; // (static shared memory <= 48 KB)
+static const BatchKernelEntry batch_tab[] = {VP_BK(1, G_SMALL), VP_BK(2, G_SMALL), VP_BK(4, G_SMALL), VP_BK(8, 16)};
 static const KernelGroup group = {nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, batch_tab, (int)(sizeof(batch_tab) / sizeof(batch_tab[0]))};
 #else
 constexpr int PANEL_HH_THREADS = 512;

@@ -77,7 +77,25 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_2_4_queue1, double, VP_F64, 2, 4, 5) \
     X(f64_3_3_batch, double, VP_F64, 3, 3, 4) \
     X(f64_3_2_batch, double, VP_F64, 3, 2, 4) \
-    X(f64_2_4_batch, double, VP_F64, 2, 4, 4)
+    X(f64_2_4_batch, double, VP_F64, 2, 4, 4) \
+    X(f64_2_1_dmma, double, VP_F64, 2, 1, 1) /* one exponential + offset */ \
+    X(f64_2_1_panel, double, VP_F64, 2, 1, 2) \
+    X(f64_2_1_fit0, double, VP_F64, 2, 1, 3) \
+    X(f64_2_1_fit1, double, VP_F64, 2, 1, 3) \
+    X(f64_2_1_queue1, double, VP_F64, 2, 1, 5) \
+    X(f64_2_1_batch, double, VP_F64, 2, 1, 4) \
+    X(f64_2_2_dmma, double, VP_F64, 2, 2, 1) /* double exponential without offset */ \
+    X(f64_2_2_panel, double, VP_F64, 2, 2, 2) \
+    X(f64_2_2_fit0, double, VP_F64, 2, 2, 3) \
+    X(f64_2_2_fit1, double, VP_F64, 2, 2, 3) \
+    X(f64_2_2_queue1, double, VP_F64, 2, 2, 5) \
+    X(f64_2_2_batch, double, VP_F64, 2, 2, 4) \
+    X(f64_4_3_dmma, double, VP_F64, 4, 3, 1) /* triple exponential + offset */ \
+    X(f64_4_3_panel, double, VP_F64, 4, 3, 2) \
+    X(f64_4_3_fit0, double, VP_F64, 4, 3, 3) \
+    X(f64_4_3_fit1, double, VP_F64, 4, 3, 3) \
+    X(f64_4_3_queue1, double, VP_F64, 4, 3, 5) \
+    X(f64_4_3_batch, double, VP_F64, 4, 3, 4)
 
 #define VP_DECLARE_GROUP(tag, T, DT, N, P, PART) const KernelGroup *vp_kernel_group_##tag();
 VP_KERNEL_GROUPS(VP_DECLARE_GROUP)

@@ -167,7 +167,7 @@ void *vp_ctx_stream(const vp_ctx *ctx);
  *   stream_kernel   auto (default) | simt | generic; applies to problems created later
  *   panel_generic, stream_stages, stream_ct, stream_occ, queue_items_per_cta, batch_slots, pool_mb,
  *   max_ctas, fit_warps (integers; max_ctas caps the grid of problems created later so that contexts can share a GPU)
- *   trace, queue_dbg, dbg_fit (0 | 1: diagnostics on stderr / in-kernel timelines) */
+ *   trace, queue_dbg, batch_dbg, dbg_fit (0 | 1: diagnostics on stderr / in-kernel timelines) */
 int vp_ctx_set_option(vp_ctx *ctx, const char *key, const char *value);
 /* Return the context's idle cached device / pinned buffers to the CUDA allocator (the cache is capped at
  * pool_mb, default 1024 MiB; co-resident frameworks may want the memory back). Synchronises the stream. */

@@ -70,11 +70,13 @@ __device__ __forceinline__ int bar_or_n(const int id, const int count, const int
         : "memory");
     return r;
 }
-__device__ __forceinline__ int ld_flag(const int *p) { return *(const volatile int *)p; }
+// Hand-off flags in shared memory: atomic accesses (what compute-sanitizer's racecheck recognises as
+// synchronisation), a block-level fence before the publishing store and after the observing load.
+__device__ __forceinline__ int ld_flag(int *p) { return atomicOr(p, 0); }
 __device__ __forceinline__ void st_flag(int *p, const int v)
 {
     __threadfence_block();
-    *(volatile int *)p = v;
+    atomicExch(p, v);
 }
 
 // Warp-level sum of KP (a power of two <= 32) values per lane by recursive halving: at the level with lane
@@ -206,7 +208,7 @@ batch_fit_kernel(const BatchArgs a)
     __shared__ double coef_acc[G][N];
     __shared__ long long prob_s[G]; // problem in the slot
     __shared__ int ev_seq[2], lm_seq[2], live_s[G];
-    __shared__ int exhausted_s, abort_s, go_s;
+    __shared__ int exhausted_s, abort_s, go_s[2]; // go_s: verdict of thread 0's bounded wait, alternating by group (a slow reader of one check never sees the next one's)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = a.md.m, q = a.md.q;
@@ -214,7 +216,7 @@ batch_fit_kernel(const BatchArgs a)
     if (tid < G) { live_s[tid] = 0; prob_s[tid] = -1; }
     if (tid < 2) { ev_seq[tid] = 0; lm_seq[tid] = 0; }
     if (tid == 0) {
-        exhausted_s = 0; abort_s = 0; go_s = 1;
+        exhausted_s = 0; abort_s = 0; go_s[0] = go_s[1] = 1;
 #pragma unroll
         for (int j = 0; j < VP_MAX_N; ++j) {
             ms.kind[j] = a.md.kind[j]; ms.npar[j] = a.md.npar[j]; ms.p0[j] = a.md.pidx[j][0]; ms.p1[j] = a.md.pidx[j][1];
@@ -234,7 +236,7 @@ batch_fit_kernel(const BatchArgs a)
             long long pnew = -1;
             if (!ld_flag(&exhausted_s)) {
                 pnew = (long long)atomicAdd(a.next, 1ull);
-                if (pnew >= a.P) { pnew = -1; *(volatile int *)&exhausted_s = 1; }
+                if (pnew >= a.P) { pnew = -1; atomicExch(&exhausted_s, 1); }
             }
             if (pnew >= 0) {
                 double x0[VP_MAX_Q];
@@ -264,7 +266,7 @@ batch_fit_kernel(const BatchArgs a)
                     }
                 }
                 if (__shfl_sync(0xffffffffu, lost, 0)) { // the compute warps are gone (bounded spin: never hang the GPU)
-                    if (lane == 0) { *a.error = 1u; *(volatile int *)&abort_s = 1; }
+                    if (lane == 0) { *a.error = 1u; atomicExch(&abort_s, 1); }
                     return;
                 }
                 __threadfence_block();
@@ -404,12 +406,12 @@ batch_fit_kernel(const BatchArgs a)
                     int ok = 1;
                     while (ld_flag(&lm_seq[grp]) < round)
                         if (ld_flag(&abort_s) || global_timer_ns() - ts > BATCH_SPIN_TIMEOUT_NS) { ok = 0; break; }
-                    go_s = ok;
-                    if (!ok) { *a.error = 1u; *(volatile int *)&abort_s = 1; }
+                    go_s[grp] = ok;
+                    if (!ok) { *a.error = 1u; atomicExch(&abort_s, 1); }
                     if (a.dbg) t_wait += global_timer_ns() - ts;
                 }
                 bar_sync_n(1, THREADS);
-                if (!go_s) return; // uniform
+                if (!go_s[grp]) return; // uniform
             }
             if (live_s[g]) { // uniform: written before lm_seq
             ++nlive;

@@ -42,23 +42,27 @@ static int batch_create_common(vp_ctx *ctx, vp_model *model, int64_t P, const vo
     const KernelTables &KT = vp_kernel_tables();
     cudaSetDevice(ctx->device);
     int pick = -1;
+    bool shape_known = false;
     for (size_t i = 0; i < KT.batch.size(); ++i) {
         const BatchKernelEntry &k = KT.batch[i];
-        if (k.n != md.n || k.p != md.p || (long long)k.rpt * k.threads < md.m) continue;
-        // smallest row tiling that covers m; among those the requested number of problem slots (default 8)
+        if (k.n != md.n || k.p != md.p) continue;
+        shape_known = true;
+        if ((long long)k.rpt * k.threads < md.m) continue;
+        // the working matrix (rpt * threads rows, rows >= m are zero) + the kernel's static shared memory must fit
+        cudaFuncAttributes fa{};
+        VP_CUDA(ctx, cudaFuncGetAttributes(&fa, k.fn));
+        if (sizeof(double) * (size_t)(md.n + md.p) * k.rpt * k.threads + fa.sharedSizeBytes > ctx->smem_optin) continue;
+        // fewest rows per thread among the tilings that cover m; among those the requested number of problem slots
         const int want = ctx->opt.batch_slots;
         if (pick < 0 || k.rpt < KT.batch[pick].rpt ||
             (k.rpt == KT.batch[pick].rpt && std::abs(k.slots - want) < std::abs(KT.batch[pick].slots - want)))
             pick = (int)i;
     }
     if (pick < 0)
-        return vp_fail(ctx, VP_ERR_MODEL_TOO_LARGE, "vp_batch: no independent-batch kernel instantiated for this model shape / m > 4096");
-    const int mpad = KT.batch[pick].rpt * KT.batch[pick].threads; // rows of the shared-memory working matrix (rows >= m are zero)
+        return vp_fail(ctx, VP_ERR_MODEL_TOO_LARGE, shape_known ? "vp_batch: m*(n+p) working matrix does not fit in shared memory (m > 4096?)"
+                                                                  : "vp_batch: no independent-batch kernel instantiated for this model shape");
+    const int mpad = KT.batch[pick].rpt * KT.batch[pick].threads; // rows of the shared-memory working matrix
     const size_t smem = sizeof(double) * (size_t)(md.n + md.p) * mpad;
-    cudaFuncAttributes fa{};
-    VP_CUDA(ctx, cudaFuncGetAttributes(&fa, KT.batch[pick].fn));
-    if (smem + fa.sharedSizeBytes > ctx->smem_optin)
-        return vp_fail(ctx, VP_ERR_MODEL_TOO_LARGE, "vp_batch: m*(n+p) working matrix does not fit in shared memory");
     VP_CUDA(ctx, vp_ensure_dynamic_smem(ctx->device, KT.batch[pick].fn, smem));
     vp_batch *b = new (std::nothrow) vp_batch();
     if (!b) return VP_ERR_OUT_OF_MEMORY;

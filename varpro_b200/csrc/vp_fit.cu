@@ -219,9 +219,7 @@ static int queue_kernel_for(const vp_problem *pr, int *lds_out)
     const vp_model *mo = pr->model;
     if (mo->hosteval || pr->comm || !pr->cached) return -1;
     const ModelDesc &md = mo->md;
-    int lds = mo->ld;
-    if (mo->dtype == VP_F64) { while (lds % 16 != 4) lds += 2; }
-    else { while (lds % 32 != 8) lds += 4; }
+    int lds = 0; // column stride of a tile slot (vp_tile_lds)
     const std::vector<QueueKernelEntry> &tab = vp_kernel_tables().queue;
     int pick = -1;
     for (size_t i = 0; i < tab.size(); ++i) {
@@ -229,10 +227,13 @@ static int queue_kernel_for(const vp_problem *pr, int *lds_out)
         if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p) continue;
         const int rows = 4 * k.ksteps * k.nwarps;
         if (rows < mo->ld) continue;
-        if (k.exact && rows > lds) continue;
+        const int lds_k = vp_tile_lds(mo->dtype, mo->ld, rows, k.exact);
+        if (lds_k < 0) continue;
         if (pick < 0 || vp_better_tiling(k.ksteps, k.nwarps, k.exact, tab[(size_t)pick].ksteps, tab[(size_t)pick].nwarps,
-                                         tab[(size_t)pick].exact, pr->ctx->opt.fit_warps))
+                                         tab[(size_t)pick].exact, pr->ctx->opt.fit_warps)) {
             pick = (int)i;
+            lds = lds_k;
+        }
     }
     if (lds_out) *lds_out = lds;
     return pick;

@@ -215,6 +215,26 @@ struct KernelTables {
 };
 const KernelTables &vp_kernel_tables(); // thread-safe, built on first use
 
+// Padded column stride (elements) of a tile slot in shared memory: the smallest value >= n whose fragment loads are
+// bank-conflict free, 4 (mod 16) doubles / 8 (mod 32) floats (see stream_kernel_dmma.cuh).
+inline int vp_pad_lds(int dtype, int n)
+{
+    if (dtype == VP_F64) { while (n % 16 != 4) n += 2; }
+    else { while (n % 32 != 8) n += 4; }
+    return n;
+}
+// The stride to use with a (rows, exact) tiling for a problem with leading dimension ld, or -1 if the tiling does not
+// apply. The unpredicated EXACT tile code needs every fragment row inside the slot (rows <= lds): when the rows of
+// the tiling exceed ld by at most 1/8, the slots are simply made that much taller (their extra rows are zero), so that
+// e.g. m = 1000 runs the EXACT code of the 1024-row tiling.
+inline int vp_tile_lds(int dtype, int ld, int rows, int exact)
+{
+    const int lds = vp_pad_lds(dtype, ld);
+    if (!exact || rows <= lds) return lds;
+    if ((long long)rows * 8 <= (long long)ld * 9) return vp_pad_lds(dtype, rows);
+    return -1;
+}
+
 // Row tilings of the DMMA-based kernels: (ksteps, nwarps) covers 4*ksteps*nwarps rows. Better = fewer rows (less
 // padding work), then the unpredicated EXACT variant, then the preferred warp count.
 inline bool vp_better_tiling(int ks, int nw, int exact, int ks0, int nw0, int exact0, int prefer_warps)

@@ -17,9 +17,7 @@ static int plan_fit_kernel(vp_problem *pr)
     if (mo->hosteval) return VP_OK; // the fused kernels evaluate the built-in device basis functions
     if (ctx->opt.stream_kernel != VP_STREAMK_AUTO) return VP_OK;
     const size_t es = vp_esize(mo->dtype);
-    int lds = mo->ld; // conflict-free fragment loads: 4 (mod 16) doubles / 8 (mod 32) floats (see stream_kernel_dmma.cuh)
-    if (mo->dtype == VP_F64) { while (lds % 16 != 4) lds += 2; }
-    else { while (lds % 32 != 8) lds += 4; }
+    int lds = 0; // column stride of a tile slot (vp_tile_lds)
     const KernelTables &KT = vp_kernel_tables();
     // the best row tiling among the fused instantiations of this shape
     int pick = -1;
@@ -27,10 +25,13 @@ static int plan_fit_kernel(vp_problem *pr)
         const FitKernelEntry &k = KT.fit[i];
         if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p) continue;
         const int rows = 4 * k.ksteps * k.nwarps;
-        if (rows < mo->ld || (k.exact && rows > lds)) continue;
+        const int lds_k = vp_tile_lds(mo->dtype, mo->ld, rows, k.exact);
+        if (rows < mo->ld || lds_k < 0) continue;
         if (pick < 0 || vp_better_tiling(k.ksteps, k.nwarps, k.exact, KT.fit[(size_t)pick].ksteps, KT.fit[(size_t)pick].nwarps,
-                                         KT.fit[(size_t)pick].exact, ctx->opt.fit_warps))
+                                         KT.fit[(size_t)pick].exact, ctx->opt.fit_warps)) {
             pick = (int)i;
+            lds = lds_k;
+        }
     }
     if (pick < 0) return VP_OK;
     const FitKernelEntry &k = KT.fit[(size_t)pick];
@@ -79,17 +80,17 @@ static int plan_stream(vp_problem *pr)
     pr->plan_dmma = -1;
     const bool allow_dmma = mo->dtype == VP_F64 && ctx->opt.stream_kernel == VP_STREAMK_AUTO;
     if (allow_dmma) {
-        int lds = mo->ld;
-        while (lds % 16 != 4) lds += 2; // conflict-free fragment loads (see stream_kernel_dmma.cuh)
+        int lds = 0; // column stride of a tile slot (vp_tile_lds)
         int pick = -1;
         for (int i = 0; i < (int)KT.dmma.size(); ++i) {
             const DmmaKernelEntry &k = KT.dmma[i];
             if (k.n != md.n || k.p != md.p) continue;
             const int rows = 4 * k.ksteps * k.nwarps;
             if (rows < mo->ld) continue;
-            if (k.exact && rows > lds) continue; // the unpredicated variant needs rows <= lds
+            const int lds_k = vp_tile_lds(VP_F64, mo->ld, rows, k.exact); // the unpredicated variant needs rows <= lds
+            if (lds_k < 0) continue;
             const int prow = pick < 0 ? 0 : 4 * KT.dmma[pick].ksteps * KT.dmma[pick].nwarps;
-            if (pick < 0 || rows < prow || (rows == prow && k.exact && !KT.dmma[pick].exact)) pick = i;
+            if (pick < 0 || rows < prow || (rows == prow && k.exact && !KT.dmma[pick].exact)) { pick = i; lds = lds_k; }
         }
         if (pick >= 0) {
             const DmmaKernelEntry &k = KT.dmma[pick];

@@ -550,7 +550,7 @@ def _extra_c4(torch, vb, W, solver, peak):
             "fits_per_s": 1e3 / ms, "ms_per_fit": _stats(times), "evaluations": nf,
             "statistics_ms_all_columns_incl_d2h": 1e3 * t_stat, "reduced_chi2_column0": chi2,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "how": "(evaluations - 1) x 4*m*S bytes / CUDA-event time of one vp_fit (work-queue kernel, single fit)"}}
+                         "how": "(evaluations - 1) x 4*m*S bytes / CUDA-event time of one vp_fit (persistent whole-fit kernel fit_kernel_dmma<float>: fp32 tiles converted to fp64 at the fragment loads; the time includes the launch and the read-back of the fit state)"}}
 
 
 def _sharded_global_fit(torch, dist, vb, api, solver, wl, rank, world, device, cols_per_rank=131072, reps=5):

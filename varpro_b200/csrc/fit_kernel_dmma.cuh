@@ -86,6 +86,11 @@ __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu_u32(unsigned int *p
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(prev) : "l"(p), "r"(v) : "memory");
     return prev;
 }
+// the same without a return value: nothing waits for the L2 round trip
+__device__ __forceinline__ void red_add_release_gpu_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
 {
     unsigned long long v;
@@ -506,6 +511,7 @@ fit_kernel_dmma(const StreamArgs<TY> a, const int lds, const FitArgs f)
 
         // ---- part row -> global (double-buffered by evaluation parity), count this CTA in ------------
         double *rows = a.partials + (size_t)(fit_mode ? (e & 1u) : 0u) * grid * a.red_stride;
+        const bool comm_on = f.comm.world >= 1; // world == 1: exchange with itself (exercises the protocol on one GPU)
         dbg_mark(a.dbg, 4);
         part_stage<N, P, CT, NWARPS>(acc, wsum_s, gv_s);
         __syncthreads();
@@ -515,13 +521,19 @@ fit_kernel_dmma(const StreamArgs<TY> a, const int lds, const FitArgs f)
             if (lane == 0) {
                 // release/acquire at gpu scope: orders the row before the count and, in whoever
                 // observes the full count, the count before the reads of everybody's rows
-                const unsigned int prev = atom_add_acq_rel_gpu_u32(fit_mode ? &f.ctl->arrived : a.ticket, 1u);
-                is_last = fit_mode ? (prev == (e + 1u) * (unsigned int)grid - 1u) : (prev == (unsigned int)grid - 1u);
+                if (fit_mode && !comm_on) {
+                    // every CTA waits for the full count below and nobody needs to know who was last: a reduction
+                    // (no return value, no L2 round trip before the polling starts)
+                    red_add_release_gpu_u32(&f.ctl->arrived, 1u);
+                    is_last = 0;
+                } else {
+                    const unsigned int prev = atom_add_acq_rel_gpu_u32(fit_mode ? &f.ctl->arrived : a.ticket, 1u);
+                    is_last = fit_mode ? (prev == (e + 1u) * (unsigned int)grid - 1u) : (prev == (unsigned int)grid - 1u);
+                }
             }
         }
         dbg_mark(a.dbg, 14);
         constexpr int NVF = 1 + NGPU; // values of a partial row
-        const bool comm_on = f.comm.world >= 1; // world == 1: exchange with itself (exercises the protocol on one GPU)
         int timed_out = 0;
         if (!fit_mode) {
             __syncthreads();

@@ -185,15 +185,14 @@ static int fit_persistent(vp_problem *pr, LmState &st, const LmConfig &cfg)
     int rc = ensure_timeline_buffer(pr);
     if (rc != VP_OK) return rc;
     FitDevice *fh = pr->fit_host;
-    memset(fh, 0, sizeof(FitDevice));
+    memset(fh, 0, VP_FIT_BLOCK_BYTES); // the state and the (zeroed) control word behind it: one copy in, one copy out
     fh->st = st; fh->cfg = cfg; fh->accepted = pr->eval; fh->cur = pr->cur; fh->evals = 0;
     cudaStream_t stream = ctx->stream;
-    VP_CUDA(ctx, cudaMemcpyAsync(pr->fit_dev, fh, sizeof(FitDevice), cudaMemcpyHostToDevice, stream));
+    VP_CUDA(ctx, cudaMemcpyAsync(pr->fit_dev, fh, VP_FIT_BLOCK_BYTES, cudaMemcpyHostToDevice, stream));
     rc = vp_launch_fused(pr, 0, /*fit_mode=*/true);
     if (rc != VP_OK) return rc;
-    VP_CUDA(ctx, cudaMemcpyAsync(fh, pr->fit_dev, sizeof(FitDevice), cudaMemcpyDeviceToHost, stream));
-    FitCtl *ch = reinterpret_cast<FitCtl *>(pr->alpha_stage + VP_MAX_Q); // pinned staging (allocated with alpha_stage)
-    VP_CUDA(ctx, cudaMemcpyAsync(ch, pr->fit_ctl, sizeof(FitCtl), cudaMemcpyDeviceToHost, stream));
+    VP_CUDA(ctx, cudaMemcpyAsync(fh, pr->fit_dev, VP_FIT_BLOCK_BYTES, cudaMemcpyDeviceToHost, stream));
+    const FitCtl *ch = reinterpret_cast<const FitCtl *>(reinterpret_cast<const unsigned char *>(fh) + VP_FIT_CTL_OFFSET);
     VP_CUDA(ctx, cudaStreamSynchronize(stream));
     if (ch->error) {
         pr->cached = false; // the coefficient buffers no longer belong to pr->alpha

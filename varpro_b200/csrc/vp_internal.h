@@ -140,7 +140,7 @@ struct vp_problem {
     double alpha[VP_MAX_Q] = {0};
     double *alpha_dev = nullptr; // = &fit_dev->st.x_trial[0]: the parameters the next evaluation is made at
     vp::FitDevice *fit_dev = nullptr;  // device-resident LM state
-    vp::FitDevice *fit_host = nullptr; // pinned staging copy
+    vp::FitDevice *fit_host = nullptr; // pinned staging copy (VP_FIT_BLOCK_BYTES: the state and the control word)
     cudaGraph_t fit_graph = nullptr;
     cudaGraphExec_t fit_exec = nullptr;
     cudaGraphConditionalHandle fit_cond = 0;
@@ -234,6 +234,10 @@ inline int vp_tile_lds(int dtype, int ld, int rows, int exact)
     if ((long long)rows * 8 <= (long long)ld * 9) return vp_pad_lds(dtype, rows);
     return -1;
 }
+
+// device / pinned block of a problem's LM state: [FitDevice | FitCtl]
+constexpr size_t VP_FIT_CTL_OFFSET = (sizeof(vp::FitDevice) + 15) / 16 * 16;
+constexpr size_t VP_FIT_BLOCK_BYTES = VP_FIT_CTL_OFFSET + sizeof(vp::FitCtl);
 
 // Row tilings of the DMMA-based kernels: (ksteps, nwarps) covers 4*ksteps*nwarps rows. Better = fewer rows (less
 // padding work), then the unpredicated EXACT variant, then the preferred warp count.

@@ -306,8 +306,7 @@ static int launch_fused_t(vp_problem *pr, int cdst, bool fit_mode)
     if (pr->comm) f.comm = pr->comm->args;
     int lds = pr->fit_lds;
     void *args[] = {(void *)&a, (void *)&lds, (void *)&f};
-    if (fit_mode) {
-        VP_CUDA(ctx, cudaMemsetAsync(pr->fit_ctl, 0, sizeof(FitCtl), stream));
+    if (fit_mode) { // (the caller's copy of the LM state has zeroed the control word behind it)
         VP_CUDA(ctx, cudaLaunchCooperativeKernel(k.fn, dim3(grid), dim3(k.nwarps * 32), args, pr->fit_smem, stream));
     } else {
         VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(grid), dim3(k.nwarps * 32), args, pr->fit_smem, stream));
@@ -515,11 +514,12 @@ static int problem_create_common(vp_ctx *ctx, vp_model *model, int64_t S, const 
     VP_TRY(DEV_ALLOC(ctx, &pr->ticket, sizeof(unsigned int)));
     VP_TRY(cudaMemsetAsync(pr->ticket, 0, sizeof(unsigned int), ctx->stream));
     VP_TRY(DEV_ALLOC(ctx, &pr->out_dev, sizeof(EvalOut)));
-    VP_TRY(DEV_ALLOC(ctx, &pr->fit_dev, sizeof(FitDevice)));
-    VP_TRY(cudaMemsetAsync(pr->fit_dev, 0, sizeof(FitDevice), ctx->stream));
-    VP_TRY(HOST_ALLOC(ctx, &pr->fit_host, sizeof(FitDevice)));
-    VP_TRY(DEV_ALLOC(ctx, &pr->fit_ctl, sizeof(FitCtl)));
-    VP_TRY(cudaMemsetAsync(pr->fit_ctl, 0, sizeof(FitCtl), ctx->stream));
+    // the LM state and, right behind it, the control word of the persistent fit kernel: ONE copy in (which also
+    // zeroes the control word) and ONE copy out per fit
+    VP_TRY(DEV_ALLOC(ctx, &pr->fit_dev, VP_FIT_BLOCK_BYTES));
+    VP_TRY(cudaMemsetAsync(pr->fit_dev, 0, VP_FIT_BLOCK_BYTES, ctx->stream));
+    VP_TRY(HOST_ALLOC(ctx, &pr->fit_host, VP_FIT_BLOCK_BYTES));
+    pr->fit_ctl = reinterpret_cast<FitCtl *>(reinterpret_cast<unsigned char *>(pr->fit_dev) + VP_FIT_CTL_OFFSET);
     pr->alpha_dev = &pr->fit_dev->st.x_trial[0];
     VP_TRY(DEV_ALLOC(ctx, &pr->phi_scratch, sizeof(double) * (size_t)m * md.n));
     VP_TRY(HOST_ALLOC(ctx, &pr->out_host, sizeof(EvalOut)));
@@ -590,7 +590,7 @@ extern "C" int vp_problem_destroy(vp_problem *pr)
     vp_ctx *ctx = pr->ctx;
     DEV_FREE(ctx, pr->Yw); DEV_FREE(ctx, pr->w_dev); DEV_FREE(ctx, pr->Pq); DEV_FREE(ctx, pr->small);
     DEV_FREE(ctx, pr->C[0]); DEV_FREE(ctx, pr->C[1]); DEV_FREE(ctx, pr->partials); DEV_FREE(ctx, pr->ticket);
-    DEV_FREE(ctx, pr->out_dev); DEV_FREE(ctx, pr->fit_dev); DEV_FREE(ctx, pr->phi_scratch); DEV_FREE(ctx, pr->fit_ctl);
+    DEV_FREE(ctx, pr->out_dev); DEV_FREE(ctx, pr->fit_dev); DEV_FREE(ctx, pr->phi_scratch); // (fit_ctl lives inside fit_dev)
     DEV_FREE(ctx, pr->Pq64);
     cudaFree(pr->dbg);
     if (pr->fit_exec) cudaGraphExecDestroy(pr->fit_exec);

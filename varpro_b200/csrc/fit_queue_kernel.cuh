@@ -158,6 +158,10 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
     auto start_evaluation = [&](const int k, const QueueFit *qf, const double (&xi)[RPT], const double (&wi)[RPT], const int cdst) {
         const ModelDesc &md = qf->md;
         const unsigned long long ts0 = dbg_on ? global_timer_ns() : 0ull;
+        // the number of fits still running only sizes the items: requested now with a relaxed load, looked at after
+        // the panel (an L2 round trip off the serial path of the finisher)
+        int active = 1;
+        if (tid == 0) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(active) : "l"(&ctl->fits_left));
         {
             double pa[RPT][NPV], pd0[RPT][P > 0 ? P : 1];
             const int bad = panel_eval_staged<N, P, RPT, THREADS>(md, xi, wi, alpha_s, staging, lds, pa, pd0);
@@ -175,7 +179,6 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
         fence_proxy_async_smem(); // generic writes to the staging area before later bulk copies into it
         if (tid == 0) {
             // items of this evaluation: about items_per_cta items per CTA over the fits still running
-            int active = ld_acquire_gpu_s32(&ctl->fits_left);
             if (active < 1) active = 1;
             const int nparts = qf->part.nparts;
             int want = (qf->items_per_cta * (int)gridDim.x + active - 1) / active;
@@ -187,13 +190,14 @@ fit_queue_kernel(QueueCtl *ctl, QueueFit *fits, const int nfits, const int lds, 
             fits[k].nitems = push_n;
             fits[k].cdst = cdst;
             *qf->ticket = 0u;
+            // reserve the queue slots now: the round trip of the atomic overlaps the fence below (the consumers look
+            // at the slot words, which are written after the fence, not at the tail)
+            push_base = atomicAdd(&ctl->tail, (unsigned long long)push_n);
         }
         __threadfence(); // panel, small outputs, cdst, ticket and (finisher) the stored LM state before the items
         __syncthreads();
         const unsigned long long ts1 = dbg_on ? global_timer_ns() : 0ull;
         if (dbg_on && tid == 0) fin_acc[3] += ts1 - ts0;
-        if (tid == 0) push_base = atomicAdd(&ctl->tail, (unsigned long long)push_n);
-        __syncthreads();
         const int nitems = push_n;
         // publish the items: one st.release per slot (the fence + barrier above ordered everything the consumers
         // will read before these stores)

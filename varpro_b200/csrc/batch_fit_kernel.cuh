@@ -6,12 +6,12 @@
 //   for p in 0..P { LevMarSolver::default().fit(SeparableProblemBuilder::new(model_p).observations(y_p).build()) }
 // (src/problem/builder.rs:116-324, src/solvers/levmar/mod.rs:238-254 per problem).
 //
-// One CTA fits one problem at a time, start to finish, and then takes the next one from a global
-// counter (fits need different numbers of evaluations): y_p is read from HBM ONCE per fit (then L2);
-// per evaluation the CTA
-//   1. regenerates Phi_w(alpha_p), D(alpha_p) from x into a shared-memory working matrix (m x (n+p))
+// One CTA keeps G problems in flight (see below) and takes the next one from a global counter whenever
+// a fit ends (fits need different numbers of evaluations): y_p is read from HBM ONCE per fit (then L2);
+// per evaluation of a problem the compute warps of the CTA
+//   1. regenerate Phi_w(alpha_p), D(alpha_p) from x into a shared-memory working matrix (m x (n+p))
 //      -- materialising Phi for 65 536 problems would take 6.4 GB --
-//   2. runs n Householder steps on [Phi_w | D | y] (y carried along in registers). EVERY ROW OF THE
+//   2. run n Householder steps on [Phi_w | D | y] (y carried along in registers). EVERY ROW OF THE
 //      WORKING SYSTEM BELONGS TO ONE THREAD, so the only thing that crosses threads is the reduction
 //      of the reflector's dot products: the sweep that applies reflector J also accumulates the dots
 //      reflector J + 1 needs, a finished row is saved and then zeroed in place and the padding rows

@@ -5,6 +5,8 @@ import os
 import re
 from fractions import Fraction
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "varpro_b200", "csrc")
 
@@ -22,7 +24,7 @@ def test_device_exp_table_reproduces_exp_to_rounding_level():
     """exp(a) = 2^k (1 + r + r^2 P9(r)), r = a - k ln2 (two-term ln 2): evaluated here in exact rational arithmetic with
     the table of the header, the scheme must agree with exp to a few 1e-17 over the reduced range and beyond -- i.e.
     the coefficients (generated with mpmath) were transcribed correctly; fp64 rounding adds <= 1 ulp on the device."""
-    import mpmath as mp
+    mp = pytest.importorskip("mpmath")
     mp.mp.dps = 50
     c = _exp_constants()
     assert c[0] == 1.4426950408889634 and c[1] == 6755399441055744.0

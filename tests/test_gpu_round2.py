@@ -566,3 +566,54 @@ def test_further_fast_path_shapes_independent_batch(shape):
         assert abs(np.sqrt(2 * res.objective_function[p]) - np.sqrt(2 * r1.minimization_report.objective_function)) <= REL_RNORM * np.linalg.norm(Y[:, p]), p
         gp.close()
     batch.close()
+
+
+def test_batch_kernel_trigonometric_kinds_match_the_single_problem_path():
+    """The O'Leary / MATLAB model (two e^{-a x} cos(b x) functions sharing parameters, shape (n, p) = (2, 4), weighted;
+    shared_test_code/src/models.rs:321-385) and the SinPhase + LinearX + Constant model as independent batches: the
+    batch kernel's evaluator for the two-parameter kinds (sincos path) against one vp_fit per problem."""
+    import varpro_b200 as vb
+    from test_gpu_parity import _batch_model
+    rng = np.random.default_rng(77)
+    # (a) O'Leary: perturbed copies of the reference data set, same start
+    wl = W.oleary()
+    P = 7
+    y0 = wl["Y"][:, 0]
+    Y = np.asfortranarray(y0[:, None] * (1.0 + 0.01 * rng.standard_normal((y0.shape[0], P))))
+    Y[:, 0] = y0
+    a0 = np.tile(np.array(wl["alpha0"]), (P, 1))
+    model = _batch_model(wl, y0.shape[0])
+    batch = vb.IndependentBatch(model, Y, a0, weights=wl["weights"])
+    res = batch.fit()
+    for p in range(P):
+        one = dict(x=wl["x"], Y=np.asfortranarray(Y[:, p:p + 1]), basis=wl["basis"], q=3, alpha0=list(wl["alpha0"]), weights=wl["weights"])
+        gp = W.make_gpu_problem(one)
+        r1 = vb.LevMarSolver.default().fit(gp)
+        assert bool(res.successful[p]) == r1.was_successful(), p
+        assert np.max(np.abs(res.nonlinear_parameters[p] - r1.nonlinear_parameters()) / np.abs(r1.nonlinear_parameters())) <= 1e-7, p
+        assert abs(np.sqrt(2 * res.objective_function[p]) - np.sqrt(2 * r1.minimization_report.objective_function)) \
+            <= REL_RNORM * np.linalg.norm(wl["weights"] * Y[:, p]), p
+        gp.close()
+    batch.close()
+    # (b) sin(omega x + phi) + 0.5 x + 1
+    m, P = 257, 6
+    x = np.linspace(0.0, 6.0, m)
+    Yb = np.empty((m, P))
+    for p in range(P):
+        om, ph = 1.7 * rng.uniform(0.97, 1.03), 0.4 * rng.uniform(0.9, 1.1)
+        Yb[:, p] = np.stack([np.sin(om * x + ph), 0.5 * x, np.ones_like(x)], axis=1) @ rng.uniform(0.5, 3.0, size=3) + 1e-3 * rng.standard_normal(m)
+    Yb = np.asfortranarray(Yb)
+    names = ["p0", "p1"]
+    model = (vb.SeparableModelBuilder(names).function(["p0", "p1"], vb.SinPhase()).invariant_function(vb.LinearX(0.5))
+             .invariant_function(vb.Constant()).independent_variable(x).initial_parameters([1.6, 0.6]).build())
+    batch = vb.IndependentBatch(model, Yb, np.tile(np.array([1.6, 0.6]), (P, 1)))
+    res = batch.fit()
+    assert res.successful.all(), res.terminations
+    for p in range(P):
+        one = dict(x=x, Y=np.asfortranarray(Yb[:, p:p + 1]), basis=SIN_LINEAR, q=2, alpha0=[1.6, 0.6], weights=None)
+        gp = _make_gpu(one)
+        r1 = vb.LevMarSolver.default().fit(gp)
+        assert np.max(np.abs(res.nonlinear_parameters[p] - r1.nonlinear_parameters()) / np.abs(r1.nonlinear_parameters())) <= 1e-7, p
+        assert abs(np.sqrt(2 * res.objective_function[p]) - np.sqrt(2 * r1.minimization_report.objective_function)) <= REL_RNORM * np.linalg.norm(Yb[:, p]), p
+        gp.close()
+    batch.close()

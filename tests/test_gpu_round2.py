@@ -617,3 +617,38 @@ def test_batch_kernel_trigonometric_kinds_match_the_single_problem_path():
         assert abs(np.sqrt(2 * res.objective_function[p]) - np.sqrt(2 * r1.minimization_report.objective_function)) <= REL_RNORM * np.linalg.norm(Yb[:, p]), p
         gp.close()
     batch.close()
+
+
+def test_batch_kernel_degenerate_starts_fail_alone():
+    """A NaN, a zero and a negative decay time as starting points inside a batch: those problems end unsuccessfully (as
+    their single-problem fits do), the others are untouched -- bitwise the results of the same batch without them."""
+    import varpro_b200 as vb
+    from test_gpu_parity import _batch_model
+    wl = W.triple_exp_batch(P=10, m=300, seed=99)
+    a0 = wl["alpha0"].copy()
+    a0[2] = [np.nan, 3.0, 9.0]
+    a0[5] = [0.0, 3.0, 9.0]
+    a0[7] = [1.0, -1e-3, 9.0]
+    model = _batch_model(wl, 300)
+    batch = vb.IndependentBatch(model, wl["Y"], a0)
+    res = batch.fit()
+    good = [p for p in range(10) if p not in (2, 5, 7)]
+    assert not res.successful[2] and not res.successful[5]
+    for p in (2, 5, 7):
+        one = dict(x=wl["x"], Y=np.asfortranarray(wl["Y"][:, p:p + 1]), basis=wl["basis"], q=3, alpha0=list(a0[p]), weights=None)
+        try:
+            gp = W.make_gpu_problem(one)
+            r1 = vb.LevMarSolver.default().fit(gp)
+            ok1 = r1.was_successful()
+            gp.close()
+        except vb.VarproError:
+            ok1 = False  # the builder's first evaluation already failed
+        assert bool(res.successful[p]) == bool(ok1), p
+    ref = vb.IndependentBatch(model, np.asfortranarray(wl["Y"][:, good]), a0[good])
+    rr = ref.fit()
+    assert rr.successful.all()
+    for i, p in enumerate(good):
+        assert np.array_equal(res.nonlinear_parameters[p], rr.nonlinear_parameters[i]), p
+        assert res.number_of_evaluations[p] == rr.number_of_evaluations[i]
+    batch.close()
+    ref.close()

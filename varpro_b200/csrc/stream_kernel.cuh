@@ -516,68 +516,114 @@ stream_kernel(const StreamArgs<T> a)
 }
 
 // -----------------------------------------------------------------------------
-// Generic fallback (any n <= VP_MAX_N, p <= VP_MAX_P, any m): one warp per
-// column, panel read through L1/L2, y read twice (second read hits L1). Same
-// outputs and partial layout as the fast kernel. Correctness path for shapes
-// the register-panel kernel is not instantiated for; not tuned.
+// Generic fallback (any n <= VP_MAX_N, p <= VP_MAX_P, any m): the streaming pass for model shapes without a
+// specialised kernel. One persistent CTA per SM keeps the panel [Q | E] in shared memory (staged once per launch;
+// read from global memory through L1/L2 if it does not fit); every warp takes TWO columns at a time, so each
+// panel entry read from shared memory serves two right-hand sides; y is read twice (the second time from L2).
+// NB = compile-time bound of n + p (8 / 12 / 20: the accumulators are registers with static indices).
+// Per-warp accumulators in shared memory, folded over the warps in order: no floating-point atomics, the result
+// is reproducible. Same outputs and partial layout as the specialised kernels.
 // -----------------------------------------------------------------------------
-template <typename T, int THREADS>
+template <typename T, int THREADS, int NB>
 __global__ void __launch_bounds__(THREADS)
-stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m)
+stream_kernel_generic(const StreamArgs<T> a, int n, int p, int m, int mp /* row stride of the staged panel, 0 = not staged */)
 {
     constexpr int NW = THREADS / 32;
     constexpr int NVMAX = 1 + VP_MAX_N * (VP_MAX_N + 1) / 2 + VP_MAX_P;
+    extern __shared__ __align__(16) double pan_s[]; // (n + p) columns of mp doubles
     __shared__ double acc_s[NVMAX];
+    __shared__ double wacc_s[NW][NVMAX];
     __shared__ double rinv_s[VP_MAX_N * VP_MAX_N];
     __shared__ double fin_scratch[FIN_SCRATCH];
     __shared__ double fin_sh[64];
     __shared__ int is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ld = a.ld;
+    const int ld = a.ld, npv = n + p;
+    const int nv = red_count(n, p);
     T *Cout = stream_cout(a);
-    for (int t = tid; t < NVMAX; t += THREADS) acc_s[t] = 0.0;
+    for (int t = tid; t < NW * NVMAX; t += THREADS) (&wacc_s[0][0])[t] = 0.0;
     for (int t = tid; t < VP_MAX_N * VP_MAX_N; t += THREADS) rinv_s[t] = a.small->Rinv[t];
+    const bool staged = mp > 0;
+    if (staged)
+        for (int idx = tid; idx < npv * mp; idx += THREADS) {
+            const int k = idx / mp, i = idx - k * mp;
+            pan_s[idx] = i < m ? (double)a.Pq[(size_t)k * a.ldp + i] : 0.0; // (Pe = Pq + n * ldp: the columns are contiguous)
+        }
     __syncthreads();
+    auto pan = [&](const int k, const int i) -> double {
+        return staged ? pan_s[k * mp + i] : (double)a.Pq[(size_t)k * a.ldp + i];
+    };
 
-    for (int s = blockIdx.x * NW + warp; s < a.S; s += gridDim.x * NW) {
-        const T *y = a.Y + (size_t)s * ld;
-        double d[VP_MAX_N + VP_MAX_P];
+    double *wacc = wacc_s[warp];
+    for (long long s0 = 2ll * ((long long)blockIdx.x * NW + warp); s0 < a.S; s0 += 2ll * gridDim.x * NW) {
+        const bool two = s0 + 1 < a.S;
+        const T *y0 = a.Y + (size_t)s0 * ld, *y1 = a.Y + (size_t)(two ? s0 + 1 : s0) * ld;
+        double d0[NB], d1[NB];
 #pragma unroll
-        for (int k = 0; k < VP_MAX_N + VP_MAX_P; ++k) d[k] = 0.0;
+        for (int k = 0; k < NB; ++k) d0[k] = d1[k] = 0.0;
+#pragma unroll 4 // (eight observation loads in flight per lane: the pass is latency-bound otherwise)
         for (int i = lane; i < m; i += 32) {
-            const double yi = (double)y[i];
+            const double v0 = (double)y0[i], v1 = (double)y1[i];
 #pragma unroll
-            for (int k = 0; k < VP_MAX_N; ++k)
-                if (k < n) d[k] += (double)a.Pq[(size_t)k * a.ldp + i] * yi;
-#pragma unroll
-            for (int e = 0; e < VP_MAX_P; ++e)
-                if (e < p) d[VP_MAX_N + e] += (double)a.Pe[(size_t)e * a.ldp + i] * yi;
+            for (int k = 0; k < NB; ++k)
+                if (k < npv) {
+                    const double pk = pan(k, i);
+                    d0[k] = fma(pk, v0, d0[k]);
+                    d1[k] = fma(pk, v1, d1[k]);
+                }
         }
 #pragma unroll
-        for (int k = 0; k < VP_MAX_N + VP_MAX_P; ++k) d[k] = warp_sum(d[k]);
-        double rs = 0.0;
+        for (int k = 0; k < NB; ++k)
+            if (k < npv) { d0[k] = warp_sum(d0[k]); d1[k] = warp_sum(d1[k]); }
+        double rs0 = 0.0, rs1 = 0.0;
+#pragma unroll 4
         for (int i = lane; i < m; i += 32) {
-            double r = (double)y[i];
+            double r0 = (double)y0[i], r1 = (double)y1[i];
 #pragma unroll
-            for (int k = 0; k < VP_MAX_N; ++k)
-                if (k < n) r -= (double)a.Pq[(size_t)k * a.ldp + i] * d[k];
-            rs += r * r;
+            for (int k = 0; k < NB; ++k)
+                if (k < n) {
+                    const double pk = pan(k, i);
+                    r0 = fma(-pk, d0[k], r0);
+                    r1 = fma(-pk, d1[k], r1);
+                }
+            rs0 = fma(r0, r0, rs0);
+            rs1 = fma(r1, r1, rs1);
         }
-        rs = warp_sum(rs);
+        rs0 = warp_sum(rs0);
+        rs1 = warp_sum(rs1);
         if (lane == 0) {
-            double coef[VP_MAX_N];
-            for (int r = 0; r < n; ++r) {
-                double sacc = 0.0;
-                for (int c2 = 0; c2 < n; ++c2) sacc += rinv_s[c2 * VP_MAX_N + r] * d[c2];
-                coef[r] = sacc;
-                Cout[(size_t)s * n + r] = (T)sacc;
+#pragma unroll 1
+            for (int c = 0; c < (two ? 2 : 1); ++c) {
+                double coef[VP_MAX_N], dd[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) dd[k] = c ? d1[k] : d0[k];
+                for (int r = 0; r < n; ++r) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int c2 = 0; c2 < VP_MAX_N; ++c2)
+                        if (c2 < n && c2 < NB) sacc += rinv_s[c2 * VP_MAX_N + r] * dd[c2];
+                    coef[r] = sacc;
+                    Cout[(size_t)(s0 + c) * n + r] = (T)sacc;
+                }
+                wacc[0] += c ? rs1 : rs0;
+                for (int r = 0; r < n; ++r)
+                    for (int c2 = r; c2 < n; ++c2) wacc[g_index(n, r, c2)] += coef[r] * coef[c2];
+#pragma unroll
+                for (int e = 0; e < VP_MAX_P; ++e)
+                    if (e < p && n + e < NB) {
+                        double de = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NB; ++k) de = (k == n + e) ? dd[k] : de;
+                        wacc[1 + n * (n + 1) / 2 + e] += coef[a.e_basis[e]] * de;
+                    }
             }
-            atomicAdd(&acc_s[0], rs);
-            for (int r = 0; r < n; ++r)
-                for (int c2 = r; c2 < n; ++c2) atomicAdd(&acc_s[g_index(n, r, c2)], coef[r] * coef[c2]);
-            for (int e = 0; e < p; ++e)
-                atomicAdd(&acc_s[1 + n * (n + 1) / 2 + e], coef[a.e_basis[e]] * d[VP_MAX_N + e]);
         }
+    }
+    __syncthreads();
+    if (tid < nv) { // fold the warps' accumulators in order
+        double t = 0.0;
+        for (int w = 0; w < NW; ++w) t += wacc_s[w][tid];
+        acc_s[tid] = t;
     }
     __syncthreads();
     stream_epilogue<T>(a, n, p, acc_s, fin_sh, fin_scratch, &is_last);

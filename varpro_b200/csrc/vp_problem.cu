@@ -6,6 +6,8 @@
 
 using namespace vp;
 
+constexpr int GENERIC_THREADS = 512; // stream_kernel_generic
+
 // the fused evaluation / persistent fit kernel (fit_kernel_dmma<TY>) for this problem, if instantiated for its shape
 static int plan_fit_kernel(vp_problem *pr)
 {
@@ -180,15 +182,22 @@ static int plan_stream(vp_problem *pr)
             }
         }
     }
-    // generic fallback: one warp per column
+    // generic fallback (stream_kernel_generic): one persistent CTA per SM, every warp two columns at a time, the panel
+    // staged in shared memory when (n + p) * m doubles fit next to the kernel's static shared memory
     pr->plan_kind = -1;
-    long long grid = (pr->S + 7) / 8;
-    const long long cap = (long long)ctx->sm_count * 8;
-    pr->plan_grid = (int)(grid < cap ? grid : cap);
-    pr->plan_nst = 0;
-    pr->plan_smem = 0;
-    pr->plan_rows = mo->ld;
-    pr->plan_ct = 1;
+    {
+        long long grid = (pr->S + 2 * (GENERIC_THREADS / 32) - 1) / (2 * (GENERIC_THREADS / 32));
+        if (grid > ctx->sm_count) grid = ctx->sm_count;
+        if (ctx->opt.max_ctas > 0 && grid > ctx->opt.max_ctas) grid = ctx->opt.max_ctas;
+        if (grid > pr->max_grid) grid = pr->max_grid;
+        pr->plan_grid = (int)(grid < 1 ? 1 : grid);
+        const int mp = (md.m + 1) / 2 * 2;
+        const size_t panel_bytes = sizeof(double) * (size_t)(md.n + md.p) * mp;
+        pr->plan_nst = 0;
+        pr->plan_smem = panel_bytes + 24 * 1024 <= ctx->smem_optin ? panel_bytes : 0; // (24 KB: static shared memory of the kernel)
+        pr->plan_rows = mo->ld;
+        pr->plan_ct = 1;
+    }
     return VP_OK;
 }
 
@@ -263,7 +272,15 @@ static int launch_stream_t(vp_problem *pr, int cdst, bool graph_mode)
         void *args[] = {(void *)&a};
         VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(pr->plan_grid), dim3(k.threads), args, pr->plan_smem, ctx->stream));
     } else {
-        stream_kernel_generic<T, 256><<<pr->plan_grid, 256, 0, ctx->stream>>>(a, md.n, md.p, md.m);
+        // generic shape: panel staged in shared memory when it fits (plan_smem from the launch plan)
+        const int npv = md.n + md.p;
+        const void *fn = npv <= 8 ? (const void *)stream_kernel_generic<T, GENERIC_THREADS, 8>
+                                  : (npv <= 12 ? (const void *)stream_kernel_generic<T, GENERIC_THREADS, 12>
+                                               : (const void *)stream_kernel_generic<T, GENERIC_THREADS, 20>);
+        int n_arg = md.n, p_arg = md.p, m_arg = md.m, mp_arg = pr->plan_smem > 0 ? (md.m + 1) / 2 * 2 : 0;
+        if (pr->plan_smem > 0) VP_CUDA(ctx, vp_ensure_dynamic_smem(ctx->device, fn, pr->plan_smem)); // (static + dynamic may exceed 48 KB)
+        void *args[] = {(void *)&a, (void *)&n_arg, (void *)&p_arg, (void *)&m_arg, (void *)&mp_arg};
+        VP_CUDA(ctx, cudaLaunchKernel(fn, dim3(pr->plan_grid), dim3(GENERIC_THREADS), args, pr->plan_smem, ctx->stream));
     }
     ctx->launches++;
     VP_CUDA(ctx, cudaGetLastError());

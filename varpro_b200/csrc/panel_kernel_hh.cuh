@@ -458,11 +458,13 @@ __device__ __forceinline__ void panel_hh_body(const ModelDesc &md, const double 
     panel_hh_factor<T, N, P, RPT, THREADS>(md, a, d0, bad, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg, svd_s);
 }
 
+// pre != nullptr: host-evaluated model -- the unweighted [Phi | D] (m x (n+p), f64, column-major) was uploaded and
+// takes the place of the device basis evaluation (vp_model_create_hosteval).
 template <typename T, int N, int P, int RPT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
                 const double *__restrict__ alpha_dev, double svd_eps, int ldp, T *__restrict__ Pq,
-                PanelSmall *__restrict__ small, unsigned long long *dbg)
+                PanelSmall *__restrict__ small, unsigned long long *dbg, const double *__restrict__ pre)
 {
     constexpr int NPV = N + P;
     constexpr int NW = THREADS / 32;
@@ -483,6 +485,26 @@ panel_kernel_hh(ModelDesc md, const T *__restrict__ x, const T *__restrict__ w,
         wi[r] = in ? (w ? (double)w[i] : 1.0) : 0.0;
     }
     __syncthreads();
+    if (pre) {
+        double a[RPT][NPV];
+        double d0[RPT][P > 0 ? P : 1];
+        int bad = 0;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int i = tid + r * THREADS;
+            const bool in = i < md.m;
+#pragma unroll
+            for (int k = 0; k < NPV; ++k) {
+                const double v = in ? wi[r] * pre[(size_t)k * md.m + i] : 0.0;
+                if (k < N) bad |= (!isfinite(v) ? 1 : 0) | (fabs(v) > RANK_HUGE_ENTRY ? (2 << k) : 0); // flag word of rank_policy.cuh
+                a[r][k] = v;
+            }
+#pragma unroll
+            for (int e = 0; e < P; ++e) d0[r][e] = a[r][N + e];
+        }
+        panel_hh_factor<T, N, P, RPT, THREADS>(md, a, d0, bad, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg, &svd_s);
+        return;
+    }
     panel_hh_body<T, N, P, RPT, THREADS>(md, xi, wi, alpha_s, svd_eps, ldp, Pq, small, red, top, dbg, &svd_s);
 }
 

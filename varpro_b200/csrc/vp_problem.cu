@@ -209,7 +209,7 @@ static int launch_panel_t(vp_problem *pr)
     const ModelDesc &md = mo->md;
     unsigned long long *dbg = pr->dbg ? pr->dbg + (size_t)pr->max_grid * VP_DBG_SLOTS : nullptr;
     // fast path: register-resident Householder panel
-    if (!ctx->opt.panel_generic && !mo->hosteval) {
+    if (!ctx->opt.panel_generic) { // (host-evaluated models too: their uploaded [Phi | D] replaces the basis evaluation)
         for (const PanelHHEntry &k : vp_kernel_tables().panel) {
             if (k.dtype != mo->dtype || k.n != md.n || k.p != md.p || (long long)k.rpt * k.threads < md.m) continue;
             ModelDesc mdc = md;
@@ -219,7 +219,8 @@ static int launch_panel_t(vp_problem *pr)
             int ldp = pr->ldp;
             void *pq = pr->Pq;
             PanelSmall *sm = pr->small;
-            void *args[] = {&mdc, &xp, &wp, &ap, &eps, &ldp, &pq, &sm, &dbg};
+            const double *pre = mo->hosteval ? mo->pre_dev : nullptr;
+            void *args[] = {&mdc, &xp, &wp, &ap, &eps, &ldp, &pq, &sm, &dbg, &pre};
             VP_CUDA(ctx, cudaLaunchKernel(k.fn, dim3(1), dim3(k.threads), args, 0, ctx->stream));
             ctx->launches++;
             return VP_OK;

@@ -497,15 +497,14 @@ _SHAPES = {
 
 
 @pytest.mark.parametrize("shape", sorted(_SHAPES))
-@pytest.mark.parametrize("S", [1, 37])
-def test_further_fast_path_shapes_state_fit_and_fit_many(shape, S):
+@pytest.mark.parametrize("S,m", [(1, 600), (37, 600), (5, 90), (21, 300)])  # m = 90 / 300: the 128- and 512-row tilings
+def test_further_fast_path_shapes_state_fit_and_fit_many(shape, S, m):
     """One exponential + offset, two exponentials, three exponentials + offset: state and fit parity with the oracle
     on the persistent kernel, vp_fit_many bitwise equal to vp_fit on the work-queue kernel, and the launch counter
     shows ONE launch per fit (the generic path would need one graph replay per evaluation)."""
     import varpro_b200 as vb
     sp = _SHAPES[shape]
     rng = np.random.default_rng(len(shape) + S)
-    m = 600
     x = np.linspace(0.0, 25.0, m)
     n = len(sp["basis"])
     cols = [np.exp(-x / t) for t in sp["tau"]] + ([np.ones_like(x)] if n > len(sp["tau"]) else [])

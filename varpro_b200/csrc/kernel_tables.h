@@ -69,11 +69,13 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_3_3_panel, double, VP_F64, 3, 3, 2) \
     X(f64_3_3_fit0, double, VP_F64, 3, 3, 3) \
     X(f64_3_3_fit1, double, VP_F64, 3, 3, 3) \
+    X(f64_3_3_queue0, double, VP_F64, 3, 3, 5) /* the small row tilings, like fit0: vp_fit_many stays bitwise vp_fit at every m */ \
     X(f64_3_3_queue1, double, VP_F64, 3, 3, 5) \
     X(f64_2_4_dmma, double, VP_F64, 2, 4, 1) \
     X(f64_2_4_panel, double, VP_F64, 2, 4, 2) \
     X(f64_2_4_fit0, double, VP_F64, 2, 4, 3) \
     X(f64_2_4_fit1, double, VP_F64, 2, 4, 3) \
+    X(f64_2_4_queue0, double, VP_F64, 2, 4, 5) /* the small row tilings, like fit0: vp_fit_many stays bitwise vp_fit at every m */ \
     X(f64_2_4_queue1, double, VP_F64, 2, 4, 5) \
     X(f64_3_3_batch, double, VP_F64, 3, 3, 4) \
     X(f64_3_2_batch, double, VP_F64, 3, 2, 4) \
@@ -82,18 +84,21 @@ typedef const KernelGroup *(*KernelGroupFn)();
     X(f64_2_1_panel, double, VP_F64, 2, 1, 2) \
     X(f64_2_1_fit0, double, VP_F64, 2, 1, 3) \
     X(f64_2_1_fit1, double, VP_F64, 2, 1, 3) \
+    X(f64_2_1_queue0, double, VP_F64, 2, 1, 5) /* the small row tilings, like fit0: vp_fit_many stays bitwise vp_fit at every m */ \
     X(f64_2_1_queue1, double, VP_F64, 2, 1, 5) \
     X(f64_2_1_batch, double, VP_F64, 2, 1, 4) \
     X(f64_2_2_dmma, double, VP_F64, 2, 2, 1) /* double exponential without offset */ \
     X(f64_2_2_panel, double, VP_F64, 2, 2, 2) \
     X(f64_2_2_fit0, double, VP_F64, 2, 2, 3) \
     X(f64_2_2_fit1, double, VP_F64, 2, 2, 3) \
+    X(f64_2_2_queue0, double, VP_F64, 2, 2, 5) /* the small row tilings, like fit0: vp_fit_many stays bitwise vp_fit at every m */ \
     X(f64_2_2_queue1, double, VP_F64, 2, 2, 5) \
     X(f64_2_2_batch, double, VP_F64, 2, 2, 4) \
     X(f64_4_3_dmma, double, VP_F64, 4, 3, 1) /* triple exponential + offset */ \
     X(f64_4_3_panel, double, VP_F64, 4, 3, 2) \
     X(f64_4_3_fit0, double, VP_F64, 4, 3, 3) \
     X(f64_4_3_fit1, double, VP_F64, 4, 3, 3) \
+    X(f64_4_3_queue0, double, VP_F64, 4, 3, 5) /* the small row tilings, like fit0: vp_fit_many stays bitwise vp_fit at every m */ \
     X(f64_4_3_queue1, double, VP_F64, 4, 3, 5) \
     X(f64_4_3_batch, double, VP_F64, 4, 3, 4)
 
